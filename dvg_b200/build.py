@@ -1,0 +1,76 @@
+"""Build recipe for libdvg_b200.so (nvcc, sm_100a only, in-tree so it travels with gpurun snapshots)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB_DIR = os.path.join(PKG, "_lib")
+LIB = os.path.join(LIB_DIR, "libdvg_b200.so")
+SOURCES = ["capi.cu", "lstm_fp32.cu", "lstm_tc.cu", "gp.cu"]
+HEADERS = ["common.cuh", "internal.cuh", "ptx.cuh", os.path.join("..", "..", "include", "dvg_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-Xptxas", "-v", "-cudart", "static",
+]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found; dvg_b200 needs the CUDA toolkit to build its kernels")
+
+
+def source_hash() -> str:
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def is_current() -> bool:
+    stamp = LIB + ".hash"
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == source_hash()
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    """Compile every .cu for sm_100a into dvg_b200/_lib/libdvg_b200.so (object files compiled in parallel)."""
+    if not force and is_current():
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src}\n{out}")
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", LIB, *objs]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    with open(os.path.join(LIB_DIR, "build.log"), "w") as fh:
+        fh.write("\n".join(log))
+    with open(LIB + ".hash", "w") as fh:
+        fh.write(source_hash())
+    if verbose:
+        print(f"built {LIB}")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,450 @@
+// Variational-GP predictive, variance trigger and rsample for the DVG rollout (fp32 CUDA-core kernels
+// with shared-memory staging; factor preparation in fp64).
+//
+// Replaces gp_layer(x) / likelihood(...) of models/gp_models.py:10-24 (gpytorch WhitenedVariationalStrategy
+// eval branch + GaussianLikelihood), the host-side trigger arithmetic of generate_frames.py:227-232,275,
+// 283-289 and .rsample() of generate_frames.py:171,292 / train.py:284.
+//
+// Per latent dimension d (x = column d of the [N,D] latent):
+//   k_m   = s exp(-0.5 ((x - z_m)/ell)^2)                         (M exps)
+//   mean  = c + sum_m alpha_m k_m                                  alpha = K_ZZ^-1 (m_q - c)       [hoisted]
+//   v     = L_ZZ^-1 k          (triangular mat-vec with the explicit inverse Linv)                 [Linv hoisted]
+//   w     = L_q^T k
+//   var   = s - |v|^2 + |w|^2 + noise
+// K_ZZ, its Cholesky factor, Linv and alpha are constant in eval mode; the reference recomputes them on
+// every call, here gp_prepare_kernel builds them once per weight load in fp64.
+#include "internal.cuh"
+
+namespace dvg {
+
+// ---------------------------------------------------------------------------------------------------
+// prepare: one CTA per latent dimension, fp64, M <= 160 (K_ZZ / L in dynamic shared memory)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double softplus_d(double x) { return x > 30.0 ? x : log1p(exp(x)); }
+
+__global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, int mp, double jitter, double noise_lb,
+                                                         const float* __restrict__ inducing,
+                                                         const float* __restrict__ var_mean,
+                                                         const float* __restrict__ chol_var,
+                                                         const float* __restrict__ mean_const,
+                                                         const float* __restrict__ raw_os,
+                                                         const float* __restrict__ raw_ls,
+                                                         const float* __restrict__ raw_noise, float* __restrict__ z_out,
+                                                         float* __restrict__ linv_out, float* __restrict__ lqt_out,
+                                                         float* __restrict__ alpha_out, float* __restrict__ hyp_out,
+                                                         double* __restrict__ work) {
+  extern __shared__ double sm[];
+  const int d = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int ld = M + 1;
+  double* A = sm;              // [M][M+1]  K_ZZ -> L (lower)
+  double* zs = A + M * ld;     // [M]
+  double* tv = zs + M;         // [M]
+  double* X = work + (size_t)d * M * M;  // [M][M] Linv in fp64 (row-major, column c owned by thread c)
+
+  const double ell = softplus_d((double)raw_ls[d]);
+  const double s = softplus_d((double)raw_os[d]);
+  const double c = (double)mean_const[d];
+  const double noise = softplus_d((double)raw_noise[d]) + noise_lb;
+  if (tid == 0) {
+    hyp_out[d * 4 + 0] = (float)ell;
+    hyp_out[d * 4 + 1] = (float)s;
+    hyp_out[d * 4 + 2] = (float)c;
+    hyp_out[d * 4 + 3] = (float)noise;
+  }
+  for (int m = tid; m < mp; m += nt) {
+    const float zf = m < M ? inducing[(size_t)d * M + m] : 0.f;
+    if (m < M) zs[m] = (double)zf;
+    z_out[(size_t)d * mp + m] = zf;
+  }
+  __syncthreads();
+  for (int e = tid; e < M * M; e += nt) {
+    const int i = e / M, j = e % M;
+    const double t = (zs[i] - zs[j]) / ell;
+    A[i * ld + j] = s * exp(-0.5 * t * t) + (i == j ? jitter : 0.0);
+  }
+  __syncthreads();
+  // left-looking Cholesky, column by column
+  for (int j = 0; j < M; ++j) {
+    double sum = 0.0;
+    const int i = j + tid;  // rows j.. handled by threads (loop if M - j > nt)
+    for (int ii = i; ii < M; ii += nt) {
+      sum = A[ii * ld + j];
+      for (int k = 0; k < j; ++k) sum -= A[ii * ld + k] * A[j * ld + k];
+      tv[ii] = sum;
+    }
+    __syncthreads();
+    const double diag = sqrt(tv[j]);
+    for (int ii = i; ii < M; ii += nt) A[ii * ld + j] = (ii == j) ? diag : tv[ii] / diag;
+    __syncthreads();
+  }
+  // X = L^-1 by forward substitution, one column per thread
+  for (int col = tid; col < M; col += nt) {
+    for (int i = 0; i < M; ++i) {
+      double v = 0.0;
+      if (i >= col) {
+        v = (i == col) ? 1.0 : 0.0;
+        for (int k = col; k < i; ++k) v -= A[i * ld + k] * X[(size_t)k * M + col];
+        v /= A[i * ld + i];
+      }
+      X[(size_t)i * M + col] = v;
+    }
+  }
+  __syncthreads();
+  // alpha = L^-T (L^-1 (m_q - c))
+  for (int i = tid; i < M; i += nt) {
+    double t = 0.0;
+    for (int k = 0; k <= i; ++k) t += X[(size_t)i * M + k] * ((double)var_mean[(size_t)d * M + k] - c);
+    tv[i] = t;
+  }
+  __syncthreads();
+  for (int j = tid; j < mp; j += nt) {
+    double a = 0.0;
+    if (j < M)
+      for (int i = j; i < M; ++i) a += X[(size_t)i * M + j] * tv[i];
+    alpha_out[(size_t)d * mp + j] = (float)a;
+  }
+  // fp32 outputs: Linv (lower) and L_q^T (upper), zero padded to mp
+  for (int e = tid; e < mp * mp; e += nt) {
+    const int r = e / mp, q = e % mp;
+    float lv = 0.f, qv = 0.f;
+    if (r < M && q < M) {
+      if (q <= r) lv = (float)X[(size_t)r * M + q];
+      if (q >= r) qv = chol_var[((size_t)d * M + q) * M + r];  // lqt[r][q] = L_q[q][r], q >= r
+    }
+    linv_out[((size_t)d * mp + r) * mp + q] = lv;
+    lqt_out[((size_t)d * mp + r) * mp + q] = qv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// predictive mean / variance: grid (row tiles, D), 128 threads = 128 rows, one latent dim per CTA.
+// Linv and L_q^T of that dim are staged in shared memory and read as warp-broadcast float4; the kernel
+// row k[] of each thread lives in registers (MREG = padded M known at compile time) or shared memory.
+// ---------------------------------------------------------------------------------------------------
+template <int MREG>
+__global__ void __launch_bounds__(128) gp_predict_kernel(int n_rows, int D, int mp, const float* __restrict__ x, int ldx,
+                                                         const int32_t* __restrict__ row_index,
+                                                         const float* __restrict__ zall,
+                                                         const float* __restrict__ linv_all,
+                                                         const float* __restrict__ lqt_all,
+                                                         const float* __restrict__ alpha_all,
+                                                         const float* __restrict__ hyp, float* __restrict__ mean,
+                                                         int ldm, float* __restrict__ var, int ldv) {
+  extern __shared__ __align__(16) float smf[];
+  const int d = blockIdx.y, tid = threadIdx.x;
+  const int MP = MREG > 0 ? MREG : mp;
+  float* s_linv = smf;                  // [MP][MP]
+  float* s_lqt = s_linv + MP * MP;      // [MP][MP]
+  float* s_z = s_lqt + MP * MP;         // [MP]
+  float* s_alpha = s_z + MP;            // [MP]
+  float* s_k = s_alpha + MP;            // [MP][128] (generic path only)
+  {
+    const float4* g1 = reinterpret_cast<const float4*>(linv_all + (size_t)d * MP * MP);
+    const float4* g2 = reinterpret_cast<const float4*>(lqt_all + (size_t)d * MP * MP);
+    for (int e = tid; e < MP * MP / 4; e += 128) {
+      reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
+      reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
+    }
+    for (int e = tid; e < MP; e += 128) {
+      s_z[e] = zall[(size_t)d * MP + e];
+      s_alpha[e] = alpha_all[(size_t)d * MP + e];
+    }
+  }
+  __syncthreads();
+  const float ell = hyp[d * 4 + 0], s = hyp[d * 4 + 1], c = hyp[d * 4 + 2], noise = hyp[d * 4 + 3];
+  const int i = blockIdx.x * 128 + tid;
+  if (i >= n_rows) return;
+  const int row = row_index ? row_index[i] : i;
+  const float xv = __ldg(x + (size_t)row * ldx + d);
+  const float inv_ell = 1.0f / ell;
+
+  float mu = 0.f, vv = 0.f, ww = 0.f;
+  if (MREG > 0) {
+    float k[MREG > 0 ? MREG : 1];
+#pragma unroll
+    for (int m = 0; m < MREG; ++m) {
+      const float t = (xv - s_z[m]) * inv_ell;
+      k[m] = s * expf(-0.5f * t * t);   // padded z entries are multiplied by zero factors below
+      mu = fmaf(s_alpha[m], k[m], mu);
+    }
+#pragma unroll
+    for (int j = 0; j < MREG; ++j) {
+      float v = 0.f, w = 0.f;
+      const int jm = (j / 4) * 4;
+#pragma unroll
+      for (int m = 0; m <= jm; m += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(s_linv + j * MREG + m);
+        v = fmaf(l4.x, k[m], v); v = fmaf(l4.y, k[m + 1], v); v = fmaf(l4.z, k[m + 2], v); v = fmaf(l4.w, k[m + 3], v);
+      }
+#pragma unroll
+      for (int m = jm; m < MREG; m += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(s_lqt + j * MREG + m);
+        w = fmaf(q4.x, k[m], w); w = fmaf(q4.y, k[m + 1], w); w = fmaf(q4.z, k[m + 2], w); w = fmaf(q4.w, k[m + 3], w);
+      }
+      vv = fmaf(v, v, vv);
+      ww = fmaf(w, w, ww);
+    }
+  } else {
+    for (int m = 0; m < MP; ++m) {
+      const float t = (xv - s_z[m]) * inv_ell;
+      const float km = s * expf(-0.5f * t * t);
+      s_k[m * 128 + tid] = km;
+      mu = fmaf(s_alpha[m], km, mu);
+    }
+    for (int j = 0; j < MP; ++j) {
+      float v = 0.f, w = 0.f;
+      const int jm = (j / 4) * 4;
+      for (int m = 0; m <= jm; m += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(s_linv + j * MP + m);
+        v = fmaf(l4.x, s_k[m * 128 + tid], v); v = fmaf(l4.y, s_k[(m + 1) * 128 + tid], v);
+        v = fmaf(l4.z, s_k[(m + 2) * 128 + tid], v); v = fmaf(l4.w, s_k[(m + 3) * 128 + tid], v);
+      }
+      for (int m = jm; m < MP; m += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(s_lqt + j * MP + m);
+        w = fmaf(q4.x, s_k[m * 128 + tid], w); w = fmaf(q4.y, s_k[(m + 1) * 128 + tid], w);
+        w = fmaf(q4.z, s_k[(m + 2) * 128 + tid], w); w = fmaf(q4.w, s_k[(m + 3) * 128 + tid], w);
+      }
+      vv = fmaf(v, v, vv);
+      ww = fmaf(w, w, ww);
+    }
+  }
+  if (mean) mean[(size_t)i * ldm + d] = c + mu;
+  if (var) var[(size_t)i * ldv + d] = (s - vv) + ww + noise;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// trigger finalize: one thread per rollout.  numpy-order float32 arithmetic (see oracle/trigger_ref.py).
+// ---------------------------------------------------------------------------------------------------
+__device__ float np_pairwise_sum(const float* a, int n) {
+  // numpy's pairwise_sum for n <= 128 (float32 add.reduce of a contiguous vector)
+  if (n < 8) {
+    float r = 0.f;
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+    return r;
+  }
+  float r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+  return res;
+}
+
+constexpr int MAX_WINDOW = 128;
+
+__global__ void gp_trigger_finalize_kernel(int S, int D, const float* __restrict__ var_rows, float* __restrict__ window,
+                                           int W, int32_t* __restrict__ count, int warmup, float factor,
+                                           float* __restrict__ value, float* __restrict__ thr,
+                                           uint8_t* __restrict__ mask) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  // generate_frames.py:230 -- np.linalg.norm(variance^T, axis=1): sequential fp32 sum over d
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float v = var_rows[(size_t)s * D + d];
+    acc = __fadd_rn(acc, __fmul_rn(v, v));
+  }
+  const float val = sqrtf(acc);
+  float* w = window + (size_t)s * W;
+  if (value) value[s] = val;
+  if (warmup) {
+    const int cnt = count[0];
+    if (cnt < W) w[cnt] = val;
+    else {  // window already full: keep sliding without a decision
+      for (int i = 0; i + 1 < W; ++i) w[i] = w[i + 1];
+      w[W - 1] = val;
+    }
+    if (thr) thr[s] = nanf("");
+    if (mask) mask[s] = 0;
+    return;
+  }
+  float loc[MAX_WINDOW];
+  for (int i = 0; i + 1 < W; ++i) loc[i] = w[i + 1];   // generate_frames.py:231
+  loc[W - 1] = val;
+  for (int i = 0; i < W; ++i) w[i] = loc[i];
+  const float mean = __fdiv_rn(np_pairwise_sum(loc, W), (float)W);
+  for (int i = 0; i < W; ++i) {
+    const float dlt = __fsub_rn(loc[i], mean);
+    loc[i] = __fmul_rn(dlt, dlt);
+  }
+  const float sd = sqrtf(__fdiv_rn(np_pairwise_sum(loc, W), (float)W));
+  const float t = __fadd_rn(mean, __fmul_rn(factor, sd));  // generate_frames.py:288
+  if (thr) thr[s] = t;
+  if (mask) mask[s] = val > t ? 1 : 0;                    // generate_frames.py:289
+}
+
+__global__ void gp_count_bump_kernel(int32_t* count, int W) {
+  if (count[0] < W) count[0] += 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rsample: one CTA per (rollout s, latent dim d); full [N,N] predictive covariance in shared memory,
+// Cholesky, y = mean + L eps.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gp_rsample_kernel(int S, int N, int D, int mp, const float* __restrict__ x,
+                                                         int ldx, const float* __restrict__ eps,
+                                                         const uint8_t* __restrict__ mask,
+                                                         const float* __restrict__ zall,
+                                                         const float* __restrict__ linv_all,
+                                                         const float* __restrict__ lqt_all,
+                                                         const float* __restrict__ alpha_all,
+                                                         const float* __restrict__ hyp, float* __restrict__ out,
+                                                         int ldo) {
+  const int s_idx = blockIdx.x, d = blockIdx.y, tid = threadIdx.x;
+  if (mask != nullptr && mask[s_idx] == 0) return;
+  extern __shared__ __align__(16) float smf[];
+  const int MP = mp;
+  const int ldk = MP + 1, lds = N + 1;
+  float* s_linv = smf;                 // [MP][MP]
+  float* s_lqt = s_linv + MP * MP;     // [MP][MP]
+  float* s_k = s_lqt + MP * MP;        // [N][MP+1]  K_xz
+  float* s_u = s_k + N * ldk;          // [N][MP+1]  (Linv k_n)
+  float* s_r = s_u + N * ldk;          // [N][MP+1]  (L_q^T k_n)
+  float* s_sig = s_r + N * ldk;        // [N][N+1]   Sigma_y -> L
+  float* s_x = s_sig + N * lds;        // [N]
+  float* s_mean = s_x + N;             // [N]
+  float* s_t = s_mean + N;             // [N]
+  for (int e = tid; e < MP * MP; e += 128) {
+    s_linv[e] = linv_all[(size_t)d * MP * MP + e];
+    s_lqt[e] = lqt_all[(size_t)d * MP * MP + e];
+  }
+  const float ell = hyp[d * 4 + 0], sc = hyp[d * 4 + 1], c = hyp[d * 4 + 2], noise = hyp[d * 4 + 3];
+  const float inv_ell = 1.0f / ell;
+  for (int n = tid; n < N; n += 128) s_x[n] = x[(size_t)(s_idx * N + n) * ldx + d];
+  __syncthreads();
+  for (int e = tid; e < N * MP; e += 128) {
+    const int n = e / MP, m = e % MP;
+    const float t = (s_x[n] - zall[(size_t)d * MP + m]) * inv_ell;
+    s_k[n * ldk + m] = sc * expf(-0.5f * t * t);
+  }
+  __syncthreads();
+  for (int e = tid; e < N * MP; e += 128) {
+    const int n = e / MP, j = e % MP;
+    float v = 0.f, w = 0.f;
+    for (int m = 0; m <= j; ++m) v = fmaf(s_linv[j * MP + m], s_k[n * ldk + m], v);
+    for (int m = j; m < MP; ++m) w = fmaf(s_lqt[j * MP + m], s_k[n * ldk + m], w);
+    s_u[n * ldk + j] = v;
+    s_r[n * ldk + j] = w;
+  }
+  for (int n = tid; n < N; n += 128) {
+    float mu = 0.f;
+    for (int m = 0; m < MP; ++m) mu = fmaf(alpha_all[(size_t)d * MP + m], s_k[n * ldk + m], mu);
+    s_mean[n] = c + mu;
+  }
+  __syncthreads();
+  for (int e = tid; e < N * N; e += 128) {
+    const int a = e / N, b = e % N;
+    if (b > a) continue;
+    float rr = 0.f, uu = 0.f;
+    for (int m = 0; m < MP; ++m) {
+      rr = fmaf(s_r[a * ldk + m], s_r[b * ldk + m], rr);
+      uu = fmaf(s_u[a * ldk + m], s_u[b * ldk + m], uu);
+    }
+    const float t = (s_x[a] - s_x[b]) * inv_ell;
+    const float kxx = a == b ? sc : sc * expf(-0.5f * t * t);
+    s_sig[a * lds + b] = rr + (kxx - uu) + (a == b ? noise : 0.f);
+  }
+  __syncthreads();
+  // Cholesky (lower), left-looking
+  for (int j = 0; j < N; ++j) {
+    for (int i = j + tid; i < N; i += 128) {
+      float sum = s_sig[i * lds + j];
+      for (int k = 0; k < j; ++k) sum = fmaf(-s_sig[i * lds + k], s_sig[j * lds + k], sum);
+      s_t[i] = sum;
+    }
+    __syncthreads();
+    const float diag = sqrtf(s_t[j]);
+    for (int i = j + tid; i < N; i += 128) s_sig[i * lds + j] = (i == j) ? diag : s_t[i] / diag;
+    __syncthreads();
+  }
+  for (int n = tid; n < N; n += 128) {
+    float acc = 0.f;
+    const float* e = eps + ((size_t)s_idx * D + d) * N;
+    for (int k = 0; k <= n; ++k) acc = fmaf(s_sig[n * lds + k], e[k], acc);
+    out[(size_t)(s_idx * N + n) * ldo + d] = s_mean[n] + acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host launchers (called from capi.cu)
+// ---------------------------------------------------------------------------------------------------
+int gp_prepare_launch(dvg_gp_s* h, const float* inducing, const float* var_mean, const float* chol_var,
+                      const float* mean_const, const float* raw_os, const float* raw_ls, const float* raw_noise,
+                      cudaStream_t stream) {
+  const int D = h->dims.num_dims, M = h->dims.num_inducing;
+  const size_t smem = sizeof(double) * ((size_t)M * (M + 1) + 2 * M);
+  DVG_REQUIRE(smem <= 227 * 1024, "num_inducing=%d too large for the on-device fp64 factorisation (max 160)", M);
+  static bool configured = false;
+  if (!configured) {
+    DVG_CUDA(cudaFuncSetAttribute(gp_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  gp_prepare_kernel<<<D, 128, smem, stream>>>(D, M, h->mp, (double)h->dims.jitter, (double)h->dims.noise_lower_bound,
+                                              inducing, var_mean, chol_var, mean_const, raw_os, raw_ls, raw_noise,
+                                              h->z, h->linv, h->lqt, h->alpha, h->hyp, h->work);
+  DVG_LAUNCH_CHECK();
+  return DVG_OK;
+}
+
+int gp_predict_launch(dvg_gp_s* h, int n_rows, const float* x, int ldx, const int32_t* row_index, float* mean, int ldm,
+                      float* var, int ldv, cudaStream_t stream) {
+  if (n_rows <= 0) return DVG_OK;
+  const int D = h->dims.num_dims, mp = h->mp;
+  dim3 grid(ceil_div(n_rows, 128), D);
+  static bool configured = false;
+  if (!configured) {
+    DVG_CUDA(cudaFuncSetAttribute(gp_predict_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  if (mp == 40) {
+    const size_t smem = sizeof(float) * (2 * 40 * 40 + 2 * 40);
+    gp_predict_kernel<40><<<grid, 128, smem, stream>>>(n_rows, D, mp, x, ldx, row_index, h->z, h->linv, h->lqt, h->alpha,
+                                                       h->hyp, mean, ldm, var, ldv);
+  } else {
+    const size_t smem = sizeof(float) * ((size_t)2 * mp * mp + 2 * mp + (size_t)mp * 128);
+    DVG_REQUIRE(smem <= 227 * 1024, "num_inducing=%d too large for the shared-memory predictive kernel", mp);
+    gp_predict_kernel<0><<<grid, 128, smem, stream>>>(n_rows, D, mp, x, ldx, row_index, h->z, h->linv, h->lqt, h->alpha,
+                                                      h->hyp, mean, ldm, var, ldv);
+  }
+  DVG_LAUNCH_CHECK();
+  return DVG_OK;
+}
+
+int gp_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t* stat_rows, float* window, int W,
+                      int32_t* count, int warmup, float factor, float* value, float* thr, uint8_t* mask,
+                      cudaStream_t stream) {
+  DVG_REQUIRE(W >= 1 && W <= MAX_WINDOW, "window_len must be in [1,%d]", MAX_WINDOW);
+  DVG_REQUIRE(S <= h->var_rows_cap, "n_rollouts=%d exceeds the reserved trigger scratch (%d)", S, h->var_rows_cap);
+  const int D = h->dims.num_dims;
+  int rc = gp_predict_launch(h, S, x, ldx, stat_rows, nullptr, 0, h->var_rows, D, stream);
+  if (rc) return rc;
+  gp_trigger_finalize_kernel<<<ceil_div(S, 64), 64, 0, stream>>>(S, D, h->var_rows, window, W, count, warmup, factor,
+                                                                value, thr, mask);
+  DVG_LAUNCH_CHECK();
+  if (warmup) {
+    gp_count_bump_kernel<<<1, 1, 0, stream>>>(count, W);
+    DVG_LAUNCH_CHECK();
+  }
+  return DVG_OK;
+}
+
+int gp_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const float* eps, const uint8_t* mask,
+                      float* out, int ldo, cudaStream_t stream) {
+  const int D = h->dims.num_dims, mp = h->mp;
+  const size_t smem = sizeof(float) * ((size_t)2 * mp * mp + 3 * (size_t)N * (mp + 1) + (size_t)N * (N + 1) + 3 * N);
+  DVG_REQUIRE(smem <= 227 * 1024, "rsample needs %zu B of shared memory for N=%d, M=%d (max 227 KB)", smem, N, mp);
+  static bool configured = false;
+  if (!configured) {
+    DVG_CUDA(cudaFuncSetAttribute(gp_rsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  gp_rsample_kernel<<<dim3(S, D), 128, smem, stream>>>(S, N, D, mp, x, ldx, eps, mask, h->z, h->linv, h->lqt, h->alpha,
+                                                       h->hyp, out, ldo);
+  DVG_LAUNCH_CHECK();
+  return DVG_OK;
+}
+
+}  // namespace dvg

@@ -1,0 +1,103 @@
+// Handle structures and cross-file launch entry points (internal; not part of the C ABI).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace dvg {
+
+constexpr int MAX_LAYERS = 8;
+
+// ---- tensor-core GEMM tile plan ------------------------------------------------------------------
+struct TcGemmPlan {
+  int n_tile = 0;    // UMMA N (multiple of 16, <= 256)
+  int n_tiles = 0;   // number of N tiles
+  int kb0 = 0;       // k-blocks (of 64) from A source 0
+  int kb1 = 0;       // k-blocks from A source 1
+  uint8_t* w = nullptr;   // packed weights [n_tiles][kb0+kb1][2][n_tile*128 B]
+  float* bias = nullptr;  // [n_tiles*n_tile] in packed column order
+};
+
+}  // namespace dvg
+
+struct dvg_lstm_s {
+  dvg_lstm_dims dims{};
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0;
+  bool tc_ok = false;  // tensor-core variants usable (sm_100 and H % 64 == 0)
+
+  // --- DVG_FP32 (FFMA) weight copies: W^T, K-major rows, padded N ---------------------------------
+  int n_head = 0;      // head columns: G_out (lstm) or 2Z interleaved mu/logvar (gaussian)
+  int hp = 0;          // H rounded up to 64
+  int np_head = 0;     // n_head rounded up to 64
+  float* f_embed_wt = nullptr;  // [G_in][hp]
+  float* f_embed_b = nullptr;   // [hp]
+  float* f_layer_wt[dvg::MAX_LAYERS] = {};  // [2H][4H], column = unit*4 + gate
+  float* f_layer_b[dvg::MAX_LAYERS] = {};   // [4H] (b_ih + b_hh), same column order
+  float* f_head_wt = nullptr;   // [H][np_head]
+  float* f_head_b = nullptr;    // [np_head]
+
+  // --- tensor-core packed weights -----------------------------------------------------------------
+  dvg::TcGemmPlan tc_embed, tc_layer[dvg::MAX_LAYERS], tc_head;
+
+  // --- scratch, grown by reserve() ----------------------------------------------------------------
+  int reserved_rows = 0;
+  float* scratch_e = nullptr;    // fp32 [rows][H]: embed output (FFMA variant)
+  uint8_t* tc_xp = nullptr;      // packed x            [RT][kbx][2][16 KB]
+  uint8_t* tc_ep = nullptr;      // packed embed output [RT][H/64][2][16 KB]
+};
+
+struct dvg_gp_s {
+  dvg_gp_dims dims{};
+  int device = 0;
+  int mp = 0;                 // M rounded up to 4
+  float* z = nullptr;         // [D][mp] inducing points
+  float* linv = nullptr;      // [D][mp][mp] L_ZZ^-1 (lower triangular, zero padded)
+  float* lqt = nullptr;       // [D][mp][mp] L_q^T  (upper triangular: lqt[j][i] = L_q[i][j], i >= j)
+  float* alpha = nullptr;     // [D][mp]
+  float* hyp = nullptr;       // [D][4]  ell, s, c, noise
+  double* work = nullptr;     // fp64 scratch for prepare [D][3][M][M]
+  float* var_rows = nullptr;  // scratch [max_rollouts][D] for the trigger
+  int var_rows_cap = 0;
+};
+
+namespace dvg {
+
+// lstm_fp32.cu
+int lstm_fp32_pack(dvg_lstm_s* h, const float* embed_w, const float* embed_b, const float* const* w_ih,
+                   const float* const* w_hh, const float* const* b_ih, const float* const* b_hh,
+                   const float* head0_w, const float* head0_b, const float* head1_w, const float* head1_b,
+                   cudaStream_t stream);
+int lstm_fp32_step(dvg_lstm_s* h, int rows, const float* x, int ldx, const float* h_in, const float* c_in,
+                   float* h_out, float* c_out, float* y, int ldy, const float* eps, float* z, float* mu,
+                   float* logvar, const uint8_t* hold, int rows_per_flag, cudaStream_t stream);
+
+// lstm_tc.cu
+int lstm_tc_pack(dvg_lstm_s* h, const float* embed_w, const float* embed_b, const float* const* w_ih,
+                 const float* const* w_hh, const float* const* b_ih, const float* const* b_hh,
+                 const float* head0_w, const float* head0_b, const float* head1_w, const float* head1_b,
+                 cudaStream_t stream);
+size_t lstm_tc_packed_state_bytes(const dvg_lstm_s* h, int rows);
+int lstm_tc_repack_state(dvg_lstm_s* h, int rows, const float* h_f32, uint8_t* hp, cudaStream_t stream);
+int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in,
+                 const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out, float* y,
+                 int ldy, const float* eps, float* z, float* mu, float* logvar, const uint8_t* hold,
+                 int rows_per_flag, cudaStream_t stream);
+void lstm_tc_free(dvg_lstm_s* h);
+size_t lstm_tc_scratch_bytes_xp(const dvg_lstm_s* h, int rows);
+size_t lstm_tc_scratch_bytes_ep(const dvg_lstm_s* h, int rows);
+
+// gp.cu
+int gp_prepare_launch(dvg_gp_s* h, const float* inducing, const float* var_mean, const float* chol_var,
+                      const float* mean_const, const float* raw_os, const float* raw_ls, const float* raw_noise,
+                      cudaStream_t stream);
+int gp_predict_launch(dvg_gp_s* h, int n_rows, const float* x, int ldx, const int32_t* row_index, float* mean, int ldm,
+                      float* var, int ldv, cudaStream_t stream);
+int gp_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t* stat_rows, float* window, int W,
+                      int32_t* count, int warmup, float factor, float* value, float* thr, uint8_t* mask,
+                      cudaStream_t stream);
+int gp_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const float* eps, const uint8_t* mask,
+                      float* out, int ldo, cudaStream_t stream);
+
+}  // namespace dvg

@@ -1,0 +1,212 @@
+"""Drop-in ``GPRegressionLayer1`` + ``GaussianLikelihood`` (reference: models/gp_models.py:10-24 and the
+``gpytorch.likelihoods.GaussianLikelihood(batch_size=g_dim)`` of generate_frames.py:67 / train.py:102).
+
+gpytorch-free: the parameters live in plain ``nn.Module`` containers whose ``state_dict`` keys are the
+gpytorch 0.3.x names the reference checkpoints hold (train.py:384-386):
+
+    gp_layer:   variational_strategy.inducing_points [D,M,1]
+                variational_strategy.variational_distribution.variational_mean [D,M]
+                variational_strategy.variational_distribution.chol_variational_covar [D,M,M]
+                variational_strategy.variational_params_initialized (0-d buffer)
+                mean_module.constant [D,1]
+                covar_module.raw_outputscale [D]
+                covar_module.base_kernel.raw_lengthscale [D,1,1]
+    likelihood: noise_covar.raw_noise [D,1]
+
+Call protocol (generate_frames.py:131,170,229,273,291; train.py:283):
+``pred = likelihood(gp_layer(h.transpose(0,1).view(D,N,1)))`` then ``pred.mean`` / ``pred.variance``
+(``[D,N]``) or ``pred.rsample()`` (``[D,N]``).  Evaluation is lazy: nothing is computed until one of the
+three is read, and each read is a single C-ABI call (``dvg_gp_predict`` / ``dvg_gp_rsample``).  The
+eval-mode constants the reference recomputes on every call (K_ZZ, its Cholesky factor, K_ZZ^-1(m-c)) are
+hoisted into ``dvg_gp_prepare`` and refreshed only when a parameter changes.
+
+Eval-mode only; the training-mode branch (diag-only data covariance, KL memo, VariationalELBO) is out
+of scope for the kernels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _capi
+
+JITTER = 1e-3
+NOISE_LOWER_BOUND = 1e-4
+
+
+class _Holder(nn.Module):
+    """Plain parameter container (keeps gpytorch's nested state_dict names)."""
+
+
+class GaussianLikelihood(nn.Module):
+    def __init__(self, batch_size=1, noise_lower_bound=NOISE_LOWER_BOUND):
+        super().__init__()
+        self.noise_covar = _Holder()
+        self.noise_covar.raw_noise = nn.Parameter(torch.zeros(batch_size, 1))
+        self.noise_lower_bound = noise_lower_bound
+
+    @property
+    def noise(self):
+        return nn.functional.softplus(self.noise_covar.raw_noise) + self.noise_lower_bound
+
+    def forward(self, pred: "GPPrediction") -> "GPPrediction":
+        return pred.with_likelihood(self)
+
+
+class _GpRuntime:
+    def __init__(self, layer, likelihood):
+        self.lib = _capi.load()
+        self.handle = None
+        self.sig = None
+        self.refresh(layer, likelihood)
+
+    @staticmethod
+    def _tensors(layer, likelihood):
+        vs = layer.variational_strategy
+        ts = [vs.inducing_points, vs.variational_distribution.variational_mean,
+              vs.variational_distribution.chol_variational_covar, layer.mean_module.constant,
+              layer.covar_module.raw_outputscale, layer.covar_module.base_kernel.raw_lengthscale]
+        if likelihood is not None:
+            ts.append(likelihood.noise_covar.raw_noise)
+        return ts
+
+    def signature(self, layer, likelihood):
+        return tuple((t.data_ptr(), t._version) for t in self._tensors(layer, likelihood))
+
+    def refresh(self, layer, likelihood):
+        ts = self._tensors(layer, likelihood)
+        for t in ts:
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise _capi.DvgError("dvg_b200 GP needs fp32 CUDA parameters (call .cuda() first); no CPU fallback")
+        dev = ts[0].device
+        D, M = ts[1].shape
+        if likelihood is None:     # latent f (no observation noise): softplus(-100) == 0, lower bound 0
+            raw_noise = torch.full((D, 1), -100.0, device=dev)
+            lb = 0.0
+        else:
+            raw_noise = ts[6]
+            lb = float(likelihood.noise_lower_bound)
+        args = [_capi.ptr(t.detach().contiguous()) for t in ts[:6]] + [_capi.ptr(raw_noise.detach().contiguous())]
+        with torch.cuda.device(dev):
+            if self.handle is None:
+                dims = _capi.GpDims(D, M, JITTER, lb)
+                hd = _capi.c_void_p()
+                _capi.check(self.lib.dvg_gp_prepare(_capi.ctypes.byref(hd), _capi.ctypes.byref(dims), *args,
+                                                    _capi.stream_ptr()), "dvg_gp_prepare")
+                self.handle = hd
+            else:
+                _capi.check(self.lib.dvg_gp_refresh(self.handle, *args, _capi.stream_ptr()), "dvg_gp_refresh")
+        self._keep = raw_noise
+        self.D, self.M, self.device = D, M, dev
+        self.sig = self.signature(layer, likelihood)
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                self.lib.dvg_gp_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class GPPrediction:
+    """Lazy stand-in for the gpytorch ``MultivariateNormal`` the rollout consumes."""
+
+    def __init__(self, layer, x, likelihood=None):
+        if x.dim() != 3 or x.shape[-1] != 1 or x.shape[0] != layer.num_dims:
+            raise ValueError(f"expected x of shape [{layer.num_dims}, N, 1], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise _capi.DvgError("dvg_b200 GP is CUDA-only (no CPU fallback); got a CPU tensor")
+        self._layer, self._lik = layer, likelihood
+        lat = x.detach()[..., 0].transpose(0, 1)        # [N, D]; the original latent when x was its view
+        if lat.dtype != torch.float32:
+            lat = lat.float()
+        if lat.stride(1) != 1 or (lat.shape[0] > 1 and lat.stride(0) < lat.shape[1]):
+            lat = lat.contiguous()
+        self._lat = lat
+        self._mv = None
+
+    def with_likelihood(self, likelihood):
+        p = GPPrediction.__new__(GPPrediction)
+        p._layer, p._lik, p._lat, p._mv = self._layer, likelihood, self._lat, None
+        return p
+
+    def _rt(self):
+        return self._layer._runtime(self._lik)
+
+    def _ld(self):
+        return self._lat.stride(0) if self._lat.shape[0] > 1 else self._lat.shape[1]
+
+    def _mean_var(self):
+        if self._mv is None:
+            rt = self._rt()
+            N, D = self._lat.shape
+            out = torch.empty(2, N, D, dtype=torch.float32, device=self._lat.device)
+            _capi.check(rt.lib.dvg_gp_predict(rt.handle, N, _capi.ptr(self._lat), self._ld(), None,
+                                              _capi.ptr(out[0]), D, _capi.ptr(out[1]), D, _capi.stream_ptr()),
+                        "dvg_gp_predict")
+            self._mv = out
+        return self._mv
+
+    @property
+    def mean(self):
+        """[D, N] (a transposed view of the [N, D] buffer the decoder wants)."""
+        return self._mean_var()[0].transpose(0, 1)
+
+    @property
+    def variance(self):
+        return self._mean_var()[1].transpose(0, 1)
+
+    def rsample(self, eps=None):
+        """mean + chol(Sigma_y) eps, eps ~ N(0,I) drawn as ``randn[D,N]`` unless injected.  Returns [D, N]."""
+        rt = self._rt()
+        N, D = self._lat.shape
+        if eps is None:
+            eps = torch.randn(D, N, device=self._lat.device, dtype=torch.float32)
+        eps = eps.to(self._lat.device, torch.float32).reshape(1, D, N).contiguous()
+        out = torch.empty(N, D, dtype=torch.float32, device=self._lat.device)
+        _capi.check(rt.lib.dvg_gp_rsample(rt.handle, 1, N, _capi.ptr(self._lat), self._ld(), _capi.ptr(eps), None,
+                                          _capi.ptr(out), D, _capi.stream_ptr()), "dvg_gp_rsample")
+        return out.transpose(0, 1)
+
+
+class GPRegressionLayer1(nn.Module):
+    def __init__(self, num_dims=90, num_inducing_points=40):
+        super().__init__()
+        D, M = num_dims, num_inducing_points
+        self.num_dims, self.num_inducing_points = D, M
+        vs = _Holder()
+        vs.inducing_points = nn.Parameter(torch.rand(D, M, 1))                       # models/gp_models.py:13
+        vs.register_buffer("variational_params_initialized", torch.tensor(1))
+        vd = _Holder()
+        vd.variational_mean = nn.Parameter(torch.zeros(D, M))
+        vd.chol_variational_covar = nn.Parameter(torch.eye(M).repeat(D, 1, 1))
+        vs.variational_distribution = vd
+        self.variational_strategy = vs
+        self.mean_module = _Holder()
+        self.mean_module.constant = nn.Parameter(torch.zeros(D, 1))
+        self.covar_module = _Holder()
+        self.covar_module.raw_outputscale = nn.Parameter(torch.zeros(D))
+        self.covar_module.base_kernel = _Holder()
+        self.covar_module.base_kernel.raw_lengthscale = nn.Parameter(torch.zeros(D, 1, 1))
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_dvg_rts", None)
+        return state
+
+    def _runtime(self, likelihood) -> _GpRuntime:
+        rts = self.__dict__.setdefault("_dvg_rts", {})
+        key = id(likelihood) if likelihood is not None else 0
+        rt = rts.get(key)
+        if rt is None:
+            rt = _GpRuntime(self, likelihood)
+            rts[key] = rt
+        elif rt.sig != rt.signature(self, likelihood):
+            rt.refresh(self, likelihood)
+        return rt
+
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError("dvg_b200 implements the eval-mode GP predictive only; call .eval() "
+                                      "(training-mode ELBO is out of scope, SURVEY 8f)")
+        return GPPrediction(self, x)

@@ -1,0 +1,192 @@
+/*
+ * dvg_b200.h -- C ABI of the B200-native DVG rollout hot path.
+ *
+ * The reference (shgaurav1/DVG) is pure Python/PyTorch and has no FFI of its own; the drop-in
+ * boundary is the Python object protocol of models/lstm.py and models/gp_models.py (see
+ * INTEGRATION.md).  This header is what that protocol binds to: every entry point below replaces the
+ * library calls the cited reference lines issue on the GPU.  Plain C: raw device pointers, sizes and a
+ * cudaStream_t; no torch types.  All calls are asynchronous on `stream` (no host sync, no D2H) unless
+ * stated; they return 0 on success and a negative dvg_status on failure (never throw);
+ * dvg_last_error() returns a thread-local description of the last failure.
+ *
+ * Ownership: every tensor passed in is owned by the caller (PyTorch).  A handle owns only its caches
+ * (packed / padded weight copies, GP factors, scratch sized by the largest `rows` seen).  One handle
+ * per (model, device); a handle is not re-entrant; independent handles are thread-safe.
+ */
+#ifndef DVG_B200_H
+#define DVG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DVG_API __attribute__((visibility("default")))
+#else
+#define DVG_API
+#endif
+
+typedef struct CUstream_st* dvg_stream_t; /* == cudaStream_t */
+typedef struct dvg_lstm_s* dvg_lstm_t;
+typedef struct dvg_gp_s* dvg_gp_t;
+
+enum dvg_status {
+  DVG_OK = 0,
+  DVG_ERR_ARG = -1,      /* bad argument / unsupported size for the requested variant */
+  DVG_ERR_CUDA = -2,     /* a CUDA runtime call failed (see dvg_last_error) */
+  DVG_ERR_ARCH = -3,     /* device is not sm_100 (tensor-core variants) */
+  DVG_ERR_STATE = -4     /* handle / state block misuse */
+};
+
+/* GEMM arithmetic of the LSTM gate / embed / head contractions. */
+enum dvg_variant {
+  DVG_FP32 = 0,    /* CUDA-core FFMA, exact fp32 products (any sizes) */
+  DVG_BF16X3 = 1,  /* tcgen05 kind::f16, operands split a = hi + lo (bf16), hi*hi + hi*lo + lo*hi,
+                      fp32 accumulate in TMEM: fp32-grade (<=1e-4 rel.) -- needs hidden_size % 64 == 0 */
+  DVG_BF16 = 2     /* tcgen05 kind::f16, single bf16 pass (2e-2 tolerance variant) */
+};
+
+enum dvg_lstm_kind {
+  DVG_LSTM = 0,          /* models/lstm.py:42-72   embed -> L x LSTMCell -> Linear + Tanh */
+  DVG_GAUSSIAN_LSTM = 1  /* models/lstm.py:140-175 embed -> L x LSTMCell -> mu_net, logvar_net, reparameterize */
+};
+
+DVG_API const char* dvg_last_error(void);
+DVG_API int dvg_version(void);
+/* sm count / compute capability of the current device (host query, synchronous). */
+DVG_API int dvg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame-predictor LSTM / gaussian_lstm
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int kind;         /* dvg_lstm_kind */
+  int input_size;   /* G_in  (embed.weight [H, G_in]) */
+  int hidden_size;  /* H */
+  int n_layers;     /* L */
+  int output_size;  /* G_out (output.0.weight [G_out, H]) or Z (mu_net/logvar_net.weight [Z, H]) */
+} dvg_lstm_dims;
+
+/* Replaces the per-call weight reads of models/lstm.py:66,69,72 (and :172-173): packs the fp32
+ * parameters once into kernel layouts (x||h concatenated along K, gate-interleaved N, padded, bf16
+ * hi/lo tile images for the tensor-core variants).  Call again (dvg_lstm_refresh) after the parameters
+ * change.  Pointers are device pointers in the reference's state_dict layout:
+ *   embed_w [H,G_in], embed_b [H]; per layer l: w_ih[l] [4H,H], w_hh[l] [4H,H], b_ih[l] [4H], b_hh[l] [4H]
+ *   (gate chunk order i,f,g,o); head0 = output.0 (or mu_net) weight [G_out,H] + bias; head1 = logvar_net
+ *   (DVG_GAUSSIAN_LSTM only, else NULL).  The w_ih.. arrays are HOST arrays of L device pointers. */
+DVG_API int dvg_lstm_prepare(dvg_lstm_t* out, const dvg_lstm_dims* dims,
+                     const float* embed_w, const float* embed_b,
+                     const float* const* w_ih, const float* const* w_hh,
+                     const float* const* b_ih, const float* const* b_hh,
+                     const float* head0_w, const float* head0_b,
+                     const float* head1_w, const float* head1_b,
+                     dvg_stream_t stream);
+DVG_API int dvg_lstm_refresh(dvg_lstm_t h,
+                     const float* embed_w, const float* embed_b,
+                     const float* const* w_ih, const float* const* w_hh,
+                     const float* const* b_ih, const float* const* b_hh,
+                     const float* head0_w, const float* head0_b,
+                     const float* head1_w, const float* head1_b,
+                     dvg_stream_t stream);
+DVG_API int dvg_lstm_destroy(dvg_lstm_t h);
+
+/* Grow the handle's scratch so that steps with up to `rows` rows never allocate (call before CUDA
+ * graph capture).  Synchronous (cudaMalloc). */
+DVG_API int dvg_lstm_reserve(dvg_lstm_t h, int rows);
+
+/* Recurrent state block (replaces the list of (h,c) tuples of models/lstm.py:58-63).  One block holds
+ *   h  fp32 [L][rows][H]   at byte offset 0
+ *   c  fp32 [L][rows][H]   at byte offset L*rows*H*4
+ *   hp bf16 hi/lo tile images of h (tensor-core A operand) at dvg_lstm_state_packed_offset()
+ * A zero-filled block is a valid initial state (init_hidden).  The caller owns the memory. */
+DVG_API size_t dvg_lstm_state_bytes(dvg_lstm_t h, int rows);
+DVG_API size_t dvg_lstm_state_packed_offset(dvg_lstm_t h, int rows);
+/* Rebuild the packed image from the fp32 h part (after the caller wrote h from outside). */
+DVG_API int dvg_lstm_state_repack(dvg_lstm_t h, int rows, void* state, dvg_stream_t stream);
+
+/* One time step of models/lstm.py:65-72 for `rows` independent rows.
+ *   x [rows, G_in] row-major with leading dimension ldx (floats);  y [rows, G_out], ldy.
+ *   state_in -> state_out (distinct blocks; state_in is not modified).
+ *   hold (optional, may be NULL): u8 flags, one per group of `rows_per_flag` consecutive rows; rows whose
+ *   flag is non-zero keep their state (state_out = state_in) -- the "LSTM is not advanced on a triggered
+ *   step" semantics of generate_frames.py:289-295; y is still produced for them. */
+DVG_API int dvg_lstm_step(dvg_lstm_t h, int variant, int rows,
+                  const float* x, int ldx,
+                  const void* state_in, void* state_out,
+                  float* y, int ldy,
+                  const uint8_t* hold, int rows_per_flag,
+                  dvg_stream_t stream);
+
+/* One time step of models/lstm.py:166-175; eps [rows, Z] is the N(0,1) draw of :163.
+ * Writes z, mu, logvar [rows, Z] (dense). */
+DVG_API int dvg_gauss_lstm_step(dvg_lstm_t h, int variant, int rows,
+                        const float* x, int ldx,
+                        const void* state_in, void* state_out,
+                        const float* eps, float* z, float* mu, float* logvar,
+                        dvg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Variational GP predictive + trigger  (models/gp_models.py:10-24 + gpytorch WhitenedVariationalStrategy
+ * + GaussianLikelihood, call sites generate_frames.py:131,170,229,273,291; train.py:283)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int num_dims;      /* D (= g_dim) */
+  int num_inducing;  /* M */
+  float jitter;             /* 1e-3 (gpytorch add_jitter) */
+  float noise_lower_bound;  /* 1e-4 (GaussianLikelihood GreaterThan constraint); 0 for the earliest 0.3.x */
+} dvg_gp_dims;
+
+/* Hoists everything that is constant in eval mode (the reference recomputes it per call): softplus
+ * hyper-parameters, K_ZZ + jitter, its Cholesky factor (fp64 on device), L_ZZ^-1, alpha = K_ZZ^-1(m_q - c),
+ * masked L_q.  Pointers are device pointers in gpytorch 0.3.x state_dict layout:
+ *   inducing [D,M,1], var_mean [D,M], chol_var [D,M,M] (raw, upper part ignored), mean_const [D,1],
+ *   raw_outputscale [D], raw_lengthscale [D,1,1], raw_noise [D,1]. */
+DVG_API int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims,
+                   const float* inducing, const float* var_mean, const float* chol_var,
+                   const float* mean_const, const float* raw_outputscale, const float* raw_lengthscale,
+                   const float* raw_noise, dvg_stream_t stream);
+DVG_API int dvg_gp_refresh(dvg_gp_t h,
+                   const float* inducing, const float* var_mean, const float* chol_var,
+                   const float* mean_const, const float* raw_outputscale, const float* raw_lengthscale,
+                   const float* raw_noise, dvg_stream_t stream);
+DVG_API int dvg_gp_destroy(dvg_gp_t h);
+
+/* likelihood(gp_layer(x)).mean / .variance for a set of latent rows.
+ *   x [*, D] row-major (ldx floats): the [N,D] latent itself -- the reference's
+ *   h.transpose(0,1).view(D,N,1) is only a strided view of it.
+ *   row_index (optional): n_rows int32 row numbers to evaluate (gather); NULL = rows 0..n_rows-1.
+ *   mean / var (either may be NULL): written at [i, d] for the i-th evaluated row, leading dims ldm / ldv. */
+DVG_API int dvg_gp_predict(dvg_gp_t h, int n_rows, const float* x, int ldx, const int32_t* row_index,
+                   float* mean, int ldm, float* var, int ldv, dvg_stream_t stream);
+
+/* Fused trigger of generate_frames.py:227-232,275,283-289 for S independent rollouts, all on device:
+ *   stat_rows [S] int32: the latent row whose variance drives rollout s (s*N + column);
+ *   value[s] = || variance[stat_rows[s], :] ||_2 ; the window (fp32 [S, window_len]) slides;
+ *   thr[s] = mean(window) + factor * std(window) (population std);  mask[s] = value > thr.
+ *   warmup != 0: value is appended at window[s][*count] without a decision (mask = 0), the
+ *   generate_frames.py:266-280 phase.  `count` is a device int32 (number of warm-up values stored). */
+DVG_API int dvg_gp_trigger(dvg_gp_t h, int n_rollouts, const float* x, int ldx, const int32_t* stat_rows,
+                   float* window, int window_len, int32_t* count, int warmup, float factor,
+                   float* value, float* thr, uint8_t* mask, dvg_stream_t stream);
+
+/* likelihood(gp_layer(x)).rsample() (generate_frames.py:171,292; train.py:284) for the rollouts whose
+ * mask is set (mask NULL = all):  latent[s*N + n, d] = mean + (chol(Sigma_y) eps)[n] with
+ * Sigma_y the full [N,N] predictive covariance of rollout s in dimension d.
+ *   x [S*N, D] (ldx), eps [S, D, N] standard normal, out [S*N, D] (ldo) -- rows of unmasked rollouts are
+ *   left untouched, so `out` can be the LSTM output buffer (on-device select). */
+DVG_API int dvg_gp_rsample(dvg_gp_t h, int n_rollouts, int n_points, const float* x, int ldx,
+                   const float* eps, const uint8_t* mask, float* out, int ldo, dvg_stream_t stream);
+
+/* Debug / test access to the hoisted factors (device->device copies into caller buffers; any may be NULL),
+ * with Mp = num_inducing rounded up to a multiple of 4 (zero padded):
+ *   linv [D,Mp,Mp] (L_ZZ^-1, lower), lqt [D,Mp,Mp] (masked L_q, transposed), alpha [D,Mp],
+ *   hyp [D,4] = (ell, s, c, noise). */
+DVG_API int dvg_gp_export(dvg_gp_t h, float* linv, float* lqt, float* alpha, float* hyp, dvg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVG_B200_H */

@@ -1,0 +1,149 @@
+"""GPU parity of the GP predictive / trigger / rsample (through the C ABI) against the CPU oracle.
+The GP oracle is a restatement of gpytorch 0.3.x (PARITY UNPINNED, see oracle/gp_ref.py); the bar is
+<= 1e-4 relative against its fp64 evaluation."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_ref, trigger_ref
+from util import make_gp, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("trained", [False, True])
+@pytest.mark.parametrize("D,M,N", [(90, 40, 50), (90, 40, 333), (17, 24, 9), (8, 64, 40), (5, 128, 30)])
+def test_predict(trained, D, M, N):
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=D + M, trained_like=trained)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    h = torch.tanh(torch.randn(N, D, generator=torch.Generator().manual_seed(N)))
+    ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h), torch.float64, "direct", full_cov=False)
+    hc = h.cuda()
+    with torch.no_grad():
+        pred = lik(gp(hc.transpose(0, 1).view(D, N, 1)))
+        mean, var = pred.mean, pred.variance
+    assert mean.shape == (D, N) and var.shape == (D, N)
+    assert relerr(var, ref["variance"]) < 1e-4
+    if trained:
+        assert relerr(mean, ref["mean"]) < 1e-4
+    else:
+        assert mean.abs().max().item() < 1e-6
+    # latent (noise-free) predictive: gp_layer(x).variance == variance - noise
+    with torch.no_grad():
+        f = gp(hc.transpose(0, 1).view(D, N, 1))
+        _, _, _, noise = gp_ref.effective_hypers(gp_sd, lik_sd, torch.float64)
+        assert relerr(f.variance, ref["variance"] - noise.reshape(-1, 1)) < 2e-4
+        assert relerr(f.mean, ref["mean"]) < 1e-4 or not trained
+
+
+def test_prepared_factors():
+    from dvg_b200 import _capi
+    D, M = 12, 40
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=3, trained_like=True)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    rt = gp._runtime(lik)
+    linv = torch.empty(D, M, M, device="cuda")
+    lqt = torch.empty(D, M, M, device="cuda")
+    alpha = torch.empty(D, M, device="cuda")
+    hyp = torch.empty(D, 4, device="cuda")
+    _capi.check(rt.lib.dvg_gp_export(rt.handle, _capi.ptr(linv), _capi.ptr(lqt), _capi.ptr(alpha), _capi.ptr(hyp),
+                                     _capi.stream_ptr()))
+    ell, s, c, noise = gp_ref.effective_hypers(gp_sd, lik_sd, torch.float64)
+    assert relerr(hyp, torch.stack([ell, s, c, noise], 1)) < 1e-6
+    Z = gp_sd[gp_ref.K_INDUCING].double()
+    K = gp_ref.kernel(Z, Z, ell, s, "direct") + 1e-3 * torch.eye(M, dtype=torch.float64)
+    L = torch.linalg.cholesky(K)
+    assert relerr(linv, torch.linalg.inv(L)) < 1e-5
+    assert relerr(lqt, torch.tril(gp_sd[gp_ref.K_VCHOL].double()).transpose(1, 2)) < 1e-6
+    a = torch.cholesky_solve((gp_sd[gp_ref.K_VMEAN].double() - c.reshape(-1, 1)).unsqueeze(-1), L).squeeze(-1)
+    assert relerr(alpha, a) < 1e-5
+
+
+@pytest.mark.parametrize("trained", [False, True])
+def test_rsample(trained):
+    D, M, N = 90, 40, 50
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=21, trained_like=trained)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    g = torch.Generator().manual_seed(2)
+    h = torch.tanh(torch.randn(N, D, generator=g))
+    eps = torch.randn(D, N, generator=g)
+    ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h), torch.float64, "direct")
+    want = gp_ref.rsample(ref["mean"], ref["covar"], eps.double())
+    with torch.no_grad():
+        got = lik(gp(h.cuda().transpose(0, 1).view(D, N, 1))).rsample(eps=eps.cuda())
+    assert got.shape == (D, N)
+    assert relerr(got, want) < 1e-4
+
+
+def test_trigger_sequence_matches_numpy_oracle():
+    """Device window / threshold / decision vs oracle/trigger_ref.py over a 60-step sequence for S=7
+    independent rollouts (decisions bit-exact outside a 1e-5 band around the threshold)."""
+    from dvg_b200 import _capi
+    D, M, N, S, W = 90, 40, 50, 7, 12
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=33, trained_like=True)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    rt = gp._runtime(lik)
+    g = torch.Generator().manual_seed(5)
+    T = 60
+    lat = torch.tanh(torch.randn(T, S * N, D, generator=g) * torch.linspace(0.3, 1.5, T).reshape(T, 1, 1))
+    stat_cols = torch.tensor([3, 0, 7, 49, 3, 21, 10])
+    stat_rows = (torch.arange(S) * N + stat_cols).int().cuda()
+    window = torch.zeros(S, W, device="cuda")
+    count = torch.zeros(1, dtype=torch.int32, device="cuda")
+    value = torch.empty(S, device="cuda")
+    thr = torch.empty(S, device="cuda")
+    mask = torch.empty(S, dtype=torch.uint8, device="cuda")
+    ctx = [[] for _ in range(S)]
+    n_checked = n_fired = 0
+    for t in range(T):
+        x = lat[t].cuda()
+        warm = 1 if t < W else 0
+        _capi.check(rt.lib.dvg_gp_trigger(rt.handle, S, _capi.ptr(x), D, _capi.ptr(stat_rows), _capi.ptr(window), W,
+                                          _capi.ptr(count), warm, float(np.float32(trigger_ref.FACTOR)),
+                                          _capi.ptr(value), _capi.ptr(thr), _capi.ptr(mask), _capi.stream_ptr()))
+        v_gpu, thr_gpu, m_gpu = value.cpu().numpy(), thr.cpu().numpy(), mask.cpu().numpy()
+        for s in range(S):
+            ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(lat[t, s * N:(s + 1) * N]),
+                                    torch.float32, "gpytorch", full_cov=False)
+            v = trigger_ref.trigger_value(ref["variance"].numpy(), int(stat_cols[s]))
+            assert abs(v_gpu[s] - v) <= 1e-4 * abs(v)
+            if warm:
+                ctx[s].append(v)
+                assert m_gpu[s] == 0
+            else:
+                c = trigger_ref.slide(np.array(ctx[s], dtype=np.float32), v)
+                ctx[s] = list(c)
+                th = trigger_ref.threshold(c)
+                assert abs(thr_gpu[s] - th) <= 1e-4 * abs(th)
+                if abs(float(v) - float(th)) > 1e-4 * abs(float(th)):
+                    assert bool(m_gpu[s]) == bool(v > th)
+                    n_checked += 1
+                    n_fired += int(v > th)
+        np.testing.assert_allclose(window.cpu().numpy()[:, :len(ctx[0])] if warm else window.cpu().numpy(),
+                                   np.array(ctx, dtype=np.float32), rtol=1e-4)
+    assert n_checked > 300 and 0 < n_fired < n_checked
+
+
+def test_rsample_mask_leaves_rows_untouched():
+    from dvg_b200 import _capi
+    D, M, N, S = 30, 40, 20, 5
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=8, trained_like=True)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    rt = gp._runtime(lik)
+    g = torch.Generator().manual_seed(1)
+    x = torch.tanh(torch.randn(S * N, D, generator=g)).cuda()
+    eps = torch.randn(S, D, N, generator=g).cuda()
+    out = torch.full((S * N, D), 7.0, device="cuda")
+    mask = torch.tensor([1, 0, 0, 1, 0], dtype=torch.uint8, device="cuda")
+    _capi.check(rt.lib.dvg_gp_rsample(rt.handle, S, N, _capi.ptr(x), D, _capi.ptr(eps), _capi.ptr(mask),
+                                      _capi.ptr(out), D, _capi.stream_ptr()))
+    out = out.cpu()
+    for s in range(S):
+        blk = out[s * N:(s + 1) * N]
+        if mask[s]:
+            ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(x[s * N:(s + 1) * N].cpu()),
+                                    torch.float64, "direct")
+            want = gp_ref.rsample(ref["mean"], ref["covar"], eps[s].cpu().double()).transpose(0, 1)
+            assert relerr(blk, want) < 1e-4
+        else:
+            assert torch.all(blk == 7.0)
