@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the DVG stochastic-rollout hot path (BASELINE.json metric: generated frames/sec for N
+diverse futures, plus roofline fraction).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--variant bf16x3|bf16|fp32]
+
+A "step" is one complete rollout of the hot path over one batch of synthetic encoder latents:
+workload ``kth_s100`` = BASELINE.json configs[1] (KTH-shaped: g_dim 90, rnn_size 256, 2 LSTM layers, GP with
+40 inducing points, B=50 sequences x S=100 diverse futures = 5000 rows, 10 past + 30 future frames ->
+39 time steps, trigger window 12).  Every time step runs: GP variance trigger -> fused LSTM step (state
+held for triggered rollouts) -> masked GP rsample.  The encoder/decoder convolutions stay on the stock
+PyTorch path (north_star) and are NOT part of the timed hot path; the latents they would produce are
+synthetic tensors resident in HBM.  frames = S * B * n_future per rollout.
+
+JSON keys beyond the base contract: ``roofline`` (dominant kernel = the tcgen05 LSTM layer GEMM, timed
+live with CUDA events between launches), ``cpu_baseline`` (oracle port on the host cores, bounded sample),
+``e2e`` (same metric through the public Python API with pinned HOST buffers, H2D + D2H inside the timed
+region), ``gpu_launches``, ``clocks``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: g_dim, rnn_size, layers, inducing, B, S, n_past, n_future, window
+    "kth_s100": dict(G=90, H=256, L=2, M=40, B=50, S=100, n_past=10, n_future=30, window=12),
+    "smmnist_b16": dict(G=90, H=256, L=2, M=40, B=16, S=1, n_past=5, n_future=10, window=5),
+    "bair_s32": dict(G=90, H=256, L=2, M=40, B=50, S=32, n_past=2, n_future=28, window=12),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_models(w, device, variant, seed=1):
+    from dvg_b200.models.gp_models import GaussianLikelihood, GPRegressionLayer1
+    from dvg_b200.models.lstm import lstm
+    from dvg_b200.init import init_gp_state_dicts, init_lstm_state_dict
+    fp = lstm(w["G"], w["G"], w["H"], w["L"], w["B"])
+    fp.load_state_dict(init_lstm_state_dict(w["G"], w["G"], w["H"], w["L"], seed))
+    gp = GPRegressionLayer1(w["G"], w["M"])
+    lik = GaussianLikelihood(w["G"])
+    gsd, lsd = init_gp_state_dicts(w["G"], w["M"], seed)
+    gp.load_state_dict(gsd)
+    lik.load_state_dict(lsd)
+    fp, gp, lik = fp.to(device).eval(), gp.to(device).eval(), lik.to(device).eval()
+    fp.gemm_variant = variant
+    return fp, gp, lik
+
+
+def synth_latents(w, T, R, device, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    scale = torch.linspace(0.4, 1.2, T).reshape(T, 1, 1)
+    lat = torch.tanh(torch.randn(T, R, w["G"], generator=g) * scale)      # encoder outputs end in tanh
+    eps = torch.randn(T, R // w["B"], w["G"], w["B"], generator=g)
+    return lat, eps
+
+
+def launches_per_rollout(w, T):
+    # trigger: predict + finalize (+ count bump while warming up); lstm: pack_x + embed + L layers + head;
+    # rsample on decision steps
+    n = 0
+    for t in range(T):
+        warm = t < w["window"]
+        n += (3 if warm else 2) + (3 + w["L"]) + (0 if warm else 1)
+    return n
+
+
+def flops_bytes(w, R):
+    G, H, L = w["G"], w["H"], w["L"]
+    f_row = 2 * (G * H + L * (2 * H) * (4 * H) + H * G)
+    b_row = 4 * (2 * (2 * L * H) + 2 * G)
+    return f_row, b_row, 2 * R * (2 * H) * (4 * H)   # last: one LSTM-layer GEMM launch
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from dvg_b200 import _capi
+    from dvg_b200.rollout import RolloutConfig, RolloutEngine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    w = WORKLOADS[args.workload]
+    T = w["n_past"] + w["n_future"] - 1
+    S, B = w["S"], w["B"]
+    R = S * B
+    fp, gp, lik = build_models(w, device, args.variant)
+    eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=w["window"], variant=args.variant))
+    lat_h, eps_h = synth_latents(w, T, R, device, seed=100 + rank)
+    lat_h, eps_h = lat_h.pin_memory(), eps_h.pin_memory()
+    lat, eps = lat_h.to(device), eps_h.to(device)
+    out = torch.empty(T, R, w["G"], device=device)
+    masks = torch.zeros(T, S, dtype=torch.uint8, device=device)
+    graph = eng.capture_latent_rollout(lat, eps, out, masks=masks)
+    # best-of-N selection stand-in for the SSIM selection (generate_frames.py:185-190): per-rollout latent
+    # MSE against the first rollout's context latents, gathered across ranks (the only collective).
+    target = lat[:, :B].clone()
+
+    def select_best():
+        sc = (out.view(T, S, B, -1) - target.view(T, 1, B, -1)).pow(2).mean(dim=(0, 3))   # [S, B]
+        if world > 1:
+            allsc = [torch.empty_like(sc) for _ in range(world)]
+            dist.all_gather(allsc, sc)
+            sc = torch.cat(allsc, 0)
+        return sc.argmin(dim=0)
+
+    def one_step():
+        graph.replay()
+        return select_best()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        best = one_step()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms.item() / args.steps
+    frames_per_step = world * S * B * w["n_future"]
+    value = frames_per_step / (ms_per_step * 1e-3)
+    n_trig = int(masks.sum().item())
+
+    # ---- e2e: public API with pinned HOST buffers, H2D and D2H inside the timed region ----
+    out_h = torch.empty(T, R, w["G"]).pin_memory()
+    best_h = torch.empty(B, dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        lat.copy_(lat_h, non_blocking=True)
+        eps.copy_(eps_h, non_blocking=True)
+        b = one_step()
+        out_h.copy_(out, non_blocking=True)
+        best_h.copy_(b, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = frames_per_step / (ms2.item() / args.steps * 1e-3)
+    h2d = lat_h.numel() * 4 + eps_h.numel() * 4
+    d2h = out_h.numel() * 4 + best_h.numel() * 8
+
+    # ---- roofline: time the dominant kernel (LSTM layer GEMM) live, events between launches ----
+    roof = None
+    if rank == 0:
+        roof = measure_roofline(eng, w, R, lat, args)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_rollout(w, T, budget_s=args.cpu_budget, threads=os.cpu_count())
+    if rank == 0:
+        f_row, b_row, _ = flops_bytes(w, R)
+        line = {
+            "metric": "generated frames/sec (N diverse futures), rollout hot path", "value": value,
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16x3": "fp32-grade (bf16x3 split products, fp32 accumulate)", "bf16": "bf16",
+                      "fp32": "fp32"}[args.variant],
+            "data": "synthetic",
+            "config": {"workload": args.workload + " (BASELINE configs[1]: KTH-shaped, B=50 x S=100 futures per GPU, "
+                       "10 past + 30 future, g_dim 90, rnn 256x2, GP M=40, trigger window 12)",
+                       "rows_per_gpu": R, "time_steps": T, "frames_per_step": frames_per_step,
+                       "row_steps_per_s": world * R * T / (ms_per_step * 1e-3),
+                       "variant": args.variant, "cuda_graph": True,
+                       "l2": "inputs+outputs per rollout = %.0f MB > 126 MB L2" % ((lat.numel() + out.numel()) * 4 / 1e6),
+                       "triggered_rollout_steps": n_trig, "scope": "hot path only; encoder/decoder convs excluded"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_rollout(w, T) * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "hot_path_algorithmic": {"flops_per_row_step": f_row, "bytes_per_row_step": b_row},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_roofline(eng, w, R, lat, args):
+    """Per-kernel device times of one LSTM step, CUDA events recorded between the launches on the
+    launching stream (dvg_lstm_profile), averaged over the bench's K steps x T time steps."""
+    from dvg_b200 import _capi
+    pk, how = peaks()
+    lib = eng.lib
+    if not hasattr(lib, "dvg_lstm_profile"):
+        return None
+    import ctypes
+    n_slots = 3 + w["L"]
+    acc = [0.0] * n_slots
+    reps = 0
+    out = torch.empty(R, w["G"], device=lat.device)
+    ms = (ctypes.c_float * 16)()
+    T = lat.shape[0]
+    for it in range(max(1, min(args.steps, 5))):
+        for t in range(T):
+            nxt = 1 - eng.cur
+            rc = lib.dvg_lstm_profile(eng.lrt.handle, eng.variant, R, _capi.ptr(lat[t]), w["G"],
+                                      _capi.ptr(eng.blocks[eng.cur]), _capi.ptr(eng.blocks[nxt]), _capi.ptr(out), w["G"],
+                                      ms, 16, _capi.stream_ptr())
+            _capi.check(rc, "dvg_lstm_profile")
+            eng.cur = nxt
+            for i in range(n_slots):
+                acc[i] += ms[i]
+            reps += 1
+    per = [a / reps for a in acc]
+    layer_ms = sum(per[2:2 + w["L"]]) / w["L"]
+    _, _, f_layer = flops_bytes(w, R)
+    achieved = f_layer / (layer_ms * 1e-3) / 1e12
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    issued = 3 if args.variant == "bf16x3" else 1
+    return {"bound": "tensor", "kernel": "tc_gemm_kernel<EPI_LSTM> (one LSTM layer, %d rows)" % R,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % how,
+            "traffic": None,
+            "tensor_issue_frac": achieved * issued / peak,
+            "note": "achieved counts ALGORITHMIC flops 2*R*2H*4H per launch; the bf16x3 variant issues 3 "
+                    "tcgen05.mma per algorithmic MMA (tensor_issue_frac = tensor-pipe work actually issued / peak)",
+            "kernel_ms": {"pack_x": per[0], "embed": per[1], "layers": per[2:2 + w["L"]], "head": per[2 + w["L"]]},
+            "lstm_step_ms": sum(per)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_rollout(w, T, budget_s, threads):
+    """Oracle port of the same trigger-mode rollout on the host cores.  The reference loops the S samples
+    sequentially (generate_frames.py:143), so a bounded number of samples is timed and frames/s reported
+    for that sample."""
+    from oracle import gp_ref, lstm_ref, trigger_ref
+    from dvg_b200.init import init_gp_state_dicts, init_lstm_state_dict
+    import numpy as np
+    torch.set_num_threads(threads)
+    sd = init_lstm_state_dict(w["G"], w["G"], w["H"], w["L"], 1)
+    gsd, lsd = init_gp_state_dicts(w["G"], w["M"], 1)
+    B, W = w["B"], w["window"]
+    g = torch.Generator().manual_seed(5)
+    lat = torch.tanh(torch.randn(T, B, w["G"], generator=g))
+    done, t0 = 0, time.perf_counter()
+    with torch.no_grad():
+        while True:
+            hid = lstm_ref.init_hidden(w["L"], B, w["H"])
+            ctx = []
+            for t in range(T):
+                pred = gp_ref.predictive(gsd, lsd, gp_ref.latent_to_gp_input(lat[t]), torch.float32, "gpytorch",
+                                         full_cov=False)
+                v = trigger_ref.trigger_value(pred["variance"].numpy(), min(3, B - 1))
+                fired = False
+                if t < W:
+                    ctx.append(v)
+                else:
+                    c = trigger_ref.slide(np.array(ctx, dtype=np.float32), v)
+                    ctx = list(c)
+                    fired = trigger_ref.decide(c, v)
+                if fired:
+                    pc = gp_ref.predictive(gsd, lsd, gp_ref.latent_to_gp_input(lat[t]), torch.float32, "gpytorch")
+                    gp_ref.rsample(pc["mean"], pc["covar"], torch.randn(w["G"], B))
+                else:
+                    _, hid = lstm_ref.lstm_forward(sd, lat[t], hid)
+            done += 1
+            el = time.perf_counter() - t0
+            if el > budget_s or done >= w["S"]:
+                break
+    return {"value": done * B * w["n_future"] / el, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": "%d of %d samples (sequential in S like generate_frames.py:143), B=%d, %d time steps, %.1f s"
+                      % (done, w["S"], B, T, el)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; /root/reference does
+    not exist on the GPU box and gpytorch is not installable) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    T = w["n_past"] + w["n_future"] - 1
+    threads = os.cpu_count()
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_rollout(w, T, budget_s=min(per_step_budget, 3.0), threads=threads)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_rollout(w, T, budget_s=per_step_budget, threads=threads))
+    el = time.perf_counter() - t0
+    v = sum(x["value"] for x in vals) / len(vals)
+    line = {"impl": "reference", "metric": "generated frames/sec (N diverse futures), rollout hot path",
+            "value": v, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": args.workload, "scope": "hot path only; CPU oracle port, bounded sample per step"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": vals[-1]["sample"]},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--workload", default="kth_s100", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,7 +20,7 @@ EXPORTS = [
     "dvg_last_error", "dvg_version", "dvg_device_info",
     "dvg_lstm_prepare", "dvg_lstm_refresh", "dvg_lstm_destroy", "dvg_lstm_reserve",
     "dvg_lstm_state_bytes", "dvg_lstm_state_packed_offset", "dvg_lstm_state_repack",
-    "dvg_lstm_step", "dvg_gauss_lstm_step",
+    "dvg_lstm_step", "dvg_lstm_profile", "dvg_gauss_lstm_step",
     "dvg_gp_prepare", "dvg_gp_refresh", "dvg_gp_destroy", "dvg_gp_predict", "dvg_gp_trigger",
     "dvg_gp_rsample", "dvg_gp_export",
 ]
@@ -77,6 +77,7 @@ def load():
     lib.dvg_lstm_state_packed_offset.argtypes = [P, c_int]
     lib.dvg_lstm_state_repack.argtypes = [P, c_int, P, P]
     lib.dvg_lstm_step.argtypes = [P, c_int, c_int, P, c_int, P, P, P, c_int, P, c_int, P]
+    lib.dvg_lstm_profile.argtypes = [P, c_int, c_int, P, c_int, P, P, P, c_int, POINTER(c_float), c_int, P]
     lib.dvg_gauss_lstm_step.argtypes = [P, c_int, c_int, P, c_int, P, P, P, P, P, P, P]
     lib.dvg_gp_prepare.argtypes = [POINTER(c_void_p), POINTER(GpDims), P, P, P, P, P, P, P, P]
     lib.dvg_gp_refresh.argtypes = [P, P, P, P, P, P, P, P, P]

@@ -48,6 +48,8 @@ static void lstm_free_all(dvg_lstm_s* h) {
   fr(h->f_embed_wt); fr(h->f_embed_b); fr(h->f_head_wt); fr(h->f_head_b);
   for (int l = 0; l < MAX_LAYERS; ++l) { fr(h->f_layer_wt[l]); fr(h->f_layer_b[l]); }
   fr(h->scratch_e); fr(h->tc_xp); fr(h->tc_ep);
+  for (int i = 0; i < 16; ++i)
+    if (h->prof_ev[i]) { cudaEventDestroy(h->prof_ev[i]); h->prof_ev[i] = nullptr; }
   lstm_tc_free(h);
 }
 
@@ -187,6 +189,26 @@ int dvg_lstm_step(dvg_lstm_t h, int variant, int rows, const float* x, int ldx, 
   DVG_REQUIRE(y && ldy >= h->dims.output_size, "bad y/ldy");
   return lstm_step_common(h, variant, rows, x, ldx, state_in, state_out, y, ldy, nullptr, nullptr, nullptr, nullptr,
                           hold, rows_per_flag, (cudaStream_t)stream);
+}
+
+int dvg_lstm_profile(dvg_lstm_t h, int variant, int rows, const float* x, int ldx, const void* state_in,
+                     void* state_out, float* y, int ldy, float* kernel_ms, int max_slots, dvg_stream_t stream) {
+  DVG_REQUIRE(h && h->dims.kind == DVG_LSTM && kernel_ms && max_slots > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  DVG_REQUIRE(!capturing(s), "dvg_lstm_profile cannot run inside stream capture");
+  for (int i = 0; i < 16; ++i)
+    if (!h->prof_ev[i]) DVG_CUDA(cudaEventCreate(&h->prof_ev[i]));
+  h->prof_on = true;
+  h->prof_n = 0;
+  int rc = lstm_step_common(h, variant, rows, x, ldx, state_in, state_out, y, ldy, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, 0, s);
+  h->prof_on = false;
+  if (rc) return rc;
+  DVG_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < max_slots; ++i) kernel_ms[i] = 0.f;
+  for (int i = 0; i + 1 < h->prof_n && i < max_slots; ++i)
+    DVG_CUDA(cudaEventElapsedTime(&kernel_ms[i], h->prof_ev[i], h->prof_ev[i + 1]));
+  return DVG_OK;
 }
 
 int dvg_gauss_lstm_step(dvg_lstm_t h, int variant, int rows, const float* x, int ldx, const void* state_in,

@@ -7,8 +7,8 @@
 //
 // Per latent dimension d (x = column d of the [N,D] latent):
 //   k_m   = s exp(-0.5 ((x - z_m)/ell)^2)                         (M exps)
-//   mean  = c + sum_m alpha_m k_m                                  alpha = K_ZZ^-1 (m_q - c)       [hoisted]
 //   v     = L_ZZ^-1 k          (triangular mat-vec with the explicit inverse Linv)                 [Linv hoisted]
+//   mean  = c + v . beta                                           beta = L_ZZ^-1 (m_q - c)        [hoisted]
 //   w     = L_q^T k
 //   var   = s - |v|^2 + |w|^2 + noise
 // K_ZZ, its Cholesky factor, Linv and alpha are constant in eval mode; the reference recomputes them on
@@ -90,18 +90,12 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, int mp, d
     }
   }
   __syncthreads();
-  // alpha = L^-T (L^-1 (m_q - c))
-  for (int i = tid; i < M; i += nt) {
+  // beta = L^-1 (m_q - c);  mean = c + (L^-1 k) . beta  (conditioned like L, not like K_ZZ)
+  for (int i = tid; i < mp; i += nt) {
     double t = 0.0;
-    for (int k = 0; k <= i; ++k) t += X[(size_t)i * M + k] * ((double)var_mean[(size_t)d * M + k] - c);
-    tv[i] = t;
-  }
-  __syncthreads();
-  for (int j = tid; j < mp; j += nt) {
-    double a = 0.0;
-    if (j < M)
-      for (int i = j; i < M; ++i) a += X[(size_t)i * M + j] * tv[i];
-    alpha_out[(size_t)d * mp + j] = (float)a;
+    if (i < M)
+      for (int k = 0; k <= i; ++k) t += X[(size_t)i * M + k] * ((double)var_mean[(size_t)d * M + k] - c);
+    alpha_out[(size_t)d * mp + i] = (float)t;
   }
   // fp32 outputs: Linv (lower) and L_q^T (upper), zero padded to mp
   for (int e = tid; e < mp * mp; e += nt) {
@@ -165,7 +159,6 @@ __global__ void __launch_bounds__(128) gp_predict_kernel(int n_rows, int D, int 
     for (int m = 0; m < MREG; ++m) {
       const float t = (xv - s_z[m]) * inv_ell;
       k[m] = s * expf(-0.5f * t * t);   // padded z entries are multiplied by zero factors below
-      mu = fmaf(s_alpha[m], k[m], mu);
     }
 #pragma unroll
     for (int j = 0; j < MREG; ++j) {
@@ -183,13 +176,13 @@ __global__ void __launch_bounds__(128) gp_predict_kernel(int n_rows, int D, int 
       }
       vv = fmaf(v, v, vv);
       ww = fmaf(w, w, ww);
+      mu = fmaf(v, s_alpha[j], mu);
     }
   } else {
     for (int m = 0; m < MP; ++m) {
       const float t = (xv - s_z[m]) * inv_ell;
       const float km = s * expf(-0.5f * t * t);
       s_k[m * 128 + tid] = km;
-      mu = fmaf(s_alpha[m], km, mu);
     }
     for (int j = 0; j < MP; ++j) {
       float v = 0.f, w = 0.f;
@@ -206,6 +199,7 @@ __global__ void __launch_bounds__(128) gp_predict_kernel(int n_rows, int D, int 
       }
       vv = fmaf(v, v, vv);
       ww = fmaf(w, w, ww);
+      mu = fmaf(v, s_alpha[j], mu);
     }
   }
   if (mean) mean[(size_t)i * ldm + d] = c + mu;
@@ -329,9 +323,10 @@ __global__ void __launch_bounds__(128) gp_rsample_kernel(int S, int N, int D, in
     s_u[n * ldk + j] = v;
     s_r[n * ldk + j] = w;
   }
+  __syncthreads();
   for (int n = tid; n < N; n += 128) {
     float mu = 0.f;
-    for (int m = 0; m < MP; ++m) mu = fmaf(alpha_all[(size_t)d * MP + m], s_k[n * ldk + m], mu);
+    for (int j = 0; j < MP; ++j) mu = fmaf(alpha_all[(size_t)d * MP + j], s_u[n * ldk + j], mu);
     s_mean[n] = c + mu;
   }
   __syncthreads();

@@ -46,6 +46,14 @@ struct dvg_lstm_s {
   float* scratch_e = nullptr;    // fp32 [rows][H]: embed output (FFMA variant)
   uint8_t* tc_xp = nullptr;      // packed x            [RT][kbx][2][16 KB]
   uint8_t* tc_ep = nullptr;      // packed embed output [RT][H/64][2][16 KB]
+
+  // --- optional per-kernel timing (dvg_lstm_profile): events recorded between launches ------------
+  bool prof_on = false;
+  int prof_n = 0;
+  cudaEvent_t prof_ev[16] = {};
+  void prof_mark(cudaStream_t s) {
+    if (prof_on && prof_n < 16) cudaEventRecord(prof_ev[prof_n++], s);
+  }
 };
 
 struct dvg_gp_s {
@@ -55,7 +63,7 @@ struct dvg_gp_s {
   float* z = nullptr;         // [D][mp] inducing points
   float* linv = nullptr;      // [D][mp][mp] L_ZZ^-1 (lower triangular, zero padded)
   float* lqt = nullptr;       // [D][mp][mp] L_q^T  (upper triangular: lqt[j][i] = L_q[i][j], i >= j)
-  float* alpha = nullptr;     // [D][mp]
+  float* alpha = nullptr;     // [D][mp] beta = L_ZZ^-1 (m_q - c)
   float* hyp = nullptr;       // [D][4]  ell, s, c, noise
   double* work = nullptr;     // fp64 scratch for prepare [D][3][M][M]
   float* var_rows = nullptr;  // scratch [max_rollouts][D] for the trigger

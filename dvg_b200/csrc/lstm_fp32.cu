@@ -226,8 +226,11 @@ int lstm_fp32_step(dvg_lstm_s* h, int rows, const float* x, int ldx, const float
   a.a0 = x; a.lda0 = ldx; a.k0 = G; a.a1 = nullptr; a.k1 = 0;
   a.wt = h->f_embed_wt; a.ldw = h->hp; a.bias = h->f_embed_b; a.n = H;
   a.out = h->scratch_e; a.ldo = H;
+  h->prof_mark(stream);
+  h->prof_mark(stream);
   ffma_gemm_kernel<EPI_BIAS><<<dim3(rt, h->hp / BN), 256, 0, stream>>>(a);
   DVG_LAUNCH_CHECK();
+  h->prof_mark(stream);
   const float* layer_in = h->scratch_e;
   for (int l = 0; l < L; ++l) {
     FfmaArgs b{};
@@ -239,6 +242,7 @@ int lstm_fp32_step(dvg_lstm_s* h, int rows, const float* x, int ldx, const float
     b.H = H; b.hold = hold; b.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
     ffma_gemm_kernel<EPI_LSTM><<<dim3(rt, 4 * H / BN), 256, 0, stream>>>(b);
     DVG_LAUNCH_CHECK();
+    h->prof_mark(stream);
     layer_in = h_out + l * lsz;
   }
   FfmaArgs c{};
@@ -253,6 +257,7 @@ int lstm_fp32_step(dvg_lstm_s* h, int rows, const float* x, int ldx, const float
     ffma_gemm_kernel<EPI_TANH><<<dim3(rt, h->np_head / BN), 256, 0, stream>>>(c);
   }
   DVG_LAUNCH_CHECK();
+  h->prof_mark(stream);
   return DVG_OK;
 }
 

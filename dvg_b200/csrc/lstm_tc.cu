@@ -489,8 +489,10 @@ int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, c
   const size_t lsz = (size_t)rows * H;
   const size_t lpk = (size_t)RT * hk * 2 * TC_A_IMG;
   int rc;
+  h->prof_mark(stream);
   tc_pack_rows_kernel<<<dim3(RT, kbx), 256, 0, stream>>>(h->tc_xp, x, ldx, rows, G, kbx);
   DVG_LAUNCH_CHECK();
+  h->prof_mark(stream);
   {
     TcArgs a{};
     a.rows = rows; a.row_tiles = RT; a.nsplit = nsplit;
@@ -498,6 +500,7 @@ int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, c
     a.w = h->tc_embed.w; a.bias = h->tc_embed.bias; a.n_tile = h->tc_embed.n_tile; a.n_tiles = h->tc_embed.n_tiles;
     a.out_packed = h->tc_ep; a.out_kb_total = hk;
     if ((rc = launch_tc<EPI_PACK>(h, a, stream))) return rc;
+    h->prof_mark(stream);
   }
   const uint8_t* layer_in = h->tc_ep;
   for (int l = 0; l < L; ++l) {
@@ -508,6 +511,7 @@ int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, c
     a.c_in = c_in + l * lsz; a.h_in = h_in + l * lsz; a.h_out = h_out + l * lsz; a.c_out = c_out + l * lsz;
     a.hp_out = hp_out + l * lpk; a.H = H; a.hold = hold; a.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
     if ((rc = launch_tc<EPI_LSTM>(h, a, stream))) return rc;
+    h->prof_mark(stream);
     layer_in = hp_out + l * lpk;
   }
   {
@@ -523,6 +527,7 @@ int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, c
       if ((rc = launch_tc<EPI_TANH>(h, a, stream))) return rc;
     }
   }
+  h->prof_mark(stream);
   return DVG_OK;
 }
 

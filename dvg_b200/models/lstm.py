@@ -111,7 +111,7 @@ class _Runtime:
         c = f[n:].view(self.L, rows, self.H)
         hidden = [(h[l], c[l]) for l in range(self.L)]
         hidden[0][0]._dvg_block = block          # lets forward() recognise its own state without a copy
-        hidden[0][0]._dvg_versions = None
+        hidden[0][0]._dvg_versions = tuple(t._version for hc in hidden for t in hc)
         return hidden
 
     def block_of(self, hidden, rows):
@@ -128,9 +128,7 @@ class _Runtime:
                     and h.shape == (rows, self.H) and c.shape == (rows, self.H)
             vers = tuple(t._version for hc in hidden for t in hc)
             if ok:
-                if h0._dvg_versions is None:
-                    h0._dvg_versions = vers
-                elif h0._dvg_versions != vers:       # caller wrote into our views in place
+                if h0._dvg_versions != vers:         # caller wrote into our views in place
                     _capi.check(self.lib.dvg_lstm_state_repack(self.handle, rows, _capi.ptr(block),
                                                                _capi.stream_ptr()), "dvg_lstm_state_repack")
                     h0._dvg_versions = vers
@@ -142,6 +140,7 @@ class _Runtime:
         for l in range(self.L):
             views[l][0].copy_(hidden[l][0].detach().to(self.device, torch.float32).reshape(rows, self.H))
             views[l][1].copy_(hidden[l][1].detach().to(self.device, torch.float32).reshape(rows, self.H))
+        views[0][0]._dvg_versions = tuple(t._version for hc in views for t in hc)
         _capi.check(self.lib.dvg_lstm_state_repack(self.handle, rows, _capi.ptr(block), _capi.stream_ptr()),
                     "dvg_lstm_state_repack")
         return block

@@ -1,0 +1,303 @@
+"""Sample-batched rollout drivers: the N-diverse-futures bookkeeping of the reference, re-designed so the
+S futures of a batch run as S*B rows of ONE fused step instead of a sequential python loop.
+
+Reference loops mirrored here (all sizes config-driven instead of the hard-coded 90/50/12/105/15):
+
+* ``generate_frames.py:138-178``  make_gifs pass B: ``for s in range(nsample)`` x ``for i in range(1, n_eval)``
+* ``train.py:262-289``            plot(): the same with nsample=5 and a resample only at i == 10
+* ``generate_frames.py:249-300``  GPtrigger_gen: variance trigger, LSTM not advanced on a triggered step
+* ``generate_frames.py:111-134``  make_gifs pass A: GP mean on the LSTM output
+
+Design
+------
+``RolloutEngine`` owns every buffer of a rollout (two ping-pong LSTM state blocks, the latent output, the
+per-rollout trigger window / value / threshold / mask) and issues, per time step, a fixed sequence of
+C-ABI calls on the current stream with no host synchronisation and no D2H copy:
+
+    trigger:  dvg_gp_trigger   (variance at the statistic row of each rollout -> window -> mask, on device)
+    advance:  dvg_lstm_step    (all S*B rows; ``hold = mask`` keeps the state of triggered rollouts)
+    resample: dvg_gp_rsample   (only CTAs of masked rollouts do work; overwrites their rows of the output)
+
+Because the sequence is static it can be captured in a CUDA graph (``capture_latent_rollout``).
+Rows are laid out rollout-major: row = s * B + b, so one rollout's B points are contiguous (rsample
+correlates exactly those B points, generate_frames.py:171).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+
+TRIGGER_FACTOR = float(np.float32(2 + 0.01 * 1))   # generate_frames.py:288, depth == 1 (:254)
+
+
+@dataclass
+class RolloutConfig:
+    n_points: int                 # B: batch sequences per rollout (N of the GP call)
+    n_rollouts: int               # S: diverse futures resident on this GPU
+    window: int = 12              # generate_frames.py:266 (warm-up length == window length)
+    stat_col: int = 3             # generate_frames.py:230 hard-coded column
+    stat_col_warmup: Optional[Sequence[int]] = None   # generate_frames.py:275 uses ``index``; default = stat_col
+    variant: str = "bf16x3"
+
+
+class RolloutEngine:
+    def __init__(self, frame_predictor, gp_layer, likelihood, cfg: RolloutConfig):
+        self.fp, self.gp, self.lik, self.cfg = frame_predictor, gp_layer, likelihood, cfg
+        self.lib = _capi.load()
+        self.S, self.B = cfg.n_rollouts, cfg.n_points
+        self.R = self.S * self.B
+        self.G = frame_predictor.output_size
+        self.D = gp_layer.num_dims
+        assert frame_predictor.input_size == self.D == self.G, "rollout needs g_dim in == out == GP dims"
+        p = next(frame_predictor.parameters())
+        if not p.is_cuda:
+            raise _capi.DvgError("RolloutEngine needs CUDA modules; there is no CPU fallback")
+        self.dev = p.device
+        self.lrt = frame_predictor._runtime()
+        self.grt = gp_layer._runtime(likelihood)
+        self.variant = _capi.VARIANTS[cfg.variant if frame_predictor.hidden_size % 64 == 0 else "fp32"]
+        _capi.check(self.lib.dvg_lstm_reserve(self.lrt.handle, self.R), "dvg_lstm_reserve")
+        S, B, dev = self.S, self.B, self.dev
+        self.blocks = [self.lrt.new_block(self.R, zero=True), self.lrt.new_block(self.R, zero=True)]
+        self.cur = 0
+        self.window = torch.zeros(S, cfg.window, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.value = torch.zeros(S, device=dev)
+        self.thr = torch.zeros(S, device=dev)
+        self.mask = torch.zeros(S, dtype=torch.uint8, device=dev)
+        base = torch.arange(S, dtype=torch.int32) * B
+        self.stat_rows = (base + cfg.stat_col).to(dev)
+        wcols = cfg.stat_col_warmup if cfg.stat_col_warmup is not None else [cfg.stat_col] * S
+        self.stat_rows_warmup = (base + torch.tensor(list(wcols), dtype=torch.int32)).to(dev)
+        # trigger scratch must exist before any graph capture
+        _capi.check(self.lib.dvg_gp_trigger(self.grt.handle, S, _capi.ptr(torch.zeros(self.R, self.D, device=dev)),
+                                            self.D, _capi.ptr(self.stat_rows), _capi.ptr(self.window), cfg.window,
+                                            _capi.ptr(self.count), 1, TRIGGER_FACTOR, None, None, None,
+                                            _capi.stream_ptr()), "dvg_gp_trigger")
+        self.reset()
+
+    # ---- state -----------------------------------------------------------------------------------
+    def reset(self):
+        """frame_predictor.hidden = init_hidden() + empty trigger window for every rollout."""
+        for b in self.blocks:
+            b.zero_()
+        self.cur = 0
+        self.window.zero_()
+        self.count.zero_()
+        self.mask.zero_()
+
+    def hidden(self):
+        """Current (h, c) views, reference layout (list of L tuples of [S*B, H])."""
+        return self.lrt.views(self.blocks[self.cur], self.R)
+
+    def load_broadcast_state(self, hidden_B):
+        """Broadcast a B-row state (context phase computed once) to all S rollouts."""
+        views = self.lrt.views(self.blocks[self.cur], self.R)
+        for l, (h, c) in enumerate(hidden_B):
+            views[l][0].copy_(h.repeat(self.S, 1))
+            views[l][1].copy_(c.repeat(self.S, 1))
+        _capi.check(self.lib.dvg_lstm_state_repack(self.lrt.handle, self.R, _capi.ptr(self.blocks[self.cur]),
+                                                   _capi.stream_ptr()), "dvg_lstm_state_repack")
+
+    # ---- per-step primitives (async, current stream) ---------------------------------------------
+    def _ld(self, t):
+        assert t.is_cuda and t.dtype == torch.float32 and t.shape == (self.R, self.G) and t.stride(1) == 1
+        return t.stride(0)
+
+    def trigger(self, h, warmup: bool):
+        rows = self.stat_rows_warmup if warmup else self.stat_rows
+        _capi.check(self.lib.dvg_gp_trigger(self.grt.handle, self.S, _capi.ptr(h), self._ld(h), _capi.ptr(rows),
+                                            _capi.ptr(self.window), self.cfg.window, _capi.ptr(self.count),
+                                            1 if warmup else 0, TRIGGER_FACTOR, _capi.ptr(self.value),
+                                            _capi.ptr(self.thr), _capi.ptr(self.mask), _capi.stream_ptr()),
+                    "dvg_gp_trigger")
+
+    def advance(self, h, out, hold: bool):
+        nxt = 1 - self.cur
+        _capi.check(self.lib.dvg_lstm_step(self.lrt.handle, self.variant, self.R, _capi.ptr(h), self._ld(h),
+                                           _capi.ptr(self.blocks[self.cur]), _capi.ptr(self.blocks[nxt]),
+                                           _capi.ptr(out), self._ld(out), _capi.ptr(self.mask) if hold else None,
+                                           self.B, _capi.stream_ptr()), "dvg_lstm_step")
+        self.cur = nxt
+
+    def resample(self, h, eps, out, masked: bool):
+        assert eps.shape == (self.S, self.D, self.B) and eps.is_contiguous()
+        _capi.check(self.lib.dvg_gp_rsample(self.grt.handle, self.S, self.B, _capi.ptr(h), self._ld(h),
+                                            _capi.ptr(eps), _capi.ptr(self.mask) if masked else None, _capi.ptr(out),
+                                            self._ld(out), _capi.stream_ptr()), "dvg_gp_rsample")
+
+    # ---- fused steps -----------------------------------------------------------------------------
+    def step_trigger_mode(self, h, eps, out, warmup: bool):
+        """One GPtrigger_gen step (generate_frames.py:266-298) for all rollouts: ``out`` [S*B, G] receives
+        the decoder input (LSTM prediction, or the GP sample for triggered rollouts)."""
+        self.trigger(h, warmup)
+        self.advance(h, out, hold=not warmup)
+        if not warmup:
+            self.resample(h, eps, out, masked=True)
+
+    def step_manual_mode(self, h, eps, out, resample: bool):
+        """One make_gifs / plot step (generate_frames.py:166-174): LSTM always advances; on a resample step
+        every rollout's decoder input is the GP sample of the *encoder* latent."""
+        self.advance(h, out, hold=False)
+        if resample:
+            self.resample(h, eps, out, masked=False)
+
+    # ---- latent-space rollout (hot path only; the bench / CUDA-graph unit) -------------------------
+    def latent_rollout(self, lat, eps, out, warmup_steps: Optional[int] = None, masks=None, values=None):
+        """Run T trigger-mode steps on pre-computed encoder latents ``lat`` [T, S*B, G] (stand-ins for
+        encoder(x_in)), writing decoder inputs to ``out`` [T, S*B, G].  ``eps`` [T, S, D, B].
+        Optional ``masks`` [T, S] u8 / ``values`` [T, S] record the trigger trace (device copies)."""
+        W = self.cfg.window if warmup_steps is None else warmup_steps
+        for t in range(lat.shape[0]):
+            self.step_trigger_mode(lat[t], eps[t], out[t], warmup=t < W)
+            if masks is not None:
+                masks[t].copy_(self.mask)
+            if values is not None:
+                values[t].copy_(self.value)
+
+    def capture_latent_rollout(self, lat, eps, out, masks=None, values=None):
+        """CUDA-graph the whole T-step latent rollout (static launch sequence, zero host work per replay).
+        T must be even so the ping-pong state returns to block 0; call ``reset()`` semantics are captured
+        too (the graph zeroes state and window first)."""
+        assert lat.shape[0] % 2 == 0 or True
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.reset()
+            self.latent_rollout(lat[:2], eps[:2], out[:2])     # warm the allocator / lazy init outside capture
+            self.reset()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            self.reset()
+            self.latent_rollout(lat, eps, out, masks=masks, values=values)
+        self.cur = 0 if lat.shape[0] % 2 == 0 else 1
+        return g
+
+
+# -------------------------------------------------------------------------------------------------------
+# Pixel-space drivers (encoder / decoder are the reference conv nets on the stock PyTorch path)
+# -------------------------------------------------------------------------------------------------------
+def _rep(t, S):
+    return t.repeat(S, *([1] * (t.dim() - 1)))
+
+
+@torch.no_grad()
+def posterior_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval,
+                      last_frame_skip=False):
+    """generate_frames.py:111-134 (B rows).  Returns the list of n_eval frames."""
+    frame_predictor.hidden = frame_predictor.init_hidden()
+    gen = [x[0]]
+    x_in = x[0]
+    skip = None
+    D = gp_layer.num_dims
+    for i in range(1, n_eval):
+        h, sk = encoder(x_in)
+        if last_frame_skip or i < n_past:
+            skip = sk
+        if i < n_past:
+            frame_predictor(h)
+            x_in = x[i]
+        else:
+            h_pred = frame_predictor(h)
+            pred = likelihood(gp_layer(h_pred.transpose(0, 1).view(D, h_pred.shape[0], 1)))
+            x_in = decoder([pred.mean.transpose(0, 1), skip])
+        gen.append(x_in)
+    return gen
+
+
+@torch.no_grad()
+def diverse_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample,
+                    eps: Optional[Dict] = None, resample_every: Optional[int] = 15,
+                    resample_at: Optional[Sequence[int]] = None, last_frame_skip=False, variant="bf16x3",
+                    record_latents=False):
+    """generate_frames.py:138-178 / train.py:262-289 with the S samples batched.
+
+    The context phase (i < n_past) is identical for every sample (teacher forcing, no randomness), so it
+    is computed once with B rows; its LSTM state is then broadcast to the S*B rows of the engine.
+    ``eps[(s, i)]`` ([D,B]) injects the rsample noise; missing entries are drawn with torch.randn.
+    Returns frames ``gen[t]`` of shape [S, B, C, H, W] (t < n_past: ground truth broadcast)."""
+    B = x[0].shape[0]
+    S = nsample
+    D = gp_layer.num_dims
+    dev = x[0].device
+    frame_predictor.hidden = frame_predictor.init_hidden()
+    skip = None
+    x_in = x[0]
+    i = 1
+    while i < min(n_past, n_eval):
+        h, skip = encoder(x_in)
+        frame_predictor(h)
+        x_in = x[i]
+        i += 1
+    eng = RolloutEngine(frame_predictor, gp_layer, likelihood,
+                        RolloutConfig(n_points=B, n_rollouts=S, variant=variant))
+    eng.load_broadcast_state(frame_predictor.hidden)
+    gens = [_rep(x[t], S).view(S, B, *x[t].shape[1:]) for t in range(i)]
+    lats = [None] * i
+    xs = _rep(x_in, S)
+    skip_s = [_rep(sk, S) for sk in skip] if skip is not None else None
+    out = torch.empty(S * B, D, device=dev)
+    for i in range(i, n_eval):
+        h, sk = encoder(xs)
+        if last_frame_skip or skip_s is None:
+            skip_s = sk
+        hit = (resample_every is not None and i % resample_every == 0) or (resample_at is not None and i in resample_at)
+        e = None
+        if hit:
+            e = torch.stack([(eps[(s, i)] if eps is not None and (s, i) in eps else torch.randn(D, B)).to(dev)
+                             for s in range(S)]).float().contiguous()
+        eng.step_manual_mode(h.contiguous(), e, out, resample=hit)
+        xs = decoder([out, skip_s])
+        gens.append(xs.view(S, B, *xs.shape[1:]))
+        if record_latents:
+            lats.append(out.clone().view(S, B, D))
+    return (gens, lats) if record_latents else gens
+
+
+@torch.no_grad()
+def trigger_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x0, n_rollouts, eps: Optional[Dict] = None,
+                    warmup=12, n_steps=105, stat_col=3, stat_cols_warmup: Optional[Sequence[int]] = None,
+                    skip_until=5, variant="bf16x3"):
+    """generate_frames.py:249-300 with the outer ``for index in range(batch_size)`` loop batched: rollout s
+    plays ``index = stat_cols_warmup[s]``.  ``eps[(s, i)]`` ([D,B]) is the rsample noise of rollout s at a
+    triggered step i.  Returns dict(gen_seq [n_steps][S,B,...], values [n_steps,S], triggers [n_steps,S],
+    latents [n_steps][S,B,D])."""
+    B = x0.shape[0]
+    S = n_rollouts
+    D = gp_layer.num_dims
+    dev = x0.device
+    cols = list(stat_cols_warmup) if stat_cols_warmup is not None else [stat_col] * S
+    eng = RolloutEngine(frame_predictor, gp_layer, likelihood,
+                        RolloutConfig(n_points=B, n_rollouts=S, window=warmup, stat_col=stat_col,
+                                      stat_col_warmup=cols, variant=variant))
+    xs = _rep(x0, S)
+    skip = None
+    out = torch.empty(S * B, D, device=dev)
+    gen_seq, latents = [], []
+    values = torch.empty(n_steps, S, device=dev)
+    trig = torch.zeros(n_steps, S, dtype=torch.uint8, device=dev)
+    zero_eps = torch.zeros(S, D, B, device=dev)
+    for i in range(n_steps):
+        h, sk = encoder(xs)
+        if i < skip_until:
+            skip = sk
+        h = h.contiguous()
+        if i < warmup:
+            e = zero_eps
+        else:
+            e = torch.stack([(eps[(s, i)] if eps is not None and (s, i) in eps else torch.randn(D, B)).to(dev)
+                             for s in range(S)]).float().contiguous()
+        eng.step_trigger_mode(h, e, out, warmup=i < warmup)
+        values[i].copy_(eng.value)
+        trig[i].copy_(eng.mask)
+        xs = decoder([out, skip])
+        gen_seq.append(xs.view(S, B, *xs.shape[1:]))
+        latents.append(out.clone().view(S, B, D))
+    return {"gen_seq": gen_seq, "values": values, "triggers": trig, "latents": latents}

@@ -120,6 +120,16 @@ DVG_API int dvg_lstm_step(dvg_lstm_t h, int variant, int rows,
                   const uint8_t* hold, int rows_per_flag,
                   dvg_stream_t stream);
 
+/* Measurement aid (bench.py roofline): dvg_lstm_step with CUDA events recorded on `stream` between the
+ * kernel launches; synchronises the stream and returns the device time of each launch in kernel_ms
+ * (slots: 0 x-pack [tensor-core variants], 1 embed, 2..L+1 the LSTM layers, L+2 head). */
+DVG_API int dvg_lstm_profile(dvg_lstm_t h, int variant, int rows,
+                     const float* x, int ldx,
+                     const void* state_in, void* state_out,
+                     float* y, int ldy,
+                     float* kernel_ms, int max_slots,
+                     dvg_stream_t stream);
+
 /* One time step of models/lstm.py:166-175; eps [rows, Z] is the N(0,1) draw of :163.
  * Writes z, mu, logvar [rows, Z] (dense). */
 DVG_API int dvg_gauss_lstm_step(dvg_lstm_t h, int variant, int rows,
@@ -140,7 +150,7 @@ typedef struct {
 } dvg_gp_dims;
 
 /* Hoists everything that is constant in eval mode (the reference recomputes it per call): softplus
- * hyper-parameters, K_ZZ + jitter, its Cholesky factor (fp64 on device), L_ZZ^-1, alpha = K_ZZ^-1(m_q - c),
+ * hyper-parameters, K_ZZ + jitter, its Cholesky factor (fp64 on device), L_ZZ^-1, beta = L_ZZ^-1(m_q - c),
  * masked L_q.  Pointers are device pointers in gpytorch 0.3.x state_dict layout:
  *   inducing [D,M,1], var_mean [D,M], chol_var [D,M,M] (raw, upper part ignored), mean_const [D,1],
  *   raw_outputscale [D], raw_lengthscale [D,1,1], raw_noise [D,1]. */
@@ -182,7 +192,7 @@ DVG_API int dvg_gp_rsample(dvg_gp_t h, int n_rollouts, int n_points, const float
 
 /* Debug / test access to the hoisted factors (device->device copies into caller buffers; any may be NULL),
  * with Mp = num_inducing rounded up to a multiple of 4 (zero padded):
- *   linv [D,Mp,Mp] (L_ZZ^-1, lower), lqt [D,Mp,Mp] (masked L_q, transposed), alpha [D,Mp],
+ *   linv [D,Mp,Mp] (L_ZZ^-1, lower), lqt [D,Mp,Mp] (masked L_q, transposed), beta [D,Mp] (= L_ZZ^-1 (m_q - c)),
  *   hyp [D,4] = (ell, s, c, noise). */
 DVG_API int dvg_gp_export(dvg_gp_t h, float* linv, float* lqt, float* alpha, float* hyp, dvg_stream_t stream);
 
