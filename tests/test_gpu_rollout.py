@@ -94,19 +94,44 @@ def test_trigger_rollout_matches_sequential_oracle():
             n_fired += int(trig[i, s])
             assert relerr(got["latents"][i][s], ref["latents"][i]) < 5e-4, (s, i)
             assert relerr(got["gen_seq"][i][s], ref["gen_seq"][i]) < 5e-4, (s, i)
-    assert n_fired > 0, "test inputs never triggered; pick another seed"
+    # (the closed toy loop settles quickly, so triggers are rare here; the trigger -> hold -> rsample
+    #  semantics are pinned by test_latent_trigger_rollout_crafted below)
+
+
+@pytest.mark.parametrize("variant", ["fp32", "bf16x3"])
+def test_latent_trigger_rollout_crafted(variant):
+    """Engine-level GPtrigger_gen semantics with guaranteed triggers: value / window / threshold / decision,
+    LSTM state held on a triggered step, GP sample substituted for the rollouts that fired."""
+    from dvg_b200.rollout import RolloutConfig, RolloutEngine
+    from util import check_latent_rollout, crafted_trigger_case
+    B, S, T, W = 10, 7, 24, 6
+    sd = lstm_ref.random_lstm_state_dict(G, G, H, L, seed=6)
+    gp_sd, lik_sd, lat, eps, jumps = crafted_trigger_case(G, M, B, S, T, W, seed=1)
+    fp = make_lstm(sd, rows=B, variant=variant)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=W, variant=variant))
+    out = torch.empty(T, S * B, G, device="cuda")
+    masks = torch.zeros(T, S, dtype=torch.uint8, device="cuda")
+    values = torch.zeros(T, S, device="cuda")
+    with torch.no_grad():
+        eng.latent_rollout(lat.cuda(), eps.cuda(), out, masks=masks, values=values)
+    torch.cuda.synchronize()
+    checked, fired = check_latent_rollout(sd, gp_sd, lik_sd, lat, eps, out.cpu(), masks.cpu(), values.cpu(), B, W)
+    assert checked > 100
+    # a jump fires unless an earlier jump of the same rollout still sits in the 6-step window
+    assert fired >= 4, (fired, sorted(jumps), masks.cpu().nonzero().tolist())
 
 
 def test_cuda_graph_latent_rollout_equals_eager():
     from dvg_b200.rollout import RolloutConfig, RolloutEngine
-    sd, gp_sd, lik_sd = _models(seed=5)
-    B, S, T, W = 10, 12, 16, 5
+    from util import crafted_trigger_case
+    B, S, T, W = 10, 12, 16, 6      # a single outlier can only fire for window >= 6 (1/W + 2.01 sqrt(W-1)/W < 1)
+    sd = lstm_ref.random_lstm_state_dict(G, G, H, L, seed=5)
+    gp_sd, lik_sd, lat, eps, jumps = crafted_trigger_case(G, M, B, S, T, W, seed=2)
     fp = make_lstm(sd, rows=B, variant="bf16x3")
     gp, lik = make_gp(gp_sd, lik_sd)
     eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=W))
-    g = torch.Generator().manual_seed(2)
-    lat = torch.tanh(torch.randn(T, S * B, G, generator=g) * torch.linspace(0.3, 1.6, T).reshape(T, 1, 1)).cuda()
-    eps = torch.randn(T, S, G, B, generator=g).cuda()
+    lat, eps = lat.cuda(), eps.cuda()
     out_e = torch.empty(T, S * B, G, device="cuda")
     m_e = torch.zeros(T, S, dtype=torch.uint8, device="cuda")
     with torch.no_grad():

@@ -34,3 +34,67 @@ def make_gp(gp_sd, lik_sd):
 
 
 TOL = {"fp32": 2e-5, "bf16x3": 1e-4, "bf16": 2e-2}
+
+
+def crafted_trigger_case(G, M, B, S, T, W, seed=0, n_jumps=6):
+    """GP whose inducing points cover only (0.5, 1): with L_q ~ 0.5 I the |L_q^T k|^2 term makes the
+    predictive variance several times larger inside that range than far from it.  Base latents live near
+    -0.8 (low variance); at a few (t, s) pairs after the warm-up the whole rollout jumps into (0.55, 0.95),
+    which makes the variance statistic jump up and the trigger fire with a wide margin.  Returns (gp_sd, lik_sd, lat [T,S*B,G], eps [T,S,G,B], jumps)."""
+    from oracle import gp_ref
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(G, M, seed=seed + 50, trained_like=True, smooth_mean=True)
+    gp_sd[gp_ref.K_INDUCING] = gp_sd[gp_ref.K_INDUCING].abs() * 0.5 + 0.5
+    g = torch.Generator().manual_seed(seed)
+    lat = -0.8 + 0.1 * torch.tanh(torch.randn(T, S * B, G, generator=g))
+    jumps = set()
+    while len(jumps) < n_jumps:
+        t = int(torch.randint(W, T, (1,), generator=g))
+        s = int(torch.randint(0, S, (1,), generator=g))
+        if all(abs(t - t2) > 1 or s != s2 for t2, s2 in jumps):
+            jumps.add((t, s))
+    for t, s in jumps:
+        lat[t, s * B:(s + 1) * B] = 0.75 + 0.2 * torch.tanh(torch.randn(B, G, generator=g))
+    eps = torch.randn(T, S, G, B, generator=g)
+    return gp_sd, lik_sd, lat, eps, jumps
+
+
+def check_latent_rollout(sd, gp_sd, lik_sd, lat, eps, out, masks, values, B, W, stat_col=3, tol=3e-4):
+    """Replay a latent-space trigger rollout on the CPU oracle, one rollout at a time (the reference's
+    sequential loop, generate_frames.py:249-300), following the device's decisions where the statistic is
+    within tolerance of the threshold and asserting them elsewhere.  Returns (#checked decisions, #fired)."""
+    import numpy as np
+    from oracle import gp_ref, lstm_ref, trigger_ref
+    T = lat.shape[0]
+    S = lat.shape[1] // B
+    L = len([k for k in sd if k.endswith("weight_ih")])
+    H = sd["embed.weight"].shape[0]
+    checked = fired_n = 0
+    for s in range(S):
+        hid = lstm_ref.init_hidden(L, B, H)
+        ctx = []
+        for t in range(T):
+            h = lat[t, s * B:(s + 1) * B]
+            pred = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h), torch.float32, "gpytorch",
+                                     full_cov=False)
+            v = trigger_ref.trigger_value(pred["variance"].numpy(), stat_col)
+            assert abs(values[t, s].item() - float(v)) <= 1e-4 * abs(float(v)), (t, s)
+            fired = False
+            if t < W:
+                ctx.append(v)
+                assert not bool(masks[t, s])
+            else:
+                c = trigger_ref.slide(np.array(ctx, dtype=np.float32), v)
+                ctx = list(c)
+                thr = trigger_ref.threshold(c)
+                if abs(float(v) - float(thr)) > 1e-4 * abs(float(thr)):
+                    assert bool(masks[t, s]) == bool(v > thr), (t, s, float(v), float(thr))
+                    checked += 1
+                fired = bool(masks[t, s])
+                fired_n += int(fired)
+            if fired:   # rsample of the encoder latent; LSTM state NOT advanced (generate_frames.py:289-292)
+                pc = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h), torch.float64, "direct")
+                want = gp_ref.rsample(pc["mean"], pc["covar"], eps[t, s].double()).transpose(0, 1).float()
+            else:
+                want, hid = lstm_ref.lstm_forward(sd, h, hid)
+            assert relerr(out[t, s * B:(s + 1) * B], want) < tol, (t, s, fired)
+    return checked, fired_n
