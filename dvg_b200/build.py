@@ -18,6 +18,8 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-Xptxas", "-v", "-cudart", "static",
 ]
+if os.environ.get("DVG_TRACE"):          # developer build: per-CTA timestamps in the tensor-core kernel
+    NVCC_FLAGS.append("-DDVG_TRACE")
 
 
 def _nvcc() -> str:

@@ -16,11 +16,15 @@
 // TMEM) -- products carry ~16 mantissa bits, i.e. fp32-grade for the <=1e-4 parity bar.
 // DVG_BF16:   D += A_hi*B_hi only.
 //
-// Kernel structure (192 threads, 1 CTA / SM, persistent over (row tile, N tile) pairs):
+// Kernel structure (320 threads, 1 CTA / SM, persistent over (row tile, N tile) pairs):
 //   warp 0     TMA producer: one lane issues the bulk copies of each k-block stage
 //   warp 1     TMEM allocator + MMA issuer: one lane issues tcgen05.mma, commits to mbarriers
-//   warps 2-5  epilogue: tcgen05.ld the accumulator (lane = row), fused pointwise math, global stores
+//   warps 2-9  epilogue: tcgen05.ld the accumulator (lane = row; two warps per TMEM lane quarter split the
+//              columns), fused pointwise math with the bias staged in smem and c prefetched, global stores
+// Clusters of up to 4 CTAs (consecutive row tiles, same N tile) share each weight k-block via TMA multicast.
 // Two TMEM accumulator buffers (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "internal.cuh"
 #include "ptx.cuh"
 
@@ -34,7 +38,7 @@ struct TcArgs {
   const uint8_t* a1; int kb1;
   const uint8_t* w;
   const float* bias;
-  int n_tile, n_tiles, nsplit, stages;
+  int n_tile, n_tiles, nsplit, stages, cm;
   // EPI_PACK
   uint8_t* out_packed; int out_kb_total;
   // EPI_LSTM
@@ -44,11 +48,51 @@ struct TcArgs {
   float* y; int ldy; int n_valid;
   // EPI_GAUSS
   const float* eps; float* z; float* mu; float* logvar; int Z;
+  unsigned long long* trace;  // DVG_TRACE builds only: per-CTA timestamps
 };
 
-constexpr int TC_THREADS = 192;
+#ifdef DVG_TRACE
+#define TRACE(slot)                                                                   \
+  do {                                                                                \
+    if (p.trace) {                                                                    \
+      unsigned long long _t;                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                          \
+      p.trace[(size_t)blockIdx.x * 32 + (slot)] = _t;                                 \
+    }                                                                                 \
+  } while (0)
+#else
+#define TRACE(slot) do {} while (0)
+#endif
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator buffer
+
+// Thread-per-row accesses touch 32 different 128-byte lines per warp instruction, and the L1TEX cost is per
+// line touched, not per byte: use the 256-bit LDG/STG of sm_100 so each line is visited as rarely as possible.
+__device__ __forceinline__ void ld256(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st256u(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
+  ld256(p, v);
+  ld256(p + 8, v + 8);
+}
+__device__ __forceinline__ void store16(float* p, const float (&v)[16]) {
+  st256(p, v);
+  st256(p + 8, v + 8);
+}
 
 __device__ __forceinline__ void store_split16(uint8_t* img_hi, uint32_t r_in_tile, uint32_t chunk0, const float (&v)[16]) {
   // 16 consecutive K elements of one row -> two 16-byte chunks in the hi image and two in the lo image.
@@ -62,13 +106,41 @@ __device__ __forceinline__ void store_split16(uint8_t* img_hi, uint32_t r_in_til
     lo[i] = pack2_bf16(l0, l1);
   }
   uint8_t* img_lo = img_hi + TC_A_IMG;
+  // chunk0 is even: the swizzled positions of chunks {chunk0, chunk0+1} form one aligned 32-byte sector,
+  // in swapped order when bit 0 of (row & 7) is set -> one 256-bit store per image.
   const uint32_t o0 = sw128_offset(r_in_tile, chunk0), o1 = sw128_offset(r_in_tile, chunk0 + 1);
-  *reinterpret_cast<uint4*>(img_hi + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(img_hi + o1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-  *reinterpret_cast<uint4*>(img_lo + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  *reinterpret_cast<uint4*>(img_lo + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  const bool swap = o1 < o0;
+  const uint32_t ob = swap ? o1 : o0;
+  uint32_t th[8], tl[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    th[i] = swap ? hi[4 + i] : hi[i];
+    th[4 + i] = swap ? hi[i] : hi[4 + i];
+    tl[i] = swap ? lo[4 + i] : lo[i];
+    tl[4 + i] = swap ? lo[i] : lo[4 + i];
+  }
+  st256u(img_hi + ob, th);
+  st256u(img_lo + ob, tl);
 }
 
+// LSTM pointwise math for 16 hidden units of one row (i,f,g,o pre-activations in r[0..63]).
+__device__ __forceinline__ void lstm_pointwise16(const uint32_t (&r)[64], const float* sb, int cb, const float (&cp)[16],
+                                                 float (&hn)[16], float (&cn)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float gi = sigmoid_f(__uint_as_float(r[i]) + sb[cb + i]);
+    const float gf = sigmoid_f(__uint_as_float(r[16 + i]) + sb[64 + cb + i]);
+    const float gg = tanh_f(__uint_as_float(r[32 + i]) + sb[128 + cb + i]);
+    const float go = sigmoid_f(__uint_as_float(r[48 + i]) + sb[192 + cb + i]);
+    cn[i] = fmaf(gf, cp[i], gi * gg);
+    hn[i] = go * tanh_f(cn[i]);
+  }
+}
+// Cluster of CM CTAs along the row-tile axis: the CM CTAs of a cluster work on CM consecutive row tiles
+// and the SAME N tile, so the weight k-block images are identical for all of them -- each CTA fetches
+// 1/CM of every weight image and TMA-multicasts it into all CM shared memories (L2 -> SM traffic for the
+// dominant operand drops by CM).  Activation images are private.  A smem stage is recycled only after the
+// MMAs of ALL CM CTAs that read it have retired (multicast tcgen05.commit onto every CTA's empty barrier).
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -76,6 +148,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B images need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.kb0 + p.kb1;
+  const int CM = p.cm;
+  const uint32_t rank = CM > 1 ? ptx::cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << CM) - 1u);
   const uint32_t b_part = (uint32_t)p.n_tile * 128u;
   const uint32_t stage_bytes = 2u * TC_A_IMG + 2u * b_part;
   const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
@@ -84,15 +159,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base - raw) + 128);  // [2][256] floats
 
   if (threadIdx.x == 0) {
+    TRACE(0);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), (uint32_t)CM);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 4);
+      ptx::mbar_init(tempty_bar(a), EPI_WARPS);
     }
     ptx::fence_barrier_init();
   }
@@ -102,30 +179,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CM > 1) ptx::cluster_sync_all();   // remote CTAs must see initialised barriers before any multicast
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) TRACE(1);
 
-  const int num_tiles = p.row_tiles * p.n_tiles;
+  // cluster-tile schedule: ct -> (row-tile group, N tile); this CTA's row tile = group*CM + rank
+  const int groups = (p.row_tiles + CM - 1) / CM;
+  const int num_ct = groups * p.n_tiles;
+  const int cid = CM > 1 ? (int)ptx::cluster_id_x() : (int)blockIdx.x;
+  const int ncl = CM > 1 ? (int)ptx::cluster_count_x() : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t a_copy = p.nsplit == 1 ? (uint32_t)TC_A_IMG : 2u * TC_A_IMG;
       const uint32_t b_copy = p.nsplit == 1 ? b_part : 2u * b_part;
+      const uint32_t slice = b_part / (uint32_t)CM;
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int rt = t / p.n_tiles, nt = t % p.n_tiles;
+      for (int ct = cid; ct < num_ct; ct += ncl) {
+        const int nt = ct % p.n_tiles;
+        int rt = (ct / p.n_tiles) * CM + (int)rank;
+        if (rt >= p.row_tiles) rt = p.row_tiles - 1;   // padding CTA of the last group: loads stay in bounds
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
           const uint8_t* asrc = kb < p.kb0 ? p.a0 + (size_t)(rt * p.kb0 + kb) * (2u * TC_A_IMG)
                                            : p.a1 + (size_t)(rt * p.kb1 + (kb - p.kb0)) * (2u * TC_A_IMG);
           const uint8_t* bsrc = p.w + (size_t)(nt * KB + kb) * (2u * b_part);
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + 2u * TC_A_IMG;
           ptx::mbar_expect_tx(full_bar(s), a_copy + b_copy);
           ptx::bulk_g2s(sa, asrc, a_copy, full_bar(s));
-          ptx::bulk_g2s(sa + 2u * TC_A_IMG, bsrc, b_copy, full_bar(s));
+          if (CM == 1) {
+            ptx::bulk_g2s(sb, bsrc, b_copy, full_bar(s));
+          } else {
+            const uint32_t off = rank * slice;
+            ptx::bulk_g2s_mcast(sb + off, bsrc + off, slice, full_bar(s), cmask);
+            if (p.nsplit != 1) ptx::bulk_g2s_mcast(sb + b_part + off, bsrc + b_part + off, slice, full_bar(s), cmask);
+          }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -137,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int ct = cid; ct < num_ct; ct += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t aph = (uint32_t)(it >> 1) & 1u;
         ptx::mbar_wait(tempty_bar(acc), aph ^ 1u);
@@ -145,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(full_bar(s), ph);
+          if (it < 2) TRACE(2 + it * 12 + kb);     // stage kb of tile `it` landed
           ptx::tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint64_t a_hi = ptx::make_sw128_desc(sa);
@@ -160,85 +254,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
               ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
             }
           }
-          ptx::umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+          // free the smem stage (in every CTA of the cluster: our multicast slices live there too)
+          if (CM == 1) ptx::umma_commit(empty_bar(s));
+          else ptx::umma_commit_mcast(empty_bar(s), cmask);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         ptx::umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (it < 2) TRACE(2 + it * 12 + 8);        // all MMAs of tile `it` issued
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2 .. 2+EPI_WARPS-1) =====================
+    const int ew = warp - 2;
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                      // two warps share a lane quarter and split the columns
     const uint32_t r_in_tile = (uint32_t)(q * 32 + lane);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const int etid = ew * 32 + lane;               // 0 .. 255
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int rt = t / p.n_tiles, nt = t % p.n_tiles;
+    for (int ct = cid; ct < num_ct; ct += ncl, ++it) {
+      const int nt = ct % p.n_tiles;
+      const int rt = (ct / p.n_tiles) * CM + (int)rank;
       const int acc = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      ptx::mbar_wait(tfull_bar(acc), aph);
-      ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + tlane + (uint32_t)(acc * ACC_STRIDE);
       const int row = rt * TC_ROWS + (int)r_in_tile;
       const bool valid = row < p.rows;
+      float* sb = s_bias + acc * 256;
+      // stage this tile's bias and prefetch the first c chunk while the MMAs are still running
+      if (etid < p.n_tile) sb[etid] = __ldg(p.bias + (size_t)nt * p.n_tile + etid);
+      float cp[16];
+      size_t idx0 = 0;
+      bool held = false;
+      if (EPI == EPI_LSTM) {
+        idx0 = (size_t)row * p.H + nt * 64 + half * 32;
+        held = valid && p.hold != nullptr && p.hold[row / p.rows_per_flag] != 0;
+        if (valid) load16(p.c_in + idx0, cp);
+      }
+      ptx::named_bar_sync(1, EPI_WARPS * 32);
+      ptx::mbar_wait(tfull_bar(acc), aph);
+      if (etid == 0 && it < 2) TRACE(2 + it * 12 + 9);   // accumulator ready
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + tlane + (uint32_t)(acc * ACC_STRIDE);
 
       if (EPI == EPI_LSTM) {
-        // tile columns: [i: 64 units][f: 64][g: 64][o: 64] of hidden units nt*64 .. nt*64+63
-        const bool held = valid && p.hold != nullptr && p.hold[row / p.rows_per_flag] != 0;
+        // tile columns: [i: 64 units][f: 64][g: 64][o: 64] of hidden units nt*64 .. nt*64+63;
+        // this warp handles units half*32 .. half*32+31 in two chunks of 16
         uint8_t* img = p.hp_out + (size_t)(rt * (p.H / 64) + nt) * (2u * TC_A_IMG);
-        const float* bias = p.bias + (size_t)nt * 256;
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int cb = half * 32 + jj * 16;       // first unit of the chunk within the tile
+          float cnext[16];
+          if (jj == 0 && valid) load16(p.c_in + idx0 + 16, cnext);
           uint32_t r[64];
-          ptx::tmem_ld16x4_wait(tacc + j * 16, tacc + 64 + j * 16, tacc + 128 + j * 16, tacc + 192 + j * 16, r);
+          ptx::tmem_ld16x4_wait(tacc + cb, tacc + 64 + cb, tacc + 128 + cb, tacc + 192 + cb, r);
           if (valid) {
-            const size_t idx = (size_t)row * p.H + nt * 64 + j * 16;
-            float cp[16], hn[16], cn[16];
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              const float4 c4 = *reinterpret_cast<const float4*>(p.c_in + idx + v4 * 4);
-              cp[v4 * 4 + 0] = c4.x; cp[v4 * 4 + 1] = c4.y; cp[v4 * 4 + 2] = c4.z; cp[v4 * 4 + 3] = c4.w;
-            }
+            const size_t idx = idx0 + jj * 16;
+            float hn[16], cn[16];
             if (held) {
-#pragma unroll
-              for (int v4 = 0; v4 < 4; ++v4) {
-                const float4 h4 = *reinterpret_cast<const float4*>(p.h_in + idx + v4 * 4);
-                hn[v4 * 4 + 0] = h4.x; hn[v4 * 4 + 1] = h4.y; hn[v4 * 4 + 2] = h4.z; hn[v4 * 4 + 3] = h4.w;
-              }
+              load16(p.h_in + idx, hn);
 #pragma unroll
               for (int i = 0; i < 16; ++i) cn[i] = cp[i];
             } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int cb = j * 16 + i;
-                const float gi = sigmoid_f(__uint_as_float(r[i]) + __ldg(bias + cb));
-                const float gf = sigmoid_f(__uint_as_float(r[16 + i]) + __ldg(bias + 64 + cb));
-                const float gg = tanh_f(__uint_as_float(r[32 + i]) + __ldg(bias + 128 + cb));
-                const float go = sigmoid_f(__uint_as_float(r[48 + i]) + __ldg(bias + 192 + cb));
-                cn[i] = fmaf(gf, cp[i], gi * gg);
-                hn[i] = go * tanh_f(cn[i]);
-              }
+              lstm_pointwise16(r, sb, cb, cp, hn, cn);
             }
+            store16(p.c_out + idx, cn);
+            store16(p.h_out + idx, hn);
+            store_split16(img, r_in_tile, (uint32_t)(cb >> 3), hn);
+            if (jj == 0) {
 #pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              *reinterpret_cast<float4*>(p.c_out + idx + v4 * 4) =
-                  make_float4(cn[v4 * 4], cn[v4 * 4 + 1], cn[v4 * 4 + 2], cn[v4 * 4 + 3]);
-              *reinterpret_cast<float4*>(p.h_out + idx + v4 * 4) =
-                  make_float4(hn[v4 * 4], hn[v4 * 4 + 1], hn[v4 * 4 + 2], hn[v4 * 4 + 3]);
+              for (int i = 0; i < 16; ++i) cp[i] = cnext[i];
             }
-            store_split16(img, r_in_tile, (uint32_t)(j * 2), hn);
           }
         }
       } else {
         const int nchunks = p.n_tile / 16;
 #pragma unroll 1
-        for (int j = 0; j < nchunks; ++j) {
+        for (int j = half; j < nchunks; j += 2) {
           float v[16];
           ptx::tmem_ld16_wait(tacc + j * 16, v);
           if (valid) {
             const int col0 = nt * p.n_tile + j * 16;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + col0 + i);
+            for (int i = 0; i < 16; ++i) v[i] += sb[j * 16 + i];
             if (EPI == EPI_PACK) {
               uint8_t* img = p.out_packed + (size_t)(rt * p.out_kb_total + (col0 >> 6)) * (2u * TC_A_IMG);
               store_split16(img, r_in_tile, (uint32_t)((col0 & 63) >> 3), v);
@@ -264,14 +361,274 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (etid == 0 && it < 2) TRACE(2 + it * 12 + 10);  // epilogue of warp 2 done
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(30);
+  if (CM > 1) ptx::cluster_sync_all();   // no CTA may exit while peers can still multicast into it
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// cta_group::2 version: a CTA PAIR owns a 256-row x n_tile tile.  Each CTA stages its own 128 activation
+// rows and HALF of the weight image (n_tile/2 columns); the leader's tcgen05.mma.cta_group::2 drives both
+// tensor cores, each accumulating its 128 rows x n_tile columns in its own TMEM.  Per CTA this halves the
+// weight bytes read from shared memory per MMA (96 -> 64 B/clk) and the stage size (96 -> 64 KB, so three
+// stages fit): the 1-CTA kernel above is shared-memory-bandwidth bound (operand reads + TMA fill > 128 B/clk).
+//   full[s]   (per CTA)  own TMA bytes landed
+//   pfull[s]  (leader)   peer's stage landed  -- relayed by the peer's otherwise idle MMA warp
+//   empty[s]  (per CTA)  multicast tcgen05.commit of the leader: stage free in both CTAs
+//   tfull[a]  (per CTA)  multicast commit: accumulator a complete in both TMEMs
+//   tempty[a] (leader)   all epilogue warps of BOTH CTAs drained accumulator a
+// ---------------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm2_kernel(const TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.kb0 + p.kb1;
+  constexpr int CM = 2;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t b_half = (uint32_t)p.n_tile * 64u;          // bytes of this CTA's half of one weight image part
+  const uint32_t b_part = (uint32_t)p.n_tile * 128u;         // bytes of a full weight image part in HBM
+  const uint32_t stage_bytes = 2u * TC_A_IMG + 2u * b_half;
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * p.stages + 4);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base - raw) + 128);  // [2][256] floats
+
+  if (threadIdx.x == 0) {
+    TRACE(0);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(pfull_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), 2 * EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) TRACE(1);
+
+  const int groups = (p.row_tiles + CM - 1) / CM;
+  const int num_ct = groups * p.n_tiles;
+  const int cid = (int)ptx::cluster_id_x();
+  const int ncl = (int)ptx::cluster_count_x();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t a_copy = p.nsplit == 1 ? (uint32_t)TC_A_IMG : 2u * TC_A_IMG;
+      const uint32_t nparts = p.nsplit == 1 ? 1u : 2u;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ct = cid; ct < num_ct; ct += ncl) {
+        const int nt = ct % p.n_tiles;
+        int rt = (ct / p.n_tiles) * CM + (int)rank;
+        if (rt >= p.row_tiles) rt = p.row_tiles - 1;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint8_t* asrc = kb < p.kb0 ? p.a0 + (size_t)(rt * p.kb0 + kb) * (2u * TC_A_IMG)
+                                           : p.a1 + (size_t)(rt * p.kb1 + (kb - p.kb0)) * (2u * TC_A_IMG);
+          const uint8_t* bsrc = p.w + (size_t)(nt * KB + kb) * (2u * b_part) + rank * b_half;
+          const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + 2u * TC_A_IMG;
+          ptx::mbar_expect_tx(full_bar(s), a_copy + nparts * b_half);
+          ptx::bulk_g2s(sa, asrc, a_copy, full_bar(s));
+          ptx::bulk_g2s(sb, bsrc, b_half, full_bar(s));
+          if (nparts == 2) ptx::bulk_g2s(sb + b_half, bsrc + b_part, b_half, full_bar(s));
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (rank == 0) {
+        // ===================== MMA issuer (leader CTA) =====================
+        const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, p.n_tile);
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int ct = cid; ct < num_ct; ct += ncl, ++it) {
+          const int acc = it & 1;
+          const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+          ptx::mbar_wait(tempty_bar(acc), aph ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_wait(full_bar(s), ph);
+            ptx::mbar_wait(pfull_bar(s), ph);
+            if (it < 2) TRACE(2 + it * 12 + kb);
+            ptx::tc_fence_after();
+            const uint32_t sa = base + (uint32_t)s * stage_bytes;
+            const uint64_t a_hi = ptx::make_sw128_desc(sa);
+            const uint64_t a_lo = ptx::make_sw128_desc(sa + TC_A_IMG);
+            const uint64_t b_hi = ptx::make_sw128_desc(sa + 2u * TC_A_IMG);
+            const uint64_t b_lo = ptx::make_sw128_desc(sa + 2u * TC_A_IMG + b_half);
+#pragma unroll
+            for (int k = 0; k < TC_KBLK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              ptx::umma2_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (p.nsplit != 1) {
+                ptx::umma2_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                ptx::umma2_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+            ptx::umma2_commit_mcast(empty_bar(s), 3);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+          ptx::umma2_commit_mcast(tfull_bar(acc), 3);
+          if (it < 2) TRACE(2 + it * 12 + 8);
+        }
+      } else {
+        // ===================== relay (peer CTA): "my stage landed" -> leader's pfull =====================
+        int s = 0;
+        uint32_t ph = 0;
+        for (int ct = cid; ct < num_ct; ct += ncl) {
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_wait(full_bar(s), ph);
+            ptx::mbar_arrive_remote(pfull_bar(s), 0);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2 .. 2+EPI_WARPS-1) =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                      // two warps share a lane quarter and split the columns
+    const uint32_t r_in_tile = (uint32_t)(q * 32 + lane);
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const int etid = ew * 32 + lane;               // 0 .. 255
+    int it = 0;
+    for (int ct = cid; ct < num_ct; ct += ncl, ++it) {
+      const int nt = ct % p.n_tiles;
+      const int rt = (ct / p.n_tiles) * CM + (int)rank;
+      const int acc = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      const int row = rt * TC_ROWS + (int)r_in_tile;
+      const bool valid = row < p.rows;
+      float* sb = s_bias + acc * 256;
+      // stage this tile's bias and prefetch the first c chunk while the MMAs are still running
+      if (etid < p.n_tile) sb[etid] = __ldg(p.bias + (size_t)nt * p.n_tile + etid);
+      float cp[16];
+      size_t idx0 = 0;
+      bool held = false;
+      if (EPI == EPI_LSTM) {
+        idx0 = (size_t)row * p.H + nt * 64 + half * 32;
+        held = valid && p.hold != nullptr && p.hold[row / p.rows_per_flag] != 0;
+        if (valid) load16(p.c_in + idx0, cp);
+      }
+      ptx::named_bar_sync(1, EPI_WARPS * 32);
+      ptx::mbar_wait(tfull_bar(acc), aph);
+      if (etid == 0 && it < 2) TRACE(2 + it * 12 + 9);   // accumulator ready
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + tlane + (uint32_t)(acc * ACC_STRIDE);
+
+      if (EPI == EPI_LSTM) {
+        // tile columns: [i: 64 units][f: 64][g: 64][o: 64] of hidden units nt*64 .. nt*64+63;
+        // this warp handles units half*32 .. half*32+31 in two chunks of 16
+        uint8_t* img = p.hp_out + (size_t)(rt * (p.H / 64) + nt) * (2u * TC_A_IMG);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int cb = half * 32 + jj * 16;       // first unit of the chunk within the tile
+          float cnext[16];
+          if (jj == 0 && valid) load16(p.c_in + idx0 + 16, cnext);
+          uint32_t r[64];
+          ptx::tmem_ld16x4_wait(tacc + cb, tacc + 64 + cb, tacc + 128 + cb, tacc + 192 + cb, r);
+          if (valid) {
+            const size_t idx = idx0 + jj * 16;
+            float hn[16], cn[16];
+            if (held) {
+              load16(p.h_in + idx, hn);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) cn[i] = cp[i];
+            } else {
+              lstm_pointwise16(r, sb, cb, cp, hn, cn);
+            }
+            store16(p.c_out + idx, cn);
+            store16(p.h_out + idx, hn);
+            store_split16(img, r_in_tile, (uint32_t)(cb >> 3), hn);
+            if (jj == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) cp[i] = cnext[i];
+            }
+          }
+        }
+      } else {
+        const int nchunks = p.n_tile / 16;
+#pragma unroll 1
+        for (int j = half; j < nchunks; j += 2) {
+          float v[16];
+          ptx::tmem_ld16_wait(tacc + j * 16, v);
+          if (valid) {
+            const int col0 = nt * p.n_tile + j * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += sb[j * 16 + i];
+            if (EPI == EPI_PACK) {
+              uint8_t* img = p.out_packed + (size_t)(rt * p.out_kb_total + (col0 >> 6)) * (2u * TC_A_IMG);
+              store_split16(img, r_in_tile, (uint32_t)((col0 & 63) >> 3), v);
+            } else if (EPI == EPI_TANH) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col0 + i < p.n_valid) p.y[(size_t)row * p.ldy + col0 + i] = tanh_f(v[i]);
+            } else {  // EPI_GAUSS: columns (2z, 2z+1) = (mu_z, logvar_z)
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const int zi = (col0 + i) >> 1;
+                if (zi < p.Z) {
+                  const size_t idx = (size_t)row * p.Z + zi;
+                  p.mu[idx] = v[i];
+                  p.logvar[idx] = v[i + 1];
+                  p.z[idx] = fmaf(p.eps[idx], expf(0.5f * v[i + 1]), v[i]);
+                }
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+        else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+      if (etid == 0 && it < 2) TRACE(2 + it * 12 + 10);  // epilogue of warp 2 done
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) TRACE(30);
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
   }
 }
 
@@ -459,24 +816,92 @@ int lstm_tc_repack_state(dvg_lstm_s* h, int rows, const float* h_f32, uint8_t* h
   return DVG_OK;
 }
 
+static bool use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVG_TC_PAIRS");     // developer switch: 0 forces the 1-CTA (multicast) kernel
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 template <int EPI>
 static int launch_tc(const dvg_lstm_s* h, TcArgs& a, cudaStream_t stream) {
-  const size_t stage_bytes = 2 * (size_t)TC_A_IMG + 2 * (size_t)a.n_tile * 128;
-  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
+  const bool pairs = use_pairs() && a.row_tiles >= 2 && a.n_tile % 32 == 0;
+  const size_t b_stage = pairs ? (size_t)a.n_tile * 128 : 2 * (size_t)a.n_tile * 128;
+  const size_t stage_bytes = 2 * (size_t)TC_A_IMG + b_stage;
+  const size_t tail = 128 /*barriers + tmem slot*/ + 2 * 256 * sizeof(float) /*bias*/;
+  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - tail;
   int stages = (int)(budget / stage_bytes);
   if (stages > 4) stages = 4;
   DVG_REQUIRE(stages >= 2, "tile too large for a 2-stage pipeline");
   a.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024 + 256;
+  const size_t smem = stages * stage_bytes + 1024 + tail;
   static bool configured = false;  // per template instantiation
   if (!configured) {
     DVG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DVG_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int tiles = a.row_tiles * a.n_tiles;
-  const int grid = tiles < h->sm_count ? tiles : h->sm_count;
-  tc_gemm_kernel<EPI><<<grid, TC_THREADS, smem, stream>>>(a);
-  DVG_LAUNCH_CHECK();
+  int cm;
+  if (pairs) {
+    cm = 2;
+  } else {
+    // 1-CTA kernel: cluster along the row-tile axis multicasts the weight images
+    cm = a.row_tiles >= 4 ? 4 : (a.row_tiles >= 2 ? 2 : 1);
+    while (cm > 1 && (a.n_tile % cm) != 0) cm >>= 1;
+  }
+  a.cm = cm;
+  const int groups = ceil_div(a.row_tiles, cm);
+  int clusters = groups * a.n_tiles;
+  const int max_clusters = h->sm_count / cm;
+  if (clusters > max_clusters) clusters = max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * cm);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cm;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cm > 1 ? 1 : 0;
+#ifdef DVG_TRACE
+  static unsigned long long* tbuf = nullptr;
+  const bool tr = EPI == EPI_LSTM && getenv("DVG_TC_TRACE") != nullptr;
+  if (tr) {
+    if (!tbuf) cudaMalloc(&tbuf, 256 * 32 * 8);
+    cudaMemsetAsync(tbuf, 0, 256 * 32 * 8, stream);
+    a.trace = tbuf;
+  }
+#endif
+  if (pairs) DVG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<EPI>, (const TcArgs)a));
+  else DVG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI>, (const TcArgs)a));
+#ifdef DVG_TRACE
+  if (tr) {
+    static int n_dump = 0;
+    cudaStreamSynchronize(stream);
+    if (n_dump++ == 6) {
+      std::vector<unsigned long long> hbuf(256 * 32);
+      cudaMemcpy(hbuf.data(), tbuf, 256 * 32 * 8, cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull;
+      for (int b = 0; b < (int)cfg.gridDim.x; ++b) if (hbuf[b * 32] && hbuf[b * 32] < t0) t0 = hbuf[b * 32];
+      fprintf(stderr, "TRACE grid=%d cm=%d pairs=%d stages=%d (ns since first CTA start)\n", (int)cfg.gridDim.x, cm,
+              (int)pairs, stages);
+      for (int b = 0; b < (int)cfg.gridDim.x; b += (b < 8 ? 1 : 13)) {
+        fprintf(stderr, "cta %3d:", b);
+        for (int i = 0; i < 31; ++i) {
+          unsigned long long v = hbuf[b * 32 + i];
+          if (i == 2 || i == 14 || i == 26) fprintf(stderr, " |");
+          fprintf(stderr, " %lld", v ? (long long)(v - t0) : -1ll);
+        }
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+#endif
   return DVG_OK;
 }
 
