@@ -122,6 +122,10 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
     DVG_CUDA(cudaMalloc(&h->tc_xp, lstm_tc_scratch_bytes_xp(h, rows)));
     DVG_CUDA(cudaMalloc(&h->tc_ep, lstm_tc_scratch_bytes_ep(h, rows)));
     DVG_CUDA(cudaMemset(h->tc_ep, 0, lstm_tc_scratch_bytes_ep(h, rows)));
+    if (h->fused_flags) cudaFree(h->fused_flags);
+    h->fused_flags = nullptr;
+    h->fused_flag_stride = (int)align_up((size_t)ceil_div(ceil_div(rows, 128), 2), 32);
+    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * (size_t)(h->dims.n_layers + 1) * h->fused_flag_stride));
   }
   h->reserved_rows = rows;
   return DVG_OK;
@@ -225,6 +229,7 @@ int dvg_gauss_lstm_step(dvg_lstm_t h, int variant, int rows, const float* x, int
 static void gp_free_all(dvg_gp_s* h) {
   auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
   fr(h->z); fr(h->linv); fr(h->lqt); fr(h->alpha); fr(h->hyp); fr(h->work); fr(h->var_rows);
+  fr(h->ticket); fr(h->trig_list); fr(h->trig_count);
 }
 
 int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* var_mean,
@@ -246,6 +251,11 @@ int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing
   if (e == cudaSuccess) e = cudaMalloc(&h->work, sizeof(double) * D * M * M);
   h->var_rows_cap = 4096;
   if (e == cudaSuccess) e = cudaMalloc(&h->var_rows, sizeof(float) * D * h->var_rows_cap);
+  if (e == cudaSuccess) e = cudaMalloc(&h->trig_list, sizeof(int) * h->var_rows_cap);
+  if (e == cudaSuccess) e = cudaMalloc(&h->trig_count, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->trig_count, 0, sizeof(int));
   if (e != cudaSuccess) {
     set_error("GP handle allocation failed: %s", cudaGetErrorString(e));
     gp_free_all(h);
@@ -299,6 +309,9 @@ int dvg_gp_trigger(dvg_gp_t h, int n_rollouts, const float* x, int ldx, const in
     h->var_rows = nullptr;
     h->var_rows_cap = 0;
     DVG_CUDA(cudaMalloc(&h->var_rows, sizeof(float) * (size_t)h->dims.num_dims * n_rollouts));
+    if (h->trig_list) cudaFree(h->trig_list);
+    h->trig_list = nullptr;
+    DVG_CUDA(cudaMalloc(&h->trig_list, sizeof(int) * (size_t)n_rollouts));
     h->var_rows_cap = n_rollouts;
   }
   return gp_trigger_launch(h, n_rollouts, x, ldx, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,

@@ -65,10 +65,72 @@ __device__ __forceinline__ float tanh_f(float x) {
   return fabsf(x) < 0.25f ? small : big;
 }
 
+// ---- fast gate math for the tensor-core epilogues --------------------------------------------------------
+// MUFU-only building blocks (1 instruction each, no range fix-ups).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+// 2^x on the FMA pipe (Cody-Waite + degree-5 minimax, max rel. err 1.9e-7 ~ MUFU.EX2): B200's MUFU pipe
+// sustains only ~8 results/clk/SM, which made the LSTM epilogue MUFU-bound; x must be <= 64.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;        // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float n = t - 12582912.f;
+  const float f = x - n;                 // [-0.5, 0.5]
+  float p = 0.001326472731307149f;
+  p = fmaf(p, f, 0.009671512991189957f);
+  p = fmaf(p, f, 0.05550733581185341f);
+  p = fmaf(p, f, 0.24022242426872253f);
+  p = fmaf(p, f, 0.6931470036506653f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // * 2^n
+}
+// LSTM cell from gate pre-activations.  a* are the raw accumulators, b* the biases PRE-SCALED by -log2(e)
+// (i, f, o) and -2 log2(e) (g), so every exponent argument is one FFMA:
+//   E_i = e^-z_i, E_f = e^-z_f, E_o = e^-z_o, E_g = e^-2 z_g;  sigmoid(z) = 1/(1+E),  tanh(z) = (1-E)/(1+E)
+//   c' = sig(f) c + sig(i) tanh(g) = [c (1+E_i)(1+E_g) + (1-E_g)(1+E_f)] / [(1+E_f)(1+E_i)(1+E_g)]   (ONE reciprocal)
+//   h' = sig(o) tanh(c')          = (1-E_c) / [(1+E_o)(1+E_c)],  E_c = e^-2 c'                     (ONE reciprocal)
+// Exponent arguments are clamped at 40 (E <= 2^40, triple products stay finite; sigmoid/tanh are saturated to
+// fp32 precision well before).  E_i, E_f, E_o use the FMA-pipe polynomial, E_g, E_c the MUFU: 4 MUFU + ~57 FP32
+// ops per hidden unit, balanced between the two pipes.  Abs. error ~3e-7.
+__device__ __forceinline__ void lstm_cell_fast(float ai, float af, float ag, float ao, float bi, float bf, float bg,
+                                               float bo, float c_prev, float& h_new, float& c_new) {
+  const float Ei = ex2_poly(fminf(fmaf(ai, -kLog2e, bi), 40.f));
+  const float Ef = ex2_poly(fminf(fmaf(af, -kLog2e, bf), 40.f));
+  const float Eo = ex2_poly(fminf(fmaf(ao, -kLog2e, bo), 40.f));
+  const float Eg = ex2_ftz(fminf(fmaf(ag, -2.f * kLog2e, bg), 40.f));
+  const float pi = 1.f + Ei, pf = 1.f + Ef, pg = 1.f + Eg;
+  const float P = pi * pg;
+  const float num = fmaf(c_prev, P, (1.f - Eg) * pf);
+  c_new = num * rcp_ftz(P * pf);
+  const float Ec = ex2_ftz(fminf(c_new * (-2.f * kLog2e), 40.f));
+  h_new = (1.f - Ec) * rcp_ftz((1.f + Eo) * (1.f + Ec));
+}
+// tanh(z + b) with the bias pre-scaled by -2 log2(e): 2 MUFU.
+__device__ __forceinline__ float tanh_fast_prescaled(float a, float b) {
+  const float E = ex2_ftz(fminf(fmaf(a, -2.f * kLog2e, b), 40.f));
+  return (1.f - E) * rcp_ftz(1.f + E);
+}
+
 // a ~= hi + lo with both bf16 (round-to-nearest): relative residual <= 2^-17.
 __device__ __forceinline__ void split_bf16(float a, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(a);
   lo = __float2bfloat16_rn(a - __bfloat162float(hi));
+}
+// Two values at once with the packed converter (cvt.rn.bf16x2.f32): returns hi pair / lo pair as bf16x2 words
+// (element 0 in the low half), same RN/RN arithmetic as split_bf16.
+__device__ __forceinline__ void split2_bf16(float a0, float a1, uint32_t& hi2, uint32_t& lo2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(a1), "f"(a0));
+  const float h0 = __uint_as_float(hi2 << 16), h1 = __uint_as_float(hi2 & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(a1 - h1), "f"(a0 - h0));
 }
 __device__ __forceinline__ uint32_t pack2_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);

@@ -115,6 +115,83 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, int mp, d
 // Linv and L_q^T of that dim are staged in shared memory and read as warp-broadcast float4; the kernel
 // row k[] of each thread lives in registers (MREG = padded M known at compile time) or shared memory.
 // ---------------------------------------------------------------------------------------------------
+// Stage one latent dimension's factors into shared memory (all 128 threads).
+__device__ __forceinline__ void gp_stage_dim(int d, int MP, int tid, const float* __restrict__ zall,
+                                             const float* __restrict__ linv_all, const float* __restrict__ lqt_all,
+                                             const float* __restrict__ alpha_all, float* s_linv, float* s_lqt,
+                                             float* s_z, float* s_alpha) {
+  const float4* g1 = reinterpret_cast<const float4*>(linv_all + (size_t)d * MP * MP);
+  const float4* g2 = reinterpret_cast<const float4*>(lqt_all + (size_t)d * MP * MP);
+  for (int e = tid; e < MP * MP / 4; e += 128) {
+    reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
+    reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
+  }
+  for (int e = tid; e < MP; e += 128) {
+    s_z[e] = zall[(size_t)d * MP + e];
+    s_alpha[e] = alpha_all[(size_t)d * MP + e];
+  }
+}
+
+// One (row, dim) evaluation: mu = (Linv k).beta, vv = |Linv k|^2, ww = |L_q^T k|^2.
+// Two independent accumulators per dot product halve the dependent-FMA chains (the kernel is latency bound
+// when only a few rows are evaluated, e.g. the trigger's one row per rollout).
+template <int MREG>
+__device__ __forceinline__ void gp_row_eval(float xv, float s, float inv_ell, int MP, int tid, const float* s_linv,
+                                            const float* s_lqt, const float* s_z, const float* s_alpha, float* s_k,
+                                            float& mu, float& vv, float& ww) {
+  mu = 0.f; vv = 0.f; ww = 0.f;
+  if (MREG > 0) {
+    float k[MREG > 0 ? MREG : 1];
+#pragma unroll
+    for (int m = 0; m < MREG; ++m) {
+      const float t = (xv - s_z[m]) * inv_ell;
+      k[m] = s * expf(-0.5f * t * t);   // padded z entries only ever meet zero factors
+    }
+#pragma unroll
+    for (int j = 0; j < MREG; ++j) {
+      float v0 = 0.f, v1 = 0.f, w0 = 0.f, w1 = 0.f;
+      const int jm = (j / 4) * 4;
+#pragma unroll
+      for (int m = 0; m <= jm; m += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(s_linv + j * MREG + m);
+        v0 = fmaf(l4.x, k[m], v0); v1 = fmaf(l4.y, k[m + 1], v1); v0 = fmaf(l4.z, k[m + 2], v0); v1 = fmaf(l4.w, k[m + 3], v1);
+      }
+#pragma unroll
+      for (int m = jm; m < MREG; m += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(s_lqt + j * MREG + m);
+        w0 = fmaf(q4.x, k[m], w0); w1 = fmaf(q4.y, k[m + 1], w1); w0 = fmaf(q4.z, k[m + 2], w0); w1 = fmaf(q4.w, k[m + 3], w1);
+      }
+      const float v = v0 + v1, w = w0 + w1;
+      vv = fmaf(v, v, vv);
+      ww = fmaf(w, w, ww);
+      mu = fmaf(v, s_alpha[j], mu);
+    }
+  } else {
+    for (int m = 0; m < MP; ++m) {
+      const float t = (xv - s_z[m]) * inv_ell;
+      s_k[m * 128 + tid] = s * expf(-0.5f * t * t);
+    }
+    for (int j = 0; j < MP; ++j) {
+      float v0 = 0.f, v1 = 0.f, w0 = 0.f, w1 = 0.f;
+      const int jm = (j / 4) * 4;
+      for (int m = 0; m <= jm; m += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(s_linv + j * MP + m);
+        v0 = fmaf(l4.x, s_k[m * 128 + tid], v0); v1 = fmaf(l4.y, s_k[(m + 1) * 128 + tid], v1);
+        v0 = fmaf(l4.z, s_k[(m + 2) * 128 + tid], v0); v1 = fmaf(l4.w, s_k[(m + 3) * 128 + tid], v1);
+      }
+      for (int m = jm; m < MP; m += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(s_lqt + j * MP + m);
+        w0 = fmaf(q4.x, s_k[m * 128 + tid], w0); w1 = fmaf(q4.y, s_k[(m + 1) * 128 + tid], w1);
+        w0 = fmaf(q4.z, s_k[(m + 2) * 128 + tid], w0); w1 = fmaf(q4.w, s_k[(m + 3) * 128 + tid], w1);
+      }
+      const float v = v0 + v1, w = w0 + w1;
+      vv = fmaf(v, v, vv);
+      ww = fmaf(w, w, ww);
+      mu = fmaf(v, s_alpha[j], mu);
+    }
+  }
+}
+
 template <int MREG>
 __global__ void __launch_bounds__(128) gp_predict_kernel(int n_rows, int D, int mp, const float* __restrict__ x, int ldx,
                                                          const int32_t* __restrict__ row_index,
@@ -132,76 +209,15 @@ __global__ void __launch_bounds__(128) gp_predict_kernel(int n_rows, int D, int 
   float* s_z = s_lqt + MP * MP;         // [MP]
   float* s_alpha = s_z + MP;            // [MP]
   float* s_k = s_alpha + MP;            // [MP][128] (generic path only)
-  {
-    const float4* g1 = reinterpret_cast<const float4*>(linv_all + (size_t)d * MP * MP);
-    const float4* g2 = reinterpret_cast<const float4*>(lqt_all + (size_t)d * MP * MP);
-    for (int e = tid; e < MP * MP / 4; e += 128) {
-      reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
-      reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
-    }
-    for (int e = tid; e < MP; e += 128) {
-      s_z[e] = zall[(size_t)d * MP + e];
-      s_alpha[e] = alpha_all[(size_t)d * MP + e];
-    }
-  }
+  gp_stage_dim(d, MP, tid, zall, linv_all, lqt_all, alpha_all, s_linv, s_lqt, s_z, s_alpha);
   __syncthreads();
   const float ell = hyp[d * 4 + 0], s = hyp[d * 4 + 1], c = hyp[d * 4 + 2], noise = hyp[d * 4 + 3];
   const int i = blockIdx.x * 128 + tid;
   if (i >= n_rows) return;
   const int row = row_index ? row_index[i] : i;
   const float xv = __ldg(x + (size_t)row * ldx + d);
-  const float inv_ell = 1.0f / ell;
-
-  float mu = 0.f, vv = 0.f, ww = 0.f;
-  if (MREG > 0) {
-    float k[MREG > 0 ? MREG : 1];
-#pragma unroll
-    for (int m = 0; m < MREG; ++m) {
-      const float t = (xv - s_z[m]) * inv_ell;
-      k[m] = s * expf(-0.5f * t * t);   // padded z entries are multiplied by zero factors below
-    }
-#pragma unroll
-    for (int j = 0; j < MREG; ++j) {
-      float v = 0.f, w = 0.f;
-      const int jm = (j / 4) * 4;
-#pragma unroll
-      for (int m = 0; m <= jm; m += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(s_linv + j * MREG + m);
-        v = fmaf(l4.x, k[m], v); v = fmaf(l4.y, k[m + 1], v); v = fmaf(l4.z, k[m + 2], v); v = fmaf(l4.w, k[m + 3], v);
-      }
-#pragma unroll
-      for (int m = jm; m < MREG; m += 4) {
-        const float4 q4 = *reinterpret_cast<const float4*>(s_lqt + j * MREG + m);
-        w = fmaf(q4.x, k[m], w); w = fmaf(q4.y, k[m + 1], w); w = fmaf(q4.z, k[m + 2], w); w = fmaf(q4.w, k[m + 3], w);
-      }
-      vv = fmaf(v, v, vv);
-      ww = fmaf(w, w, ww);
-      mu = fmaf(v, s_alpha[j], mu);
-    }
-  } else {
-    for (int m = 0; m < MP; ++m) {
-      const float t = (xv - s_z[m]) * inv_ell;
-      const float km = s * expf(-0.5f * t * t);
-      s_k[m * 128 + tid] = km;
-    }
-    for (int j = 0; j < MP; ++j) {
-      float v = 0.f, w = 0.f;
-      const int jm = (j / 4) * 4;
-      for (int m = 0; m <= jm; m += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(s_linv + j * MP + m);
-        v = fmaf(l4.x, s_k[m * 128 + tid], v); v = fmaf(l4.y, s_k[(m + 1) * 128 + tid], v);
-        v = fmaf(l4.z, s_k[(m + 2) * 128 + tid], v); v = fmaf(l4.w, s_k[(m + 3) * 128 + tid], v);
-      }
-      for (int m = jm; m < MP; m += 4) {
-        const float4 q4 = *reinterpret_cast<const float4*>(s_lqt + j * MP + m);
-        w = fmaf(q4.x, s_k[m * 128 + tid], w); w = fmaf(q4.y, s_k[(m + 1) * 128 + tid], w);
-        w = fmaf(q4.z, s_k[(m + 2) * 128 + tid], w); w = fmaf(q4.w, s_k[(m + 3) * 128 + tid], w);
-      }
-      vv = fmaf(v, v, vv);
-      ww = fmaf(w, w, ww);
-      mu = fmaf(v, s_alpha[j], mu);
-    }
-  }
+  float mu, vv, ww;
+  gp_row_eval<MREG>(xv, s, 1.0f / ell, MP, tid, s_linv, s_lqt, s_z, s_alpha, s_k, mu, vv, ww);
   if (mean) mean[(size_t)i * ldm + d] = c + mu;
   if (var) var[(size_t)i * ldv + d] = (s - vv) + ww + noise;
 }
@@ -229,23 +245,19 @@ __device__ float np_pairwise_sum(const float* a, int n) {
 
 constexpr int MAX_WINDOW = 128;
 
-__global__ void gp_trigger_finalize_kernel(int S, int D, const float* __restrict__ var_rows, float* __restrict__ window,
-                                           int W, int32_t* __restrict__ count, int warmup, float factor,
-                                           float* __restrict__ value, float* __restrict__ thr,
-                                           uint8_t* __restrict__ mask) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
+// One rollout's decision (numpy float32 arithmetic, see oracle/trigger_ref.py).  Returns the mask bit.
+__device__ int gp_trigger_decide(int s, int D, const float* vrow, float* window, int W, int cnt, int warmup,
+                                 float factor, float* value, float* thr, uint8_t* mask) {
   // generate_frames.py:230 -- np.linalg.norm(variance^T, axis=1): sequential fp32 sum over d
   float acc = 0.f;
   for (int d = 0; d < D; ++d) {
-    const float v = var_rows[(size_t)s * D + d];
+    const float v = vrow[d];
     acc = __fadd_rn(acc, __fmul_rn(v, v));
   }
   const float val = sqrtf(acc);
   float* w = window + (size_t)s * W;
   if (value) value[s] = val;
   if (warmup) {
-    const int cnt = count[0];
     if (cnt < W) w[cnt] = val;
     else {  // window already full: keep sliding without a decision
       for (int i = 0; i + 1 < W; ++i) w[i] = w[i + 1];
@@ -253,7 +265,7 @@ __global__ void gp_trigger_finalize_kernel(int S, int D, const float* __restrict
     }
     if (thr) thr[s] = nanf("");
     if (mask) mask[s] = 0;
-    return;
+    return 0;
   }
   float loc[MAX_WINDOW];
   for (int i = 0; i + 1 < W; ++i) loc[i] = w[i + 1];   // generate_frames.py:231
@@ -266,29 +278,102 @@ __global__ void gp_trigger_finalize_kernel(int S, int D, const float* __restrict
   }
   const float sd = sqrtf(__fdiv_rn(np_pairwise_sum(loc, W), (float)W));
   const float t = __fadd_rn(mean, __fmul_rn(factor, sd));  // generate_frames.py:288
+  const int fired = val > t ? 1 : 0;                       // generate_frames.py:289
   if (thr) thr[s] = t;
-  if (mask) mask[s] = val > t ? 1 : 0;                    // generate_frames.py:289
+  if (mask) mask[s] = (uint8_t)fired;
+  return fired;
 }
 
-__global__ void gp_count_bump_kernel(int32_t* count, int W) {
-  if (count[0] < W) count[0] += 1;
+// Fused trigger: grid (ceil(S/128), D).  Phase 1: variance at the statistic row of every rollout for this CTA's
+// latent dim -> var_rows[s][d].  Phase 2 (the LAST CTA to finish, found with an atomic ticket): per-rollout norm,
+// window update, threshold, decision, warm-up counter bump, and a compacted list of the rollouts that fired
+// (consumed by gp_rsample_list_kernel) -- one launch instead of predict + finalize + counter kernels.
+template <int MREG>
+__global__ void __launch_bounds__(128) gp_trigger_kernel(int S, int D, int mp, const float* __restrict__ x, int ldx,
+                                                         const int32_t* __restrict__ stat_rows,
+                                                         const float* __restrict__ zall,
+                                                         const float* __restrict__ linv_all,
+                                                         const float* __restrict__ lqt_all,
+                                                         const float* __restrict__ alpha_all,
+                                                         const float* __restrict__ hyp, float* var_rows,
+                                                         unsigned int* ticket, float* window, int W, int32_t* count,
+                                                         int warmup, float factor, float* value, float* thr,
+                                                         uint8_t* mask, int* trig_list, int* trig_count) {
+  extern __shared__ __align__(16) float smf[];
+  __shared__ int s_last;
+  const int d = blockIdx.y, tid = threadIdx.x;
+  const int MP = MREG > 0 ? MREG : mp;
+  float* s_linv = smf;
+  float* s_lqt = s_linv + MP * MP;
+  float* s_z = s_lqt + MP * MP;
+  float* s_alpha = s_z + MP;
+  float* s_k = s_alpha + MP;
+  const int i = blockIdx.x * 128 + tid;
+  float xv = 0.f;
+  if (i < S) xv = __ldg(x + (size_t)stat_rows[i] * ldx + d);    // issue the (DRAM) load before staging
+  gp_stage_dim(d, MP, tid, zall, linv_all, lqt_all, alpha_all, s_linv, s_lqt, s_z, s_alpha);
+  __syncthreads();
+  if (i < S) {
+    const float ell = hyp[d * 4 + 0], s = hyp[d * 4 + 1], noise = hyp[d * 4 + 3];
+    float mu, vv, ww;
+    gp_row_eval<MREG>(xv, s, 1.0f / ell, MP, tid, s_linv, s_lqt, s_z, s_alpha, s_k, mu, vv, ww);
+    var_rows[(size_t)i * D + d] = (s - vv) + ww + noise;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) *trig_count = 0;
+  const int cnt = count[0];
+  __syncthreads();
+  // the matrices in smf are dead now: reuse the buffer for 128 variance rows at a time (coalesced L2 reads;
+  // a per-thread dependent chain of 90 L2 loads made this phase 18 us)
+  for (int base = 0; base < S; base += 128) {
+    const int nrow = S - base < 128 ? S - base : 128;
+    __syncthreads();
+    {  // 8 independent loads in flight per thread (a plain strided loop serialises ~70 L2 round trips)
+      const float* src = var_rows + (size_t)base * D;
+      const int n = nrow * D;
+      for (int e0 = 0; e0 < n; e0 += 128 * 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * 128 + tid;
+          t[u] = e < n ? __ldcg(src + e) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * 128 + tid;
+          if (e < n) smf[e] = t[u];
+        }
+      }
+    }
+    __syncthreads();
+    const int s = base + tid;
+    if (tid < nrow && gp_trigger_decide(s, D, smf + tid * D, window, W, cnt, warmup, factor, value, thr, mask))
+      trig_list[atomicAdd(trig_count, 1)] = s;
+  }
+  if (tid == 0) {
+    *ticket = 0;                                   // ready for the next launch
+    if (warmup && cnt < W) count[0] = cnt + 1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // rsample: one CTA per (rollout s, latent dim d); full [N,N] predictive covariance in shared memory,
 // Cholesky, y = mean + L eps.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gp_rsample_kernel(int S, int N, int D, int mp, const float* __restrict__ x,
+__device__ __forceinline__ void gp_rsample_body(int s_idx, int d, int N, int D, int mp, const float* __restrict__ x,
                                                          int ldx, const float* __restrict__ eps,
-                                                         const uint8_t* __restrict__ mask,
                                                          const float* __restrict__ zall,
                                                          const float* __restrict__ linv_all,
                                                          const float* __restrict__ lqt_all,
                                                          const float* __restrict__ alpha_all,
                                                          const float* __restrict__ hyp, float* __restrict__ out,
                                                          int ldo) {
-  const int s_idx = blockIdx.x, d = blockIdx.y, tid = threadIdx.x;
-  if (mask != nullptr && mask[s_idx] == 0) return;
+  const int tid = threadIdx.x;
   extern __shared__ __align__(16) float smf[];
   const int MP = mp;
   const int ldk = MP + 1, lds = N + 1;
@@ -363,6 +448,39 @@ __global__ void __launch_bounds__(128) gp_rsample_kernel(int S, int N, int D, in
   }
 }
 
+
+// grid (S, D): one CTA per (rollout, dim); CTAs of unmasked rollouts exit.
+__global__ void __launch_bounds__(128) gp_rsample_kernel(int S, int N, int D, int mp, const float* __restrict__ x, int ldx,
+                                                         const float* __restrict__ eps,
+                                                         const uint8_t* __restrict__ mask,
+                                                         const float* __restrict__ zall,
+                                                         const float* __restrict__ linv_all,
+                                                         const float* __restrict__ lqt_all,
+                                                         const float* __restrict__ alpha_all,
+                                                         const float* __restrict__ hyp, float* __restrict__ out, int ldo) {
+  if (mask != nullptr && mask[blockIdx.x] == 0) return;
+  gp_rsample_body(blockIdx.x, blockIdx.y, N, D, mp, x, ldx, eps, zall, linv_all, lqt_all, alpha_all, hyp, out, ldo);
+}
+
+// grid (D, splits): driven by the compacted list of triggered rollouts written by gp_trigger_kernel, so a step
+// in which nothing fired costs D*splits empty CTAs instead of S*D.
+__global__ void __launch_bounds__(128) gp_rsample_list_kernel(int N, int D, int mp, const float* __restrict__ x, int ldx,
+                                                              const float* __restrict__ eps,
+                                                              const int* __restrict__ trig_list,
+                                                              const int* __restrict__ trig_count,
+                                                              const float* __restrict__ zall,
+                                                              const float* __restrict__ linv_all,
+                                                              const float* __restrict__ lqt_all,
+                                                              const float* __restrict__ alpha_all,
+                                                              const float* __restrict__ hyp, float* __restrict__ out,
+                                                              int ldo) {
+  const int n = *trig_count;
+  for (int i = blockIdx.y; i < n; i += gridDim.y) {
+    gp_rsample_body(trig_list[i], blockIdx.x, N, D, mp, x, ldx, eps, zall, linv_all, lqt_all, alpha_all, hyp, out, ldo);
+    __syncthreads();   // shared memory is reused by the next rollout
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host launchers (called from capi.cu)
 // ---------------------------------------------------------------------------------------------------
@@ -413,16 +531,36 @@ int gp_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t
                       cudaStream_t stream) {
   DVG_REQUIRE(W >= 1 && W <= MAX_WINDOW, "window_len must be in [1,%d]", MAX_WINDOW);
   DVG_REQUIRE(S <= h->var_rows_cap, "n_rollouts=%d exceeds the reserved trigger scratch (%d)", S, h->var_rows_cap);
-  const int D = h->dims.num_dims;
-  int rc = gp_predict_launch(h, S, x, ldx, stat_rows, nullptr, 0, h->var_rows, D, stream);
-  if (rc) return rc;
-  gp_trigger_finalize_kernel<<<ceil_div(S, 64), 64, 0, stream>>>(S, D, h->var_rows, window, W, count, warmup, factor,
-                                                                value, thr, mask);
-  DVG_LAUNCH_CHECK();
-  if (warmup) {
-    gp_count_bump_kernel<<<1, 1, 0, stream>>>(count, W);
-    DVG_LAUNCH_CHECK();
+  const int D = h->dims.num_dims, mp = h->mp;
+  dim3 grid(ceil_div(S, 128), D);
+  static bool configured = false;
+  if (!configured) {
+    DVG_CUDA(cudaFuncSetAttribute(gp_trigger_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));  // + static smem
+    configured = true;
   }
+  const size_t fin_smem = sizeof(float) * 128 * (size_t)D;   // finalize phase: 128 variance rows
+  if (mp == 40) {
+    size_t smem = sizeof(float) * (2 * 40 * 40 + 2 * 40);
+    if (smem < fin_smem) smem = fin_smem;
+    static bool c40 = false;
+    if (!c40) {
+      DVG_CUDA(cudaFuncSetAttribute(gp_trigger_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      c40 = true;
+    }
+    gp_trigger_kernel<40><<<grid, 128, smem, stream>>>(S, D, mp, x, ldx, stat_rows, h->z, h->linv, h->lqt, h->alpha, h->hyp,
+                                                       h->var_rows, h->ticket, window, W, count, warmup, factor, value,
+                                                       thr, mask, h->trig_list, h->trig_count);
+  } else {
+    size_t smem = sizeof(float) * ((size_t)2 * mp * mp + 2 * mp + (size_t)mp * 128);
+    if (smem < fin_smem) smem = fin_smem;
+    DVG_REQUIRE(smem <= 226 * 1024, "num_inducing=%d too large for the shared-memory predictive kernel", mp);
+    gp_trigger_kernel<0><<<grid, 128, smem, stream>>>(S, D, mp, x, ldx, stat_rows, h->z, h->linv, h->lqt, h->alpha, h->hyp,
+                                                      h->var_rows, h->ticket, window, W, count, warmup, factor, value,
+                                                      thr, mask, h->trig_list, h->trig_count);
+  }
+  DVG_LAUNCH_CHECK();
+  h->last_mask = mask;   // dvg_gp_rsample(mask == this pointer) may use the compacted list
+  h->last_mask_rollouts = S;
   return DVG_OK;
 }
 
@@ -434,10 +572,16 @@ int gp_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const 
   static bool configured = false;
   if (!configured) {
     DVG_CUDA(cudaFuncSetAttribute(gp_rsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DVG_CUDA(cudaFuncSetAttribute(gp_rsample_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  gp_rsample_kernel<<<dim3(S, D), 128, smem, stream>>>(S, N, D, mp, x, ldx, eps, mask, h->z, h->linv, h->lqt, h->alpha,
-                                                       h->hyp, out, ldo);
+  if (mask != nullptr && mask == h->last_mask && S == h->last_mask_rollouts) {
+    gp_rsample_list_kernel<<<dim3(D, 4), 128, smem, stream>>>(N, D, mp, x, ldx, eps, h->trig_list, h->trig_count, h->z,
+                                                               h->linv, h->lqt, h->alpha, h->hyp, out, ldo);
+  } else {
+    gp_rsample_kernel<<<dim3(S, D), 128, smem, stream>>>(S, N, D, mp, x, ldx, eps, mask, h->z, h->linv, h->lqt, h->alpha,
+                                                         h->hyp, out, ldo);
+  }
   DVG_LAUNCH_CHECK();
   return DVG_OK;
 }

@@ -40,6 +40,11 @@ struct dvg_lstm_s {
 
   // --- tensor-core packed weights -----------------------------------------------------------------
   dvg::TcGemmPlan tc_embed, tc_layer[dvg::MAX_LAYERS], tc_head;
+  dvg::TcGemmPlan tc_layer0f;    // layer 0 with the embed Linear folded in (fused step kernel)
+  float* fold_wx = nullptr;      // [4H][G]  W_ih0 W_e
+  float* fold_bx = nullptr;      // [4H]     W_ih0 b_e + b_ih0 + b_hh0
+  int* fused_flags = nullptr;    // [(L+1)][fused_flag_stride] per-row-group dependency counters
+  int fused_flag_stride = 0;
 
   // --- scratch, grown by reserve() ----------------------------------------------------------------
   int reserved_rows = 0;
@@ -68,6 +73,11 @@ struct dvg_gp_s {
   double* work = nullptr;     // fp64 scratch for prepare [D][3][M][M]
   float* var_rows = nullptr;  // scratch [max_rollouts][D] for the trigger
   int var_rows_cap = 0;
+  unsigned int* ticket = nullptr;   // last-CTA-done counter of the fused trigger kernel (self-resetting)
+  int* trig_list = nullptr;         // [max_rollouts] compacted rollouts that fired in the last trigger call
+  int* trig_count = nullptr;
+  const uint8_t* last_mask = nullptr;  // mask buffer the list corresponds to
+  int last_mask_rollouts = 0;
 };
 
 namespace dvg {

@@ -98,13 +98,7 @@ __device__ __forceinline__ void store_split16(uint8_t* img_hi, uint32_t r_in_til
   // 16 consecutive K elements of one row -> two 16-byte chunks in the hi image and two in the lo image.
   uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v[2 * i], h0, l0);
-    split_bf16(v[2 * i + 1], h1, l1);
-    hi[i] = pack2_bf16(h0, h1);
-    lo[i] = pack2_bf16(l0, l1);
-  }
+  for (int i = 0; i < 8; ++i) split2_bf16(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
   uint8_t* img_lo = img_hi + TC_A_IMG;
   // chunk0 is even: the swizzled positions of chunks {chunk0, chunk0+1} form one aligned 32-byte sector,
   // in swapped order when bit 0 of (row & 7) is set -> one 256-bit store per image.
@@ -126,15 +120,12 @@ __device__ __forceinline__ void store_split16(uint8_t* img_hi, uint32_t r_in_til
 // LSTM pointwise math for 16 hidden units of one row (i,f,g,o pre-activations in r[0..63]).
 __device__ __forceinline__ void lstm_pointwise16(const uint32_t (&r)[64], const float* sb, int cb, const float (&cp)[16],
                                                  float (&hn)[16], float (&cn)[16]) {
+  // sb holds the biases pre-scaled by -log2e (i, f, o) / -2 log2e (g): see lstm_cell_fast
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float gi = sigmoid_f(__uint_as_float(r[i]) + sb[cb + i]);
-    const float gf = sigmoid_f(__uint_as_float(r[16 + i]) + sb[64 + cb + i]);
-    const float gg = tanh_f(__uint_as_float(r[32 + i]) + sb[128 + cb + i]);
-    const float go = sigmoid_f(__uint_as_float(r[48 + i]) + sb[192 + cb + i]);
-    cn[i] = fmaf(gf, cp[i], gi * gg);
-    hn[i] = go * tanh_f(cn[i]);
-  }
+  for (int i = 0; i < 16; ++i)
+    lstm_cell_fast(__uint_as_float(r[i]), __uint_as_float(r[16 + i]), __uint_as_float(r[32 + i]),
+                   __uint_as_float(r[48 + i]), sb[cb + i], sb[64 + cb + i], sb[128 + cb + i], sb[192 + cb + i], cp[i],
+                   hn[i], cn[i]);
 }
 // Cluster of CM CTAs along the row-tile axis: the CM CTAs of a cluster work on CM consecutive row tiles
 // and the SAME N tile, so the weight k-block images are identical for all of them -- each CTA fetches
@@ -143,7 +134,7 @@ __device__ __forceinline__ void lstm_pointwise16(const uint32_t (&r)[64], const 
 // MMAs of ALL CM CTAs that read it have retired (multicast tcgen05.commit onto every CTA's empty barrier).
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B images need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,7 +272,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
       const bool valid = row < p.rows;
       float* sb = s_bias + acc * 256;
       // stage this tile's bias and prefetch the first c chunk while the MMAs are still running
-      if (etid < p.n_tile) sb[etid] = __ldg(p.bias + (size_t)nt * p.n_tile + etid);
+      if (etid < p.n_tile) {
+        float bv = __ldg(p.bias + (size_t)nt * p.n_tile + etid);
+        if (EPI == EPI_LSTM) bv *= (etid >> 6) == 2 ? -2.f * kLog2e : -kLog2e;
+        sb[etid] = bv;
+      }
       float cp[16];
       size_t idx0 = 0;
       bool held = false;
@@ -390,7 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
 // ---------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm2_kernel(const TcArgs p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -535,7 +530,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm2_kernel(const TcArgs p)
       const bool valid = row < p.rows;
       float* sb = s_bias + acc * 256;
       // stage this tile's bias and prefetch the first c chunk while the MMAs are still running
-      if (etid < p.n_tile) sb[etid] = __ldg(p.bias + (size_t)nt * p.n_tile + etid);
+      if (etid < p.n_tile) {
+        float bv = __ldg(p.bias + (size_t)nt * p.n_tile + etid);
+        if (EPI == EPI_LSTM) bv *= (etid >> 6) == 2 ? -2.f * kLog2e : -kLog2e;
+        sb[etid] = bv;
+      }
       float cp[16];
       size_t idx0 = 0;
       bool held = false;
@@ -629,6 +628,472 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm2_kernel(const TcArgs p)
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Whole LSTM time step in ONE persistent launch (cta_group::2 pairs).
+//
+// Work items, in dependency order (item index = scheduling order, pair p runs items p, p+P, p+2P, ...):
+//   PACKX(rg)        x rows of row group rg (256 rows) -> bf16 hi/lo operand images        (epilogue warps only)
+//   LSTM_0(rg, nt)   layer 0 with the embed folded in: A = [x | h_0], K = G' + H           needs PACKX(rg)
+//   LSTM_l(rg, nt)   A = [h'_{l-1} | h_l]                                                   needs LSTM_{l-1}(rg, *)
+//   HEAD(rg)         tanh(h'_{L-1} W_o^T + b_o)  or  mu/logvar/z                            needs LSTM_{L-1}(rg, *)
+// A dependency is a per-row-group counter in global memory: the epilogue publishes with
+// (st.global ... ; __threadfence ; bar ; atomicAdd), the TMA producer acquires it, issues fence.proxy.async and
+// only then lets the async proxy read the images the other pair wrote.  All pairs are co-resident (one CTA per
+// SM, grid <= #SMs) and every item only waits on items with a smaller index, so the schedule cannot deadlock.
+// Versus one launch per GEMM this removes 4 launches + prologues per step and lets the second wave of one
+// layer (160 tiles on 148 SMs) overlap the first wave of the next.
+// ---------------------------------------------------------------------------------------------------
+enum { PH_PACKX = 0, PH_LSTM = 1, PH_TANH = 2, PH_GAUSS = 3 };
+constexpr int MAX_PHASES = MAX_LAYERS + 2;
+
+struct FusedPhase {
+  int type, n_tile, n_tiles, kb0, kb1, item_begin;
+  const uint8_t* a0; const uint8_t* a1; const uint8_t* w; const float* bias;
+  const int* wait_flags; int wait_target; int* done_flags;
+  const float* c_in; const float* h_in; float* h_out; float* c_out; uint8_t* hp_out;   // LSTM
+  float* y; int ldy; int n_valid;                                                       // TANH
+  const float* eps; float* z; float* mu; float* logvar; int Z;                          // GAUSS
+  const float* x; int ldx; int G; uint8_t* xp; int kbx;                                 // PACKX
+};
+struct FusedArgs {
+  int rows, row_tiles, groups, nsplit, stages, n_phases, total_items, H, rows_per_flag;
+  uint32_t stage_bytes;
+  const uint8_t* hold;
+  unsigned long long* trace;
+  FusedPhase ph[MAX_PHASES];
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_constant__ FusedArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = raw;   // declared __align__(1024); checked below (SWIZZLE_128B images need it)
+  if ((raw & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("dvg_b200: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int CM = 2;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t stage_bytes = p.stage_bytes;
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * p.stages + 4);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base - raw) + 128);  // [2][256] floats
+  uint8_t* s_ebuf = smem_raw + (bar_base - raw) + 128 + 2 * 256 * sizeof(float);  // [EPI_WARPS][4 KB]
+
+  if (threadIdx.x == 0) {
+    TRACE(0);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(pfull_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), 2 * EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (threadIdx.x == 0) TRACE(1);
+  const int cid = (int)ptx::cluster_id_x();
+  const int ncl = (int)ptx::cluster_count_x();
+  auto phase_of = [&](int item) {
+    int k = 0;
+    while (k + 1 < p.n_phases && item >= p.ph[k + 1].item_begin) ++k;
+    return k;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t a_copy = p.nsplit == 1 ? (uint32_t)TC_A_IMG : 2u * TC_A_IMG;
+      const uint32_t nparts = p.nsplit == 1 ? 1u : 2u;
+      int s = 0;
+      uint32_t phs = 0;
+      int pm = 0;
+      for (int item = cid; item < p.total_items; item += ncl) {
+        const FusedPhase& f = p.ph[phase_of(item)];
+        if (f.type == PH_PACKX) continue;
+        if (pm < 3) TRACE(2 + pm * 8 + 0);
+        const int j = item - f.item_begin;
+        const int rg = j / f.n_tiles, nt = j % f.n_tiles;
+        int rt = rg * CM + (int)rank;
+        if (rt >= p.row_tiles) rt = p.row_tiles - 1;
+        const int KB = f.kb0 + f.kb1;
+        const uint32_t b_half = (uint32_t)f.n_tile * 64u, b_part = (uint32_t)f.n_tile * 128u;
+        bool dep_ok = f.wait_flags == nullptr;
+        for (int i = 0; i < KB; ++i) {
+          // recurrent (a1 / h) k-blocks first: they never depend on the previous phase of this step
+          const int kb = i < f.kb1 ? f.kb0 + i : i - f.kb1;
+          if (kb < f.kb0 && !dep_ok) {
+            int target = f.wait_target;   // < 0: x-pack units of this row group (1 or 2 row tiles x kbx k-blocks)
+            if (target < 0) target = p.ph[0].kbx * (p.row_tiles - rg * CM >= CM ? CM : p.row_tiles - rg * CM);
+            const long long t0 = clock64();
+            while (ld_acquire(f.wait_flags + rg) < target) {
+              if (clock64() - t0 > 4000000000LL) {
+                printf("dvg_b200: dependency wait timed out (item %d)\n", item);
+                __trap();
+              }
+            }
+            ptx::fence_proxy_async_all();   // generic-proxy writes of the producer pairs -> visible to our TMA reads
+            dep_ok = true;
+            if (pm <= 3) TRACE(2 + (pm - 1) * 8 + 1);
+          }
+          ptx::mbar_wait(empty_bar(s), phs ^ 1u);
+          const uint8_t* asrc = kb < f.kb0 ? f.a0 + (size_t)(rt * f.kb0 + kb) * (2u * TC_A_IMG)
+                                           : f.a1 + (size_t)(rt * f.kb1 + (kb - f.kb0)) * (2u * TC_A_IMG);
+          const uint8_t* bsrc = f.w + (size_t)(nt * KB + kb) * (2u * b_part) + rank * b_half;
+          const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + 2u * TC_A_IMG;
+          ptx::mbar_expect_tx(full_bar(s), a_copy + nparts * b_half);
+          ptx::bulk_g2s(sa, asrc, a_copy, full_bar(s));
+          ptx::bulk_g2s(sb, bsrc, b_half, full_bar(s));
+          if (nparts == 2) ptx::bulk_g2s(sb + b_half, bsrc + b_part, b_half, full_bar(s));
+          if (++s == p.stages) { s = 0; phs ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phs = 0;
+      int mit = 0;
+      for (int item = cid; item < p.total_items; item += ncl) {
+        const FusedPhase& f = p.ph[phase_of(item)];
+        if (f.type == PH_PACKX) continue;
+        const int KB = f.kb0 + f.kb1;
+        if (rank == 0) {
+          // ===================== MMA issuer (leader CTA) =====================
+          const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, f.n_tile);
+          const uint32_t b_half = (uint32_t)f.n_tile * 64u;
+          const int acc = mit & 1;
+          const uint32_t aph = (uint32_t)(mit >> 1) & 1u;
+          ptx::mbar_wait(tempty_bar(acc), aph ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_wait(full_bar(s), phs);
+            ptx::mbar_wait(pfull_bar(s), phs);
+            if (mit < 3 && kb == 0) TRACE(2 + mit * 8 + 2);
+            ptx::tc_fence_after();
+            const uint32_t sa = base + (uint32_t)s * stage_bytes;
+            const uint64_t a_hi = ptx::make_sw128_desc(sa);
+            const uint64_t a_lo = ptx::make_sw128_desc(sa + TC_A_IMG);
+            const uint64_t b_hi = ptx::make_sw128_desc(sa + 2u * TC_A_IMG);
+            const uint64_t b_lo = ptx::make_sw128_desc(sa + 2u * TC_A_IMG + b_half);
+#pragma unroll
+            for (int k = 0; k < TC_KBLK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              ptx::umma2_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (p.nsplit != 1) {
+                ptx::umma2_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                ptx::umma2_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+            ptx::umma2_commit_mcast(empty_bar(s), 3);
+            if (++s == p.stages) { s = 0; phs ^= 1u; }
+          }
+          ptx::umma2_commit_mcast(tfull_bar(acc), 3);
+          if (mit < 3) TRACE(2 + mit * 8 + 3);
+        } else {
+          // ===================== relay (peer CTA): "my stage landed" -> leader's pfull =====================
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_wait(full_bar(s), phs);
+            ptx::mbar_arrive_remote(pfull_bar(s), 0);
+            if (++s == p.stages) { s = 0; phs ^= 1u; }
+          }
+        }
+        ++mit;
+      }
+    }
+  } else {
+    // ===================== epilogue / SIMT worker warps (2 .. 2+EPI_WARPS-1) =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t r_in_tile = (uint32_t)(q * 32 + lane);
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const int etid = ew * 32 + lane;
+    // ---- x-pack prologue: x [rows, G] fp32 -> bf16 hi/lo operand images.  (row tile, k-block) units are spread
+    //      over ALL CTAs; all 32 loads of a thread are issued before the first use (DRAM-latency bound otherwise).
+    {
+      const FusedPhase& f = p.ph[0];
+      const int units = p.row_tiles * f.kbx;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int prt = u / f.kbx, kb = u % f.kbx;
+        uint8_t* img = f.xp + (size_t)(prt * f.kbx + kb) * (2u * TC_A_IMG);
+        float v[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int qd = etid + i * 256;
+          const int r = qd >> 3, chunk = qd & 7;
+          const int row = prt * TC_ROWS + r;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int kk = kb * 64 + chunk * 8 + e;
+            v[i][e] = (row < p.rows && kk < f.G) ? __ldg(f.x + (size_t)row * f.ldx + kk) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int qd = etid + i * 256;
+          const int r = qd >> 3, chunk = qd & 7;
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[i][2 * e], h0, l0);
+            split_bf16(v[i][2 * e + 1], h1, l1);
+            hi[e] = pack2_bf16(h0, h1);
+            lo[e] = pack2_bf16(l0, l1);
+          }
+          const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)chunk);
+          *reinterpret_cast<uint4*>(img + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(img + TC_A_IMG + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        __threadfence();
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+        if (etid == 0) atomicAdd(f.done_flags + (prt >> 1), 1);
+      }
+    }
+    int mit = 0;
+    for (int item = cid; item < p.total_items; item += ncl) {
+      const FusedPhase& f = p.ph[phase_of(item)];
+      const int j = item - f.item_begin;
+      const int rg = j / f.n_tiles, nt = j % f.n_tiles;
+      const int rt = rg * CM + (int)rank;
+      if (f.type == PH_PACKX) {
+        // (done in the prologue below by all CTAs; the phase only exists to carry the flags)
+      } else {
+        const int acc = mit & 1;
+        const uint32_t aph = (uint32_t)(mit >> 1) & 1u;
+        const int tm = mit;
+        ++mit;
+        const int row = rt * TC_ROWS + (int)r_in_tile;
+        const bool valid = row < p.rows;
+        float* sb = s_bias + acc * 256;
+        if (etid < f.n_tile) {
+          float bv = __ldg(f.bias + (size_t)nt * f.n_tile + etid);
+          if (f.type == PH_LSTM) bv *= (etid >> 6) == 2 ? -2.f * kLog2e : -kLog2e;
+          else if (f.type == PH_TANH) bv *= -2.f * kLog2e;
+          sb[etid] = bv;
+        }
+        // LSTM items: all fp32 state I/O goes through a warp-private 32 x 128 B transpose buffer so that every
+        // global access is a full 128-byte line per 8 lanes (thread-per-row accesses cost one L1TEX pass per
+        // line per instruction and made the epilogue the critical path).
+        uint8_t* eb = s_ebuf + ew * 4096;
+        const int er = lane >> 3, ec = lane & 7;           // coalesced mapping: 4 rows x 8 chunks per instruction
+        const int row_w0 = rt * TC_ROWS + q * 32;          // first row of this warp
+        bool held = false;
+        size_t idx0 = 0;
+        float4 cin[8];
+        if (f.type == PH_LSTM) {
+          idx0 = (size_t)row * p.H + nt * 64 + half * 32;
+          held = valid && p.hold != nullptr && p.hold[row / p.rows_per_flag] != 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + er;
+            cin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_w0 + rr < p.rows)
+              cin[i] = __ldg(reinterpret_cast<const float4*>(f.c_in + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32) + ec);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + er;
+            *reinterpret_cast<float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4)) = cin[i];
+          }
+          __syncwarp();
+        }
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+        ptx::mbar_wait(tfull_bar(acc), aph);
+        if (etid == 0 && tm < 3) TRACE(2 + tm * 8 + 4);
+        ptx::tc_fence_after();
+        const uint32_t tacc = tmem_base + tlane + (uint32_t)(acc * ACC_STRIDE);
+        if (f.type == PH_LSTM) {
+          uint8_t* img = f.hp_out + (size_t)(rt * (p.H / 64) + nt) * (2u * TC_A_IMG);
+          float hn[32];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int cb = half * 32 + jj * 16;
+            uint32_t r[64];
+            ptx::tmem_ld16x4_wait(tacc + cb, tacc + 64 + cb, tacc + 128 + cb, tacc + 192 + cb, r);
+            if (etid == 0 && tm == 0 && jj == 0) TRACE(26);
+            float cp[16], cn[16], hc[16];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 t = *reinterpret_cast<const float4*>(eb + lane * 128 + (((jj * 4 + c4) ^ (lane & 7)) << 4));
+              cp[c4 * 4 + 0] = t.x; cp[c4 * 4 + 1] = t.y; cp[c4 * 4 + 2] = t.z; cp[c4 * 4 + 3] = t.w;
+            }
+            if (held) {
+              load16(f.h_in + idx0 + jj * 16, hc);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) cn[i] = cp[i];
+            } else {
+              lstm_pointwise16(r, sb, cb, cp, hc, cn);
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)   // c' replaces c in place (same thread, same addresses)
+              *reinterpret_cast<float4*>(eb + lane * 128 + (((jj * 4 + c4) ^ (lane & 7)) << 4)) =
+                  make_float4(cn[c4 * 4], cn[c4 * 4 + 1], cn[c4 * 4 + 2], cn[c4 * 4 + 3]);
+            if (etid == 0 && tm == 0 && jj == 0) TRACE(27);
+            if (valid) store_split16(img, r_in_tile, (uint32_t)(cb >> 3), hc);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hn[jj * 16 + i] = hc[i];
+          }
+          if (etid == 0 && tm == 0) TRACE(28);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {      // c' tile -> global, 128-byte lines
+            const int rr = i * 4 + er;
+            const float4 t = *reinterpret_cast<const float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4));
+            if (row_w0 + rr < p.rows)
+              reinterpret_cast<float4*>(f.c_out + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32)[ec] = t;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<float4*>(eb + lane * 128 + ((c8 ^ (lane & 7)) << 4)) =
+                make_float4(hn[c8 * 4], hn[c8 * 4 + 1], hn[c8 * 4 + 2], hn[c8 * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {      // h' tile -> global
+            const int rr = i * 4 + er;
+            const float4 t = *reinterpret_cast<const float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4));
+            if (row_w0 + rr < p.rows)
+              reinterpret_cast<float4*>(f.h_out + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32)[ec] = t;
+          }
+          __syncwarp();
+          if (etid == 0 && tm == 0) TRACE(29);
+        } else if (f.type == PH_TANH) {
+          // y = tanh(acc + b): this warp owns rows q*32.. and columns half*n_tile/2 ..; groups of <= 32 columns go
+          // through the transpose buffer so the [rows, G] output is written in full row segments.
+          const int ncol_half = f.n_tile / 2;
+          const int c_begin = half * ncol_half;
+          const bool vec2 = (f.ldy & 1) == 0 && (f.n_valid & 1) == 0;
+          for (int g0 = 0; g0 < ncol_half; g0 += 32) {
+            const int gw = ncol_half - g0 < 32 ? ncol_half - g0 : 32;   // 32 or 16
+            for (int c16 = 0; c16 < gw; c16 += 16) {
+              float v[16];
+              ptx::tmem_ld16_wait(tacc + c_begin + g0 + c16, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = tanh_fast_prescaled(v[i], sb[c_begin + g0 + c16 + i]);
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4)
+                *reinterpret_cast<float4*>(eb + lane * 128 + ((((c16 >> 2) + c4) ^ (lane & 7)) << 4)) =
+                    make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+            }
+            __syncwarp();
+            const int lpr = gw >> 1;              // lanes per row (one float2 each)
+            const int rpi = 32 / lpr;             // rows per instruction
+            for (int i = 0; i < 32 / rpi; ++i) {
+              const int rr = i * rpi + lane / lpr;
+              const int cc = (lane % lpr) * 2;
+              const float2 t = *reinterpret_cast<const float2*>(eb + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4);
+              const int col = c_begin + g0 + cc;
+              const int grow = row_w0 + rr;
+              if (grow < p.rows && col < f.n_valid) {
+                float* dst = f.y + (size_t)grow * f.ldy + col;
+                if (vec2) *reinterpret_cast<float2*>(dst) = t;
+                else { dst[0] = t.x; if (col + 1 < f.n_valid) dst[1] = t.y; }
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+          const int nchunks = f.n_tile / 16;
+#pragma unroll 1
+          for (int jc = half; jc < nchunks; jc += 2) {
+            float v[16];
+            ptx::tmem_ld16_wait(tacc + jc * 16, v);
+            if (valid) {
+              const int col0 = nt * f.n_tile + jc * 16;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += sb[jc * 16 + i];
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const int zi = (col0 + i) >> 1;
+                if (zi < f.Z) {
+                  const size_t idx = (size_t)row * f.Z + zi;
+                  f.mu[idx] = v[i];
+                  f.logvar[idx] = v[i + 1];
+                  f.z[idx] = fmaf(f.eps[idx], expf(0.5f * v[i + 1]), v[i]);
+                }
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+          else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
+        }
+        if (etid == 0 && tm < 3) {
+          TRACE(2 + tm * 8 + 5);
+#ifdef DVG_TRACE
+          if (p.trace) p.trace[(size_t)blockIdx.x * 32 + 2 + tm * 8 + 6] = 1000000ull + item;
+#endif
+        }
+      }
+      // publish: everything this CTA wrote for the item is visible before the counter moves
+      if (f.done_flags != nullptr && f.type != PH_PACKX) {
+        __threadfence();
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+        if (etid == 0) atomicAdd(f.done_flags + rg, 1);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) TRACE(30);
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+}
+
+// W_x = W_ih0 W_e  ([4H, G]),  b_x = W_ih0 b_e + b_ih0 + b_hh0  -- the embed Linear folded into layer 0 (fp64 accumulate).
+__global__ void fold_embed_kernel(const float* __restrict__ w_ih0, const float* __restrict__ embed_w,
+                                  const float* __restrict__ embed_b, const float* __restrict__ b_ih0,
+                                  const float* __restrict__ b_hh0, int H, int G, float* __restrict__ wx,
+                                  float* __restrict__ bx) {
+  const int r = blockIdx.x;   // gate row 0..4H-1
+  for (int g = threadIdx.x; g <= G; g += blockDim.x) {
+    double acc = 0.0;
+    if (g < G) {
+      for (int k = 0; k < H; ++k) acc += (double)w_ih0[(size_t)r * H + k] * (double)embed_w[(size_t)k * G + g];
+      wx[(size_t)r * G + g] = (float)acc;
+    } else {
+      for (int k = 0; k < H; ++k) acc += (double)w_ih0[(size_t)r * H + k] * (double)embed_b[k];
+      bx[r] = (float)(acc + (double)b_ih0[r] + (double)b_hh0[r]);
+    }
   }
 }
 
@@ -771,8 +1236,19 @@ int lstm_tc_pack(dvg_lstm_s* h, const float* embed_w, const float* embed_b, cons
     if ((rc = plan_alloc(h->tc_layer[l], 256, hk, hk, hk))) return rc;
     if ((rc = plan_pack(h->tc_layer[l], w_ih[l], H, w_hh[l], H, b_ih[l], b_hh[l], 4 * H, 1, H, stream))) return rc;
   }
+  // layer 0 with the embed folded in (fused step kernel): K = [x (G padded to 64) | h_0]
+  {
+    if (!h->fold_wx) {
+      DVG_CUDA(cudaMalloc(&h->fold_wx, sizeof(float) * 4 * H * G));
+      DVG_CUDA(cudaMalloc(&h->fold_bx, sizeof(float) * 4 * H));
+    }
+    fold_embed_kernel<<<4 * H, 128, 0, stream>>>(w_ih[0], embed_w, embed_b, b_ih[0], b_hh[0], H, G, h->fold_wx, h->fold_bx);
+    DVG_LAUNCH_CHECK();
+    if ((rc = plan_alloc(h->tc_layer0f, 256, hk, ceil_div(G, 64), hk))) return rc;
+    if ((rc = plan_pack(h->tc_layer0f, h->fold_wx, G, w_hh[0], H, h->fold_bx, nullptr, 4 * H, 1, H, stream))) return rc;
+  }
   const int n_head = gauss ? 2 * h->dims.output_size : h->dims.output_size;
-  const int hn = (int)align_up(n_head, 16);
+  const int hn = (int)align_up(n_head, 32);
   DVG_REQUIRE(hn <= 256, "tensor-core head supports at most 256 output columns (got %d)", n_head);
   if ((rc = plan_alloc(h->tc_head, hn, 1, hk, 0))) return rc;
   if (gauss) {
@@ -792,6 +1268,12 @@ void lstm_tc_free(dvg_lstm_s* h) {
   };
   fr(h->tc_embed);
   fr(h->tc_head);
+  fr(h->tc_layer0f);
+  if (h->fold_wx) cudaFree(h->fold_wx);
+  if (h->fold_bx) cudaFree(h->fold_bx);
+  if (h->fused_flags) cudaFree(h->fused_flags);
+  h->fold_wx = h->fold_bx = nullptr;
+  h->fused_flags = nullptr;
   for (int l = 0; l < MAX_LAYERS; ++l) fr(h->tc_layer[l]);
 }
 
@@ -905,6 +1387,125 @@ static int launch_tc(const dvg_lstm_s* h, TcArgs& a, cudaStream_t stream) {
   return DVG_OK;
 }
 
+
+static bool use_fused() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVG_TC_FUSED");     // developer switch: 0 = one launch per GEMM
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+static int lstm_tc_step_fused(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in,
+                              const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
+                              float* y, int ldy, const float* eps, float* z, float* mu, float* logvar,
+                              const uint8_t* hold, int rows_per_flag, cudaStream_t stream) {
+  const int G = h->dims.input_size, H = h->dims.hidden_size, L = h->dims.n_layers;
+  const int hk = H / 64, RT = ceil_div(rows, TC_ROWS), kbx = ceil_div(G, 64);
+  const int groups = ceil_div(RT, 2);
+  const size_t lsz = (size_t)rows * H;
+  const size_t lpk = (size_t)RT * hk * 2 * TC_A_IMG;
+  FusedArgs a{};
+  a.rows = rows; a.row_tiles = RT; a.groups = groups; a.nsplit = nsplit; a.H = H;
+  a.hold = hold; a.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
+  int* flags = h->fused_flags;
+  DVG_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(L + 1) * h->fused_flag_stride, stream));
+  int np = 0, item = 0;
+  {  // PACKX
+    FusedPhase& f = a.ph[np];
+    f.type = PH_PACKX; f.n_tile = 0; f.n_tiles = 1; f.item_begin = item;
+    f.x = x; f.ldx = ldx; f.G = G; f.xp = h->tc_xp; f.kbx = kbx;
+    f.done_flags = flags;
+    ++np;   // no items: the x-pack runs as a prologue spread over all CTAs
+  }
+  for (int l = 0; l < L; ++l) {
+    FusedPhase& f = a.ph[np];
+    const TcGemmPlan& pl = l == 0 ? h->tc_layer0f : h->tc_layer[l];
+    f.type = PH_LSTM; f.n_tile = 256; f.n_tiles = hk; f.item_begin = item;
+    f.a0 = l == 0 ? h->tc_xp : hp_out + (l - 1) * lpk; f.kb0 = l == 0 ? kbx : hk;
+    f.a1 = hp_in + l * lpk; f.kb1 = hk;
+    f.w = pl.w; f.bias = pl.bias;
+    f.wait_flags = flags + (size_t)l * h->fused_flag_stride; f.wait_target = l == 0 ? -1 : 2 * hk;   // l == 0: per-group target set below
+    f.done_flags = flags + (size_t)(l + 1) * h->fused_flag_stride;
+    f.c_in = c_in + l * lsz; f.h_in = h_in + l * lsz; f.h_out = h_out + l * lsz; f.c_out = c_out + l * lsz;
+    f.hp_out = hp_out + l * lpk;
+    item += groups * hk; ++np;
+  }
+  {  // head
+    FusedPhase& f = a.ph[np];
+    const bool gauss = h->dims.kind == DVG_GAUSSIAN_LSTM;
+    f.type = gauss ? PH_GAUSS : PH_TANH; f.n_tile = h->tc_head.n_tile; f.n_tiles = 1; f.item_begin = item;
+    f.a0 = hp_out + (L - 1) * lpk; f.kb0 = hk; f.a1 = nullptr; f.kb1 = 0;
+    f.w = h->tc_head.w; f.bias = h->tc_head.bias;
+    f.wait_flags = flags + (size_t)L * h->fused_flag_stride; f.wait_target = 2 * hk;
+    f.done_flags = nullptr;
+    f.y = y; f.ldy = ldy; f.n_valid = h->dims.output_size;
+    f.eps = eps; f.z = z; f.mu = mu; f.logvar = logvar; f.Z = h->dims.output_size;
+    item += groups; ++np;
+  }
+  a.n_phases = np; a.total_items = item;
+  const size_t stage_bytes = 2 * (size_t)TC_A_IMG + 2 * (size_t)256 * 64;
+  const size_t tail = 128 + 2 * 256 * sizeof(float) + (size_t)EPI_WARPS * 4096;   // barriers, bias, transpose buffers
+  int stages = (int)((227 * 1024 - tail) / stage_bytes);
+  if (stages > 4) stages = 4;
+  a.stages = stages; a.stage_bytes = (uint32_t)stage_bytes;
+  const size_t smem = stages * stage_bytes + tail;
+  static bool configured = false;
+  if (!configured) {
+    DVG_CUDA(cudaFuncSetAttribute(lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  int pairs = h->sm_count / 2;
+  if (pairs > a.total_items) pairs = a.total_items;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pairs * 2);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef DVG_TRACE
+  static unsigned long long* tbuf = nullptr;
+  const bool tr = getenv("DVG_TC_TRACE") != nullptr;
+  if (tr) {
+    if (!tbuf) cudaMalloc(&tbuf, 256 * 32 * 8);
+    cudaMemsetAsync(tbuf, 0, 256 * 32 * 8, stream);
+    a.trace = tbuf;
+  }
+#endif
+  h->prof_mark(stream);
+  DVG_CUDA(cudaLaunchKernelEx(&cfg, lstm_fused_kernel, (const FusedArgs)a));
+  h->prof_mark(stream);
+#ifdef DVG_TRACE
+  if (tr) {
+    static int n_dump = 0;
+    cudaStreamSynchronize(stream);
+    if (n_dump++ == 4) {
+      std::vector<unsigned long long> hbuf(256 * 32);
+      cudaMemcpy(hbuf.data(), tbuf, 256 * 32 * 8, cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull;
+      for (int b = 0; b < (int)cfg.gridDim.x; ++b) if (hbuf[b * 32] && hbuf[b * 32] < t0) t0 = hbuf[b * 32];
+      fprintf(stderr, "FUSED TRACE grid=%d items=%d stages=%d: start setup | per MMA item: depwait depok stage0 mma_issued acc_ready epi_done item | end\n",
+              (int)cfg.gridDim.x, a.total_items, stages);
+      for (int b = 0; b < (int)cfg.gridDim.x; b += (b < 4 ? 1 : (b < 60 ? 6 : 8))) {
+        fprintf(stderr, "cta %3d:", b);
+        for (int i = 0; i < 31; ++i) {
+          unsigned long long v = hbuf[b * 32 + i];
+          if (i == 2 || i == 10 || i == 18 || i == 26) fprintf(stderr, " |");
+          if (v >= 1000000ull && v < 2000000ull) fprintf(stderr, " #%lld", (long long)(v - 1000000ull));
+          else fprintf(stderr, " %lld", v ? (long long)(v - t0) : -1ll);
+        }
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+#endif
+  return DVG_OK;
+}
+
 int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in,
                  const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out, float* y,
                  int ldy, const float* eps, float* z, float* mu, float* logvar, const uint8_t* hold,
@@ -914,6 +1515,9 @@ int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, c
   const size_t lsz = (size_t)rows * H;
   const size_t lpk = (size_t)RT * hk * 2 * TC_A_IMG;
   int rc;
+  if (use_fused() && use_pairs() && RT >= 2)
+    return lstm_tc_step_fused(h, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, eps, z, mu,
+                              logvar, hold, rows_per_flag, stream);
   h->prof_mark(stream);
   tc_pack_rows_kernel<<<dim3(RT, kbx), 256, 0, stream>>>(h->tc_xp, x, ldx, rows, G, kbx);
   DVG_LAUNCH_CHECK();
