@@ -121,7 +121,7 @@ def synth_latents(w, T, R, device, seed):
 def launches_per_rollout(w, T):
     # per time step: fused trigger kernel (1) + fused LSTM-step kernel (1; a cudaMemset node for its dependency
     # counters is not counted) + list-driven rsample kernel on decision steps (1)
-    return sum(2 + (0 if t < w["window"] else 1) for t in range(T))
+    return sum(2 + (0 if t < w["window"] else 1) for t in range(T)) + 1     # + the scoring kernel
 
 
 def flops_bytes(w, R):
@@ -136,7 +136,7 @@ def run_ours(args):
     import torch.distributed as dist
     from dvg_b200 import _capi
     from dvg_b200 import shard
-    from dvg_b200.rollout import RolloutConfig, RolloutEngine
+    from dvg_b200.rollout import RolloutConfig, RolloutEngine, score_rollouts
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -161,7 +161,7 @@ def run_ours(args):
     target = lat[:, :B].clone()
 
     def select_best():
-        sc = (out.view(T, S, B, -1) - target.view(T, 1, B, -1)).pow(2).mean(dim=(0, 3))   # [S_local, B]
+        sc = score_rollouts(out, target, S, B)              # [S_local, B], one fused pass over `out`
         allsc = shard.gather_scores(sc, world * S)          # the only collective: one all-gather of scores
         return shard.select_best(allsc, higher_is_better=False)
 

@@ -229,7 +229,7 @@ int dvg_gauss_lstm_step(dvg_lstm_t h, int variant, int rows, const float* x, int
 static void gp_free_all(dvg_gp_s* h) {
   auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
   fr(h->z); fr(h->linv); fr(h->lqt); fr(h->alpha); fr(h->hyp); fr(h->work); fr(h->var_rows);
-  fr(h->ticket); fr(h->trig_list); fr(h->trig_count);
+  fr(h->ticket); fr(h->trig_list); fr(h->trig_count); fr(h->linvT); fr(h->lq);
 }
 
 int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* var_mean,
@@ -246,6 +246,8 @@ int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing
   if (e == cudaSuccess) e = cudaMalloc(&h->z, sizeof(float) * D * mp);
   if (e == cudaSuccess) e = cudaMalloc(&h->linv, sizeof(float) * D * mp * mp);
   if (e == cudaSuccess) e = cudaMalloc(&h->lqt, sizeof(float) * D * mp * mp);
+  if (e == cudaSuccess) e = cudaMalloc(&h->linvT, sizeof(float) * D * mp * mp);
+  if (e == cudaSuccess) e = cudaMalloc(&h->lq, sizeof(float) * D * mp * mp);
   if (e == cudaSuccess) e = cudaMalloc(&h->alpha, sizeof(float) * D * mp);
   if (e == cudaSuccess) e = cudaMalloc(&h->hyp, sizeof(float) * D * 4);
   if (e == cudaSuccess) e = cudaMalloc(&h->work, sizeof(double) * D * M * M);
@@ -253,8 +255,8 @@ int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing
   if (e == cudaSuccess) e = cudaMalloc(&h->var_rows, sizeof(float) * D * h->var_rows_cap);
   if (e == cudaSuccess) e = cudaMalloc(&h->trig_list, sizeof(int) * h->var_rows_cap);
   if (e == cudaSuccess) e = cudaMalloc(&h->trig_count, sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, sizeof(unsigned int) * (1 + h->var_rows_cap / 8 + 1));
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int) * (1 + h->var_rows_cap / 8 + 1));
   if (e == cudaSuccess) e = cudaMemset(h->trig_count, 0, sizeof(int));
   if (e != cudaSuccess) {
     set_error("GP handle allocation failed: %s", cudaGetErrorString(e));
@@ -312,6 +314,10 @@ int dvg_gp_trigger(dvg_gp_t h, int n_rollouts, const float* x, int ldx, const in
     if (h->trig_list) cudaFree(h->trig_list);
     h->trig_list = nullptr;
     DVG_CUDA(cudaMalloc(&h->trig_list, sizeof(int) * (size_t)n_rollouts));
+    if (h->ticket) cudaFree(h->ticket);
+    h->ticket = nullptr;
+    DVG_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int) * (size_t)(2 + n_rollouts / 8)));
+    DVG_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int) * (size_t)(2 + n_rollouts / 8)));
     h->var_rows_cap = n_rollouts;
   }
   return gp_trigger_launch(h, n_rollouts, x, ldx, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,
@@ -336,6 +342,13 @@ int dvg_gp_export(dvg_gp_t h, float* linv, float* lq, float* alpha, float* hyp, 
   if (alpha) DVG_CUDA(cudaMemcpyAsync(alpha, h->alpha, sizeof(float) * D * mp, cudaMemcpyDeviceToDevice, s));
   if (hyp) DVG_CUDA(cudaMemcpyAsync(hyp, h->hyp, sizeof(float) * D * 4, cudaMemcpyDeviceToDevice, s));
   return DVG_OK;
+}
+
+int dvg_rollout_score(int n_steps, int n_rollouts, int n_points, int dim, const float* latents, const float* target,
+                      float* scores, dvg_stream_t stream) {
+  DVG_REQUIRE(latents && target && scores, "null argument");
+  DVG_REQUIRE(n_steps > 0 && n_rollouts > 0 && n_points > 0 && dim > 0, "bad sizes");
+  return rollout_score_launch(n_steps, n_rollouts, n_points, dim, latents, target, scores, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, int mp, d
                                                          const float* __restrict__ raw_ls,
                                                          const float* __restrict__ raw_noise, float* __restrict__ z_out,
                                                          float* __restrict__ linv_out, float* __restrict__ lqt_out,
+                                                         float* __restrict__ linvT_out, float* __restrict__ lq_out,
                                                          float* __restrict__ alpha_out, float* __restrict__ hyp_out,
                                                          double* __restrict__ work) {
   extern __shared__ double sm[];
@@ -107,6 +108,8 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, int mp, d
     }
     linv_out[((size_t)d * mp + r) * mp + q] = lv;
     lqt_out[((size_t)d * mp + r) * mp + q] = qv;
+    linvT_out[((size_t)d * mp + q) * mp + r] = lv;   // transposed copies: lane-per-row kernels read [m][j]
+    lq_out[((size_t)d * mp + q) * mp + r] = qv;
   }
 }
 
@@ -245,56 +248,20 @@ __device__ float np_pairwise_sum(const float* a, int n) {
 
 constexpr int MAX_WINDOW = 128;
 
-// One rollout's decision (numpy float32 arithmetic, see oracle/trigger_ref.py).  Returns the mask bit.
-__device__ int gp_trigger_decide(int s, int D, const float* vrow, float* window, int W, int cnt, int warmup,
-                                 float factor, float* value, float* thr, uint8_t* mask) {
-  // generate_frames.py:230 -- np.linalg.norm(variance^T, axis=1): sequential fp32 sum over d
-  float acc = 0.f;
-  for (int d = 0; d < D; ++d) {
-    const float v = vrow[d];
-    acc = __fadd_rn(acc, __fmul_rn(v, v));
-  }
-  const float val = sqrtf(acc);
-  float* w = window + (size_t)s * W;
-  if (value) value[s] = val;
-  if (warmup) {
-    if (cnt < W) w[cnt] = val;
-    else {  // window already full: keep sliding without a decision
-      for (int i = 0; i + 1 < W; ++i) w[i] = w[i + 1];
-      w[W - 1] = val;
-    }
-    if (thr) thr[s] = nanf("");
-    if (mask) mask[s] = 0;
-    return 0;
-  }
-  float loc[MAX_WINDOW];
-  for (int i = 0; i + 1 < W; ++i) loc[i] = w[i + 1];   // generate_frames.py:231
-  loc[W - 1] = val;
-  for (int i = 0; i < W; ++i) w[i] = loc[i];
-  const float mean = __fdiv_rn(np_pairwise_sum(loc, W), (float)W);
-  for (int i = 0; i < W; ++i) {
-    const float dlt = __fsub_rn(loc[i], mean);
-    loc[i] = __fmul_rn(dlt, dlt);
-  }
-  const float sd = sqrtf(__fdiv_rn(np_pairwise_sum(loc, W), (float)W));
-  const float t = __fadd_rn(mean, __fmul_rn(factor, sd));  // generate_frames.py:288
-  const int fired = val > t ? 1 : 0;                       // generate_frames.py:289
-  if (thr) thr[s] = t;
-  if (mask) mask[s] = (uint8_t)fired;
-  return fired;
-}
-
-// Fused trigger: grid (ceil(S/128), D).  Phase 1: variance at the statistic row of every rollout for this CTA's
-// latent dim -> var_rows[s][d].  Phase 2 (the LAST CTA to finish, found with an atomic ticket): per-rollout norm,
-// window update, threshold, decision, warm-up counter bump, and a compacted list of the rollouts that fired
-// (consumed by gp_rsample_list_kernel) -- one launch instead of predict + finalize + counter kernels.
+// Fused trigger: grid (ceil(S/128), D), 256 threads.  Phase 1: two threads per (rollout, dim) task -- thread h=0
+// accumulates |Linv k|^2, thread h=1 accumulates |L_q^T k|^2 -- with the factors of the CTA's dim staged in
+// shared memory (warp-broadcast float4 reads) and k[] in registers; var_rows is written TRANSPOSED [D][S] so both
+// this store and the finalize loads are coalesced.  Phase 2 (the last CTA to finish, atomic ticket): one thread
+// per rollout loads its D variances in register batches of 32 (independent loads, one L2 round trip per batch),
+// sums them in numpy's sequential fp32 order, updates the window, thresholds, decides, and appends fired
+// rollouts to the compacted list used by gp_rsample_list_kernel.  (History: thread-per-task without the v/w split
+// was 10 us + 2 more launches; a warp-per-task variant was issue-bound at 33 us.)
 template <int MREG>
-__global__ void __launch_bounds__(128) gp_trigger_kernel(int S, int D, int mp, const float* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256) gp_trigger_kernel(int S, int D, int mp, const float* __restrict__ x, int ldx,
                                                          const int32_t* __restrict__ stat_rows,
                                                          const float* __restrict__ zall,
                                                          const float* __restrict__ linv_all,
                                                          const float* __restrict__ lqt_all,
-                                                         const float* __restrict__ alpha_all,
                                                          const float* __restrict__ hyp, float* var_rows,
                                                          unsigned int* ticket, float* window, int W, int32_t* count,
                                                          int warmup, float factor, float* value, float* thr,
@@ -306,54 +273,114 @@ __global__ void __launch_bounds__(128) gp_trigger_kernel(int S, int D, int mp, c
   float* s_linv = smf;
   float* s_lqt = s_linv + MP * MP;
   float* s_z = s_lqt + MP * MP;
-  float* s_alpha = s_z + MP;
-  float* s_k = s_alpha + MP;
-  const int i = blockIdx.x * 128 + tid;
+  const int half = tid >> 7;                 // 0: v = Linv k,  1: w = L_q^T k
+  const int li = tid & 127;
+  const int i = blockIdx.x * 128 + li;
   float xv = 0.f;
-  if (i < S) xv = __ldg(x + (size_t)stat_rows[i] * ldx + d);    // issue the (DRAM) load before staging
-  gp_stage_dim(d, MP, tid, zall, linv_all, lqt_all, alpha_all, s_linv, s_lqt, s_z, s_alpha);
-  __syncthreads();
-  if (i < S) {
-    const float ell = hyp[d * 4 + 0], s = hyp[d * 4 + 1], noise = hyp[d * 4 + 3];
-    float mu, vv, ww;
-    gp_row_eval<MREG>(xv, s, 1.0f / ell, MP, tid, s_linv, s_lqt, s_z, s_alpha, s_k, mu, vv, ww);
-    var_rows[(size_t)i * D + d] = (s - vv) + ww + noise;
+  if (i < S) xv = __ldg(x + (size_t)stat_rows[i] * ldx + d);     // issue the (possibly DRAM) load before staging
+  {
+    const float4* g1 = reinterpret_cast<const float4*>(linv_all + (size_t)d * MP * MP);
+    const float4* g2 = reinterpret_cast<const float4*>(lqt_all + (size_t)d * MP * MP);
+    for (int e = tid; e < MP * MP / 4; e += 256) {
+      reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
+      reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
+    }
+    for (int e = tid; e < MP; e += 256) s_z[e] = zall[(size_t)d * MP + e];
   }
+  __syncthreads();
+  const float ell = hyp[d * 4 + 0], sc = hyp[d * 4 + 1], noise = hyp[d * 4 + 3];
+  const float inv_ell = 1.0f / ell;
+  float part = 0.f;                           // |v|^2 (half 0) or |w|^2 (half 1)
+  if (i < S) {
+    const float* mat = half == 0 ? s_linv : s_lqt;
+    if (MREG > 0) {
+      float k[MREG > 0 ? MREG : 1];
+#pragma unroll
+      for (int m = 0; m < MREG; ++m) {
+        const float t = (xv - s_z[m]) * inv_ell;
+        k[m] = sc * expf(-0.5f * t * t);
+      }
+#pragma unroll
+      for (int j = 0; j < MREG; ++j) {
+        // row j of Linv is non-zero for m <= j, row j of L_q^T for m >= j; both are zero padded, so use the
+        // full row (branch-free, identical code for the two halves) with two accumulators
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int m = 0; m < MREG; m += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(mat + j * MREG + m);
+          a0 = fmaf(l4.x, k[m], a0); a1 = fmaf(l4.y, k[m + 1], a1); a0 = fmaf(l4.z, k[m + 2], a0); a1 = fmaf(l4.w, k[m + 3], a1);
+        }
+        const float a = a0 + a1;
+        part = fmaf(a, a, part);
+      }
+    } else {
+      for (int j = 0; j < MP; ++j) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int m = 0; m < MP; m += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(mat + j * MP + m);
+          float kq[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float t = (xv - s_z[m + e]) * inv_ell;
+            kq[e] = sc * expf(-0.5f * t * t);
+          }
+          a0 = fmaf(l4.x, kq[0], a0); a1 = fmaf(l4.y, kq[1], a1); a0 = fmaf(l4.z, kq[2], a0); a1 = fmaf(l4.w, kq[3], a1);
+        }
+        const float a = a0 + a1;
+        part = fmaf(a, a, part);
+      }
+    }
+  }
+  // combine the two halves through shared memory (smf is dead after the barrier)
+  __syncthreads();
+  if (half == 1) smf[li] = part;
+  __syncthreads();
+  if (half == 0 && i < S) var_rows[(size_t)d * S + i] = (sc - part) + smf[li] + noise;
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1 ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (tid == 0) *trig_count = 0;
   const int cnt = count[0];
-  __syncthreads();
-  // the matrices in smf are dead now: reuse the buffer for 128 variance rows at a time (coalesced L2 reads;
-  // a per-thread dependent chain of 90 L2 loads made this phase 18 us)
-  for (int base = 0; base < S; base += 128) {
-    const int nrow = S - base < 128 ? S - base : 128;
-    __syncthreads();
-    {  // 8 independent loads in flight per thread (a plain strided loop serialises ~70 L2 round trips)
-      const float* src = var_rows + (size_t)base * D;
-      const int n = nrow * D;
-      for (int e0 = 0; e0 < n; e0 += 128 * 8) {
-        float t[8];
+  for (int s = tid; s < S; s += 256) {
+    float acc = 0.f;
+    for (int d0 = 0; d0 < D; d0 += 32) {
+      float v[32];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * 128 + tid;
-          t[u] = e < n ? __ldcg(src + e) : 0.f;
-        }
+      for (int u = 0; u < 32; ++u) v[u] = d0 + u < D ? __ldcg(var_rows + (size_t)(d0 + u) * S + s) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * 128 + tid;
-          if (e < n) smf[e] = t[u];
-        }
-      }
+      for (int u = 0; u < 32; ++u)
+        if (d0 + u < D) acc = __fadd_rn(acc, __fmul_rn(v[u], v[u]));   // generate_frames.py:230, sequential in d
     }
-    __syncthreads();
-    const int s = base + tid;
-    if (tid < nrow && gp_trigger_decide(s, D, smf + tid * D, window, W, cnt, warmup, factor, value, thr, mask))
-      trig_list[atomicAdd(trig_count, 1)] = s;
+    const float val = sqrtf(acc);
+    float* wdw = window + (size_t)s * W;
+    int fired = 0;
+    if (value) value[s] = val;
+    if (warmup) {
+      if (cnt < W) wdw[cnt] = val;
+      else {
+        for (int q = 0; q + 1 < W; ++q) wdw[q] = wdw[q + 1];
+        wdw[W - 1] = val;
+      }
+      if (thr) thr[s] = nanf("");
+    } else {
+      float loc[MAX_WINDOW];
+      for (int q = 0; q + 1 < W; ++q) loc[q] = wdw[q + 1];   // generate_frames.py:231
+      loc[W - 1] = val;
+      for (int q = 0; q < W; ++q) wdw[q] = loc[q];
+      const float mean = __fdiv_rn(np_pairwise_sum(loc, W), (float)W);
+      for (int q = 0; q < W; ++q) {
+        const float dlt = __fsub_rn(loc[q], mean);
+        loc[q] = __fmul_rn(dlt, dlt);
+      }
+      const float sd = sqrtf(__fdiv_rn(np_pairwise_sum(loc, W), (float)W));
+      const float t = __fadd_rn(mean, __fmul_rn(factor, sd));  // generate_frames.py:288
+      fired = val > t ? 1 : 0;                                  // generate_frames.py:289
+      if (thr) thr[s] = t;
+    }
+    if (mask) mask[s] = (uint8_t)fired;
+    if (fired) trig_list[atomicAdd(trig_count, 1)] = s;
   }
   if (tid == 0) {
     *ticket = 0;                                   // ready for the next launch
@@ -497,7 +524,7 @@ int gp_prepare_launch(dvg_gp_s* h, const float* inducing, const float* var_mean,
   }
   gp_prepare_kernel<<<D, 128, smem, stream>>>(D, M, h->mp, (double)h->dims.jitter, (double)h->dims.noise_lower_bound,
                                               inducing, var_mean, chol_var, mean_const, raw_os, raw_ls, raw_noise,
-                                              h->z, h->linv, h->lqt, h->alpha, h->hyp, h->work);
+                                              h->z, h->linv, h->lqt, h->linvT, h->lq, h->alpha, h->hyp, h->work);
   DVG_LAUNCH_CHECK();
   return DVG_OK;
 }
@@ -532,32 +559,25 @@ int gp_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t
   DVG_REQUIRE(W >= 1 && W <= MAX_WINDOW, "window_len must be in [1,%d]", MAX_WINDOW);
   DVG_REQUIRE(S <= h->var_rows_cap, "n_rollouts=%d exceeds the reserved trigger scratch (%d)", S, h->var_rows_cap);
   const int D = h->dims.num_dims, mp = h->mp;
+  // the fired list is rebuilt by every call: reset its counter first (tiny memset node)
+  DVG_CUDA(cudaMemsetAsync(h->trig_count, 0, sizeof(int), stream));
   dim3 grid(ceil_div(S, 128), D);
+  size_t smem = sizeof(float) * ((size_t)2 * mp * mp + mp);
+  if (smem < 128 * sizeof(float)) smem = 128 * sizeof(float);
+  DVG_REQUIRE(smem <= 226 * 1024, "num_inducing=%d too large for the shared-memory trigger kernel", mp);
   static bool configured = false;
   if (!configured) {
-    DVG_CUDA(cudaFuncSetAttribute(gp_trigger_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));  // + static smem
+    DVG_CUDA(cudaFuncSetAttribute(gp_trigger_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
-  const size_t fin_smem = sizeof(float) * 128 * (size_t)D;   // finalize phase: 128 variance rows
-  if (mp == 40) {
-    size_t smem = sizeof(float) * (2 * 40 * 40 + 2 * 40);
-    if (smem < fin_smem) smem = fin_smem;
-    static bool c40 = false;
-    if (!c40) {
-      DVG_CUDA(cudaFuncSetAttribute(gp_trigger_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      c40 = true;
-    }
-    gp_trigger_kernel<40><<<grid, 128, smem, stream>>>(S, D, mp, x, ldx, stat_rows, h->z, h->linv, h->lqt, h->alpha, h->hyp,
+  if (mp == 40)
+    gp_trigger_kernel<40><<<grid, 256, smem, stream>>>(S, D, mp, x, ldx, stat_rows, h->z, h->linv, h->lqt, h->hyp,
                                                        h->var_rows, h->ticket, window, W, count, warmup, factor, value,
                                                        thr, mask, h->trig_list, h->trig_count);
-  } else {
-    size_t smem = sizeof(float) * ((size_t)2 * mp * mp + 2 * mp + (size_t)mp * 128);
-    if (smem < fin_smem) smem = fin_smem;
-    DVG_REQUIRE(smem <= 226 * 1024, "num_inducing=%d too large for the shared-memory predictive kernel", mp);
-    gp_trigger_kernel<0><<<grid, 128, smem, stream>>>(S, D, mp, x, ldx, stat_rows, h->z, h->linv, h->lqt, h->alpha, h->hyp,
+  else
+    gp_trigger_kernel<0><<<grid, 256, smem, stream>>>(S, D, mp, x, ldx, stat_rows, h->z, h->linv, h->lqt, h->hyp,
                                                       h->var_rows, h->ticket, window, W, count, warmup, factor, value,
                                                       thr, mask, h->trig_list, h->trig_count);
-  }
   DVG_LAUNCH_CHECK();
   h->last_mask = mask;   // dvg_gp_rsample(mask == this pointer) may use the compacted list
   h->last_mask_rollouts = S;

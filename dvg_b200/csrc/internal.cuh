@@ -68,12 +68,14 @@ struct dvg_gp_s {
   float* z = nullptr;         // [D][mp] inducing points
   float* linv = nullptr;      // [D][mp][mp] L_ZZ^-1 (lower triangular, zero padded)
   float* lqt = nullptr;       // [D][mp][mp] L_q^T  (upper triangular: lqt[j][i] = L_q[i][j], i >= j)
+  float* linvT = nullptr;     // [D][mp][mp] transpose of linv  (lane-per-row trigger kernel reads [m][j])
+  float* lq = nullptr;        // [D][mp][mp] masked L_q, row-major
   float* alpha = nullptr;     // [D][mp] beta = L_ZZ^-1 (m_q - c)
   float* hyp = nullptr;       // [D][4]  ell, s, c, noise
   double* work = nullptr;     // fp64 scratch for prepare [D][3][M][M]
   float* var_rows = nullptr;  // scratch [max_rollouts][D] for the trigger
   int var_rows_cap = 0;
-  unsigned int* ticket = nullptr;   // last-CTA-done counter of the fused trigger kernel (self-resetting)
+  unsigned int* ticket = nullptr;   // [1 + max groups] last-CTA tickets of the fused trigger kernel (self-resetting)
   int* trig_list = nullptr;         // [max_rollouts] compacted rollouts that fired in the last trigger call
   int* trig_count = nullptr;
   const uint8_t* last_mask = nullptr;  // mask buffer the list corresponds to
@@ -117,5 +119,9 @@ int gp_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t
                       cudaStream_t stream);
 int gp_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const float* eps, const uint8_t* mask,
                       float* out, int ldo, cudaStream_t stream);
+
+// rollout.cu
+int rollout_score_launch(int T, int S, int B, int G, const float* out, const float* target, float* scores,
+                         cudaStream_t stream);
 
 }  // namespace dvg

@@ -181,6 +181,18 @@ class RolloutEngine:
         return g
 
 
+def score_rollouts(out: torch.Tensor, target: torch.Tensor, n_rollouts: int, n_points: int) -> torch.Tensor:
+    """Latent-space best-of-N scoring on the device (one pass, ``dvg_rollout_score``): ``out`` [T, S*B, G],
+    ``target`` [T, B, G] -> mean-squared-error scores [S, B] (lower is better)."""
+    T, R, G = out.shape
+    assert R == n_rollouts * n_points and target.shape == (T, n_points, G)
+    assert out.is_cuda and out.is_contiguous() and target.is_contiguous()
+    scores = torch.empty(n_rollouts, n_points, device=out.device, dtype=torch.float32)
+    _capi.check(_capi.load().dvg_rollout_score(T, n_rollouts, n_points, G, _capi.ptr(out), _capi.ptr(target),
+                                               _capi.ptr(scores), _capi.stream_ptr()), "dvg_rollout_score")
+    return scores
+
+
 # -------------------------------------------------------------------------------------------------------
 # Pixel-space drivers (encoder / decoder are the reference conv nets on the stock PyTorch path)
 # -------------------------------------------------------------------------------------------------------

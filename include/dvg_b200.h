@@ -198,6 +198,15 @@ DVG_API int dvg_gp_rsample(dvg_gp_t h, int n_rollouts, int n_points, const float
  *   hyp [D,4] = (ell, s, c, noise). */
 DVG_API int dvg_gp_export(dvg_gp_t h, float* linv, float* lqt, float* alpha, float* hyp, dvg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N-diverse-futures bookkeeping
+ * ---------------------------------------------------------------------------------------------- */
+/* Device-side scoring pass of the best-of-N selection (the reference scores every sample on the host after a
+ * D2H copy per frame, generate_frames.py:175-178,185-190): scores[s, b] = mean over (t, g) of
+ * (latents[t, s*B + b, g] - target[t, b, g])^2.  latents [T, S*B, dim] dense, target [T, B, dim], scores [S, B]. */
+DVG_API int dvg_rollout_score(int n_steps, int n_rollouts, int n_points, int dim, const float* latents,
+                      const float* target, float* scores, dvg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,14 @@ def test_cuda_graph_latent_rollout_equals_eager():
     assert torch.equal(m_e, m_g)
     assert torch.equal(out_e, out_g)
     assert 0 < int(m_e.sum()) < m_e.numel()
+
+
+def test_score_rollouts_matches_torch():
+    from dvg_b200.rollout import score_rollouts
+    T, S, B = 7, 5, 6
+    g = torch.Generator().manual_seed(3)
+    out = torch.randn(T, S * B, G, generator=g).cuda()
+    target = torch.randn(T, B, G, generator=g).cuda()
+    got = score_rollouts(out, target, S, B)
+    want = (out.view(T, S, B, G) - target.view(T, 1, B, G)).double().pow(2).mean(dim=(0, 3))
+    assert relerr(got, want) < 1e-5
