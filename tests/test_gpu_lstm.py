@@ -169,3 +169,47 @@ def test_autograd_delegate_matches_fast_path():
         m.hidden = m.init_hidden()
         y = m(x)
     assert relerr(y, y_grad) < 2e-5
+
+
+# --- BASELINE.json configs as parity cases (config 1, 3, 4 row counts; config 5 hidden sizes) -------------------
+@pytest.mark.parametrize("rows,H,L", [(16, 256, 2),        # cfg 1: SM-MNIST, batch 16, one rollout
+                                      (1600, 256, 2),      # cfg 3: BAIR, 32 rollouts x 50 per GPU
+                                      (6400, 256, 2),      # cfg 4: UCF, batch 64 x 100 samples
+                                      (257, 512, 1),       # cfg 5 sweep: hidden 512 (odd row count: 3 row tiles)
+                                      (130, 1024, 2)])     # cfg 5 sweep: hidden 1024
+def test_config_shapes(rows, H, L):
+    sd = lstm_ref.random_lstm_state_dict(90, 90, H, L, seed=H + rows)
+    gen = torch.Generator().manual_seed(1)
+    xs = [torch.tanh(torch.randn(rows, 90, generator=gen)) for _ in range(3)]
+    for variant in ("bf16x3", "fp32"):
+        m = make_lstm(sd, rows=rows, variant=variant)
+        hid = lstm_ref.init_hidden(L, rows, H)
+        with torch.no_grad():
+            m.hidden = m.init_hidden()
+            for t, x in enumerate(xs):
+                y_ref, hid = lstm_ref.lstm_forward(sd, x, hid)
+                y = m(x.cuda())
+                tol = TOL[variant] * (1 if t == 0 else 3)
+                assert relerr(y, y_ref) < tol, (variant, t, relerr(y, y_ref))
+                assert relerr(m.hidden[L - 1][0], hid[L - 1][0]) < tol, (variant, t)
+                assert relerr(m.hidden[0][1], hid[0][1]) < tol, (variant, t)
+
+
+def test_unfused_tensor_core_path_matches_fused(monkeypatch):
+    """The one-launch-per-GEMM tensor-core path (used for a single row tile) and the fused persistent step
+    kernel must agree: run 300 rows (fused) against the same rows split into 3 calls of 100 (single tile)."""
+    sd = lstm_ref.random_lstm_state_dict(90, 90, 256, 2, seed=21)
+    x = torch.tanh(torch.randn(300, 90, generator=torch.Generator().manual_seed(2))).cuda()
+    with torch.no_grad():
+        big = make_lstm(sd, rows=300, variant="bf16x3")
+        big.hidden = big.init_hidden()
+        y_big = big(x)
+        y_big = big(y_big)
+        outs = []
+        for i in range(3):
+            small = make_lstm(sd, rows=100, variant="bf16x3")
+            small.hidden = small.init_hidden()
+            y = small(x[i * 100:(i + 1) * 100])
+            outs.append(small(y))
+        y_small = torch.cat(outs)
+    assert relerr(y_big, y_small) < 2e-5
