@@ -119,9 +119,9 @@ def synth_latents(w, T, R, device, seed):
 
 
 def launches_per_rollout(w, T):
-    # per time step: fused trigger kernel (1) + fused LSTM-step kernel (1; a cudaMemset node for its dependency
-    # counters is not counted) + list-driven rsample kernel on decision steps (1)
-    return sum(2 + (0 if t < w["window"] else 1) for t in range(T)) + 1     # + the scoring kernel
+    # per time step: ONE persistent kernel (GP trigger + whole LSTM step; a cudaMemset node for its counters is
+    # not counted) + the list-driven rsample kernel on decision steps; + one scoring kernel per rollout
+    return sum(1 + (0 if t < w["window"] else 1) for t in range(T)) + 1
 
 
 def flops_bytes(w, R):

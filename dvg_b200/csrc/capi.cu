@@ -125,7 +125,7 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
     if (h->fused_flags) cudaFree(h->fused_flags);
     h->fused_flags = nullptr;
     h->fused_flag_stride = (int)align_up((size_t)ceil_div(ceil_div(rows, 128), 2), 32);
-    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * (size_t)(h->dims.n_layers + 1) * h->fused_flag_stride));
+    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * ((size_t)(h->dims.n_layers + 1) * h->fused_flag_stride + 1)));
   }
   h->reserved_rows = rows;
   return DVG_OK;
@@ -342,6 +342,35 @@ int dvg_gp_export(dvg_gp_t h, float* linv, float* lq, float* alpha, float* hyp, 
   if (alpha) DVG_CUDA(cudaMemcpyAsync(alpha, h->alpha, sizeof(float) * D * mp, cudaMemcpyDeviceToDevice, s));
   if (hyp) DVG_CUDA(cudaMemcpyAsync(hyp, h->hyp, sizeof(float) * D * 4, cudaMemcpyDeviceToDevice, s));
   return DVG_OK;
+}
+
+int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows, const float* x, int ldx, const void* state_in,
+                     void* state_out, float* y, int ldy, int n_rollouts, const int32_t* stat_rows, float* window,
+                     int window_len, int32_t* count, int warmup, float factor, float* value, float* thr, uint8_t* mask,
+                     dvg_stream_t stream) {
+  DVG_REQUIRE(h && g && x && state_in && state_out && y && stat_rows && window && count && mask, "null argument");
+  DVG_REQUIRE(h->dims.kind == DVG_LSTM, "handle is not an lstm");
+  DVG_REQUIRE(n_rollouts > 0 && rows % n_rollouts == 0, "rows must be a multiple of n_rollouts");
+  DVG_REQUIRE(h->dims.input_size == g->dims.num_dims, "latent size mismatch between LSTM and GP");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tc = variant == DVG_BF16X3 || variant == DVG_BF16;
+  if (tc && rows <= h->reserved_rows && n_rollouts <= g->var_rows_cap && window_len >= 1 && window_len <= 128 &&
+      ldx >= h->dims.input_size && ldy >= h->dims.output_size && state_in != state_out &&
+      lstm_tc_can_fuse_trigger(h, g, rows)) {
+    const size_t lsz = (size_t)h->dims.n_layers * rows * h->dims.hidden_size;
+    const size_t poff = dvg_lstm_state_packed_offset(h, rows);
+    const float* h_in = (const float*)state_in;
+    float* h_out = (float*)state_out;
+    return lstm_tc_rollout_step(h, g, variant == DVG_BF16 ? 1 : 3, rows, x, ldx, h_in, h_in + lsz,
+                                (const uint8_t*)state_in + poff, h_out, h_out + lsz, (uint8_t*)state_out + poff, y, ldy,
+                                n_rollouts, stat_rows, window, window_len, count, warmup, factor, value, thr, mask, s);
+  }
+  // not fusable (fp32 variant, single row tile, large inducing set, scratch not reserved): two calls, same semantics
+  int rc = dvg_gp_trigger(g, n_rollouts, x, ldx, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,
+                          stream);
+  if (rc) return rc;
+  return dvg_lstm_step(h, variant, rows, x, ldx, state_in, state_out, y, ldy, warmup ? nullptr : mask,
+                       rows / n_rollouts, stream);
 }
 
 int dvg_rollout_score(int n_steps, int n_rollouts, int n_points, int dim, const float* latents, const float* target,

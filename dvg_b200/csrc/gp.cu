@@ -13,6 +13,7 @@
 //   var   = s - |v|^2 + |w|^2 + noise
 // K_ZZ, its Cholesky factor, Linv and alpha are constant in eval mode; the reference recomputes them on
 // every call, here gp_prepare_kernel builds them once per weight load in fp64.
+#include "gp_trigger.cuh"
 #include "internal.cuh"
 
 namespace dvg {
@@ -228,25 +229,7 @@ __global__ void __launch_bounds__(128) gp_predict_kernel(int n_rows, int D, int 
 // ---------------------------------------------------------------------------------------------------
 // trigger finalize: one thread per rollout.  numpy-order float32 arithmetic (see oracle/trigger_ref.py).
 // ---------------------------------------------------------------------------------------------------
-__device__ float np_pairwise_sum(const float* a, int n) {
-  // numpy's pairwise_sum for n <= 128 (float32 add.reduce of a contiguous vector)
-  if (n < 8) {
-    float r = 0.f;
-    for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
-    return r;
-  }
-  float r[8];
-  for (int j = 0; j < 8; ++j) r[j] = a[j];
-  int i = 8;
-  for (; i < n - (n % 8); i += 8)
-    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
-  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __fadd_rn(res, a[i]);
-  return res;
-}
 
-constexpr int MAX_WINDOW = 128;
 
 // Fused trigger: grid (ceil(S/128), D), 256 threads.  Phase 1: two threads per (rollout, dim) task -- thread h=0
 // accumulates |Linv k|^2, thread h=1 accumulates |L_q^T k|^2 -- with the factors of the CTA's dim staged in
@@ -289,48 +272,8 @@ __global__ void __launch_bounds__(256) gp_trigger_kernel(int S, int D, int mp, c
   }
   __syncthreads();
   const float ell = hyp[d * 4 + 0], sc = hyp[d * 4 + 1], noise = hyp[d * 4 + 3];
-  const float inv_ell = 1.0f / ell;
   float part = 0.f;                           // |v|^2 (half 0) or |w|^2 (half 1)
-  if (i < S) {
-    const float* mat = half == 0 ? s_linv : s_lqt;
-    if (MREG > 0) {
-      float k[MREG > 0 ? MREG : 1];
-#pragma unroll
-      for (int m = 0; m < MREG; ++m) {
-        const float t = (xv - s_z[m]) * inv_ell;
-        k[m] = sc * expf(-0.5f * t * t);
-      }
-#pragma unroll
-      for (int j = 0; j < MREG; ++j) {
-        // row j of Linv is non-zero for m <= j, row j of L_q^T for m >= j; both are zero padded, so use the
-        // full row (branch-free, identical code for the two halves) with two accumulators
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int m = 0; m < MREG; m += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(mat + j * MREG + m);
-          a0 = fmaf(l4.x, k[m], a0); a1 = fmaf(l4.y, k[m + 1], a1); a0 = fmaf(l4.z, k[m + 2], a0); a1 = fmaf(l4.w, k[m + 3], a1);
-        }
-        const float a = a0 + a1;
-        part = fmaf(a, a, part);
-      }
-    } else {
-      for (int j = 0; j < MP; ++j) {
-        float a0 = 0.f, a1 = 0.f;
-        for (int m = 0; m < MP; m += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(mat + j * MP + m);
-          float kq[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float t = (xv - s_z[m + e]) * inv_ell;
-            kq[e] = sc * expf(-0.5f * t * t);
-          }
-          a0 = fmaf(l4.x, kq[0], a0); a1 = fmaf(l4.y, kq[1], a1); a0 = fmaf(l4.z, kq[2], a0); a1 = fmaf(l4.w, kq[3], a1);
-        }
-        const float a = a0 + a1;
-        part = fmaf(a, a, part);
-      }
-    }
-  }
+  if (i < S) part = gp_trig_partial<MREG>(xv, sc, 1.0f / ell, MP, half == 0 ? s_linv : s_lqt, s_z, half != 0);
   // combine the two halves through shared memory (smf is dead after the barrier)
   __syncthreads();
   if (half == 1) smf[li] = part;
@@ -343,45 +286,8 @@ __global__ void __launch_bounds__(256) gp_trigger_kernel(int S, int D, int mp, c
   if (!s_last) return;
   __threadfence();
   const int cnt = count[0];
-  for (int s = tid; s < S; s += 256) {
-    float acc = 0.f;
-    for (int d0 = 0; d0 < D; d0 += 32) {
-      float v[32];
-#pragma unroll
-      for (int u = 0; u < 32; ++u) v[u] = d0 + u < D ? __ldcg(var_rows + (size_t)(d0 + u) * S + s) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 32; ++u)
-        if (d0 + u < D) acc = __fadd_rn(acc, __fmul_rn(v[u], v[u]));   // generate_frames.py:230, sequential in d
-    }
-    const float val = sqrtf(acc);
-    float* wdw = window + (size_t)s * W;
-    int fired = 0;
-    if (value) value[s] = val;
-    if (warmup) {
-      if (cnt < W) wdw[cnt] = val;
-      else {
-        for (int q = 0; q + 1 < W; ++q) wdw[q] = wdw[q + 1];
-        wdw[W - 1] = val;
-      }
-      if (thr) thr[s] = nanf("");
-    } else {
-      float loc[MAX_WINDOW];
-      for (int q = 0; q + 1 < W; ++q) loc[q] = wdw[q + 1];   // generate_frames.py:231
-      loc[W - 1] = val;
-      for (int q = 0; q < W; ++q) wdw[q] = loc[q];
-      const float mean = __fdiv_rn(np_pairwise_sum(loc, W), (float)W);
-      for (int q = 0; q < W; ++q) {
-        const float dlt = __fsub_rn(loc[q], mean);
-        loc[q] = __fmul_rn(dlt, dlt);
-      }
-      const float sd = sqrtf(__fdiv_rn(np_pairwise_sum(loc, W), (float)W));
-      const float t = __fadd_rn(mean, __fmul_rn(factor, sd));  // generate_frames.py:288
-      fired = val > t ? 1 : 0;                                  // generate_frames.py:289
-      if (thr) thr[s] = t;
-    }
-    if (mask) mask[s] = (uint8_t)fired;
-    if (fired) trig_list[atomicAdd(trig_count, 1)] = s;
-  }
+  for (int s = tid; s < S; s += 256)
+    gp_trig_finalize_rollout(s, S, D, var_rows, window, W, cnt, warmup, factor, value, thr, mask, trig_list, trig_count);
   if (tid == 0) {
     *ticket = 0;                                   // ready for the next launch
     if (warmup && cnt < W) count[0] = cnt + 1;

@@ -108,6 +108,12 @@ void lstm_tc_free(dvg_lstm_s* h);
 size_t lstm_tc_scratch_bytes_xp(const dvg_lstm_s* h, int rows);
 size_t lstm_tc_scratch_bytes_ep(const dvg_lstm_s* h, int rows);
 
+bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows);
+int lstm_tc_rollout_step(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
+                         const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
+                         float* y, int ldy, int S, const int32_t* stat_rows, float* window, int W, int32_t* count,
+                         int warmup, float factor, float* value, float* thr, uint8_t* mask, cudaStream_t stream);
+
 // gp.cu
 int gp_prepare_launch(dvg_gp_s* h, const float* inducing, const float* var_mean, const float* chol_var,
                       const float* mean_const, const float* raw_os, const float* raw_ls, const float* raw_noise,

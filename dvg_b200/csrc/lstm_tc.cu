@@ -25,6 +25,7 @@
 // Two TMEM accumulator buffers (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <stdlib.h>
 
+#include "gp_trigger.cuh"
 #include "internal.cuh"
 #include "ptx.cuh"
 
@@ -659,11 +660,23 @@ struct FusedPhase {
   const float* eps; float* z; float* mu; float* logvar; int Z;                          // GAUSS
   const float* x; int ldx; int G; uint8_t* xp; int kbx;                                 // PACKX
 };
+// GP variance trigger folded into the step kernel: it only needs the step's input latents, and the epilogue warps
+// of every CTA are idle until the first accumulator is ready (~10 us), so the trigger runs there for free; the
+// LSTM epilogues read its mask (hold flags) after `mask_ready` is published.
+struct TrigArgs {
+  int enabled, S, D, mp, ldx, W, warmup;
+  float factor;
+  const float* x; const int32_t* stat_rows;
+  const float* z; const float* linv; const float* lqt; const float* hyp;
+  float* var_rows; unsigned int* ticket; float* window; int32_t* count;
+  float* value; float* thr; uint8_t* mask; int* trig_list; int* trig_count; int* mask_ready;
+};
 struct FusedArgs {
   int rows, row_tiles, groups, nsplit, stages, n_phases, total_items, H, rows_per_flag;
   uint32_t stage_bytes;
   const uint8_t* hold;
   unsigned long long* trace;
+  TrigArgs trig;
   FusedPhase ph[MAX_PHASES];
 };
 
@@ -881,6 +894,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_
         if (etid == 0) atomicAdd(f.done_flags + (prt >> 1), 1);
       }
     }
+    // ---- GP variance trigger (generate_frames.py:227-232,275,283-289) on the otherwise idle epilogue warps:
+    //      CTA c < D evaluates latent dim c for every rollout (two threads per task, factors staged in the
+    //      transpose-buffer region); the last of those CTAs finalises all rollouts and publishes the mask.
+    if (p.trig.enabled && (int)blockIdx.x < p.trig.D) {
+      const TrigArgs& g = p.trig;
+      const int d = blockIdx.x, MP = g.mp;
+      float* s_linv = reinterpret_cast<float*>(s_ebuf);
+      float* s_lqt = s_linv + MP * MP;
+      float* s_z = s_lqt + MP * MP;
+      int* s_flag = reinterpret_cast<int*>(smem_raw + (bar_base - raw) + 120);
+      {
+        const float4* g1 = reinterpret_cast<const float4*>(g.linv + (size_t)d * MP * MP);
+        const float4* g2 = reinterpret_cast<const float4*>(g.lqt + (size_t)d * MP * MP);
+        for (int e = etid; e < MP * MP / 4; e += 256) {
+          reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
+          reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
+        }
+        for (int e = etid; e < MP; e += 256) s_z[e] = g.z[(size_t)d * MP + e];
+      }
+      ptx::named_bar_sync(1, EPI_WARPS * 32);
+      const float ell = g.hyp[d * 4 + 0], sc = g.hyp[d * 4 + 1], noise = g.hyp[d * 4 + 3];
+      const int hf = etid >> 7, li = etid & 127;
+      for (int base_s = 0; base_s < g.S; base_s += 128) {
+        const int i = base_s + li;
+        float part = 0.f;
+        if (i < g.S) {
+          const float xv = __ldg(g.x + (size_t)g.stat_rows[i] * g.ldx + d);
+          const float* mat = hf == 0 ? s_linv : s_lqt;
+          part = MP == 40 ? gp_trig_partial<40>(xv, sc, 1.0f / ell, MP, mat, s_z, hf != 0)
+                          : gp_trig_partial<0>(xv, sc, 1.0f / ell, MP, mat, s_z, hf != 0);
+        }
+        if (hf == 1) s_bias[li] = part;
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+        if (hf == 0 && i < g.S) g.var_rows[(size_t)d * g.S + i] = (sc - part) + s_bias[li] + noise;
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+      }
+      if (etid == 0) TRACE(26);
+      __threadfence();
+      ptx::named_bar_sync(1, EPI_WARPS * 32);
+      if (etid == 0) *s_flag = atomicAdd(g.ticket, 1u) == (unsigned)g.D - 1u ? 1 : 0;
+      ptx::named_bar_sync(1, EPI_WARPS * 32);
+      if (*s_flag) {
+        __threadfence();
+        if (etid == 0) *g.trig_count = 0;
+        const int cnt = g.count[0];
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+        for (int sidx = etid; sidx < g.S; sidx += 256)
+          gp_trig_finalize_rollout(sidx, g.S, g.D, g.var_rows, g.window, g.W, cnt, g.warmup, g.factor, g.value, g.thr,
+                                   g.mask, g.trig_list, g.trig_count);
+        __threadfence();
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+        if (etid == 0) {
+          *g.ticket = 0;
+          if (g.warmup && cnt < g.W) g.count[0] = cnt + 1;
+          __threadfence();
+          atomicExch(g.mask_ready, 1);
+        }
+      }
+      ptx::named_bar_sync(1, EPI_WARPS * 32);    // the transpose buffers are reused by the tile epilogues
+    }
     int mit = 0;
     for (int item = cid; item < p.total_items; item += ncl) {
       const FusedPhase& f = p.ph[phase_of(item)];
@@ -914,6 +987,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_
         float4 cin[8];
         if (f.type == PH_LSTM) {
           idx0 = (size_t)row * p.H + nt * 64 + half * 32;
+          if (p.trig.enabled && p.hold != nullptr) {
+            while (ld_acquire(p.trig.mask_ready) == 0) {
+            }
+            if (etid == 0 && tm == 0) TRACE(27);
+          }
           held = valid && p.hold != nullptr && p.hold[row / p.rows_per_flag] != 0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -942,7 +1020,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_
             const int cb = half * 32 + jj * 16;
             uint32_t r[64];
             ptx::tmem_ld16x4_wait(tacc + cb, tacc + 64 + cb, tacc + 128 + cb, tacc + 192 + cb, r);
-            if (etid == 0 && tm == 0 && jj == 0) TRACE(26);
             float cp[16], cn[16], hc[16];
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
@@ -960,12 +1037,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_
             for (int c4 = 0; c4 < 4; ++c4)   // c' replaces c in place (same thread, same addresses)
               *reinterpret_cast<float4*>(eb + lane * 128 + (((jj * 4 + c4) ^ (lane & 7)) << 4)) =
                   make_float4(cn[c4 * 4], cn[c4 * 4 + 1], cn[c4 * 4 + 2], cn[c4 * 4 + 3]);
-            if (etid == 0 && tm == 0 && jj == 0) TRACE(27);
             if (valid) store_split16(img, r_in_tile, (uint32_t)(cb >> 3), hc);
 #pragma unroll
             for (int i = 0; i < 16; ++i) hn[jj * 16 + i] = hc[i];
           }
           if (etid == 0 && tm == 0) TRACE(28);
+          // The accumulator is drained and this CTA's slice of the packed h' image is written: release the TMEM
+          // buffer and publish the dependency NOW -- consumers (next layer / head) only read the packed images,
+          // so the fp32 state stores below are off the critical path.
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+            else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
+          }
+          if (f.done_flags != nullptr) {
+            __threadfence();
+            ptx::named_bar_sync(1, EPI_WARPS * 32);
+            if (etid == 0) atomicAdd(f.done_flags + rg, 1);
+          }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {      // c' tile -> global, 128-byte lines
@@ -1047,11 +1137,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_
             }
           }
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
-          else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
+        if (f.type != PH_LSTM) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+            else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
+          }
         }
         if (etid == 0 && tm < 3) {
           TRACE(2 + tm * 8 + 5);
@@ -1061,7 +1153,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_
         }
       }
       // publish: everything this CTA wrote for the item is visible before the counter moves
-      if (f.done_flags != nullptr && f.type != PH_PACKX) {
+      if (f.done_flags != nullptr && f.type != PH_PACKX && f.type != PH_LSTM) {
         __threadfence();
         ptx::named_bar_sync(1, EPI_WARPS * 32);
         if (etid == 0) atomicAdd(f.done_flags + rg, 1);
@@ -1400,7 +1492,8 @@ static bool use_fused() {
 static int lstm_tc_step_fused(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in,
                               const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
                               float* y, int ldy, const float* eps, float* z, float* mu, float* logvar,
-                              const uint8_t* hold, int rows_per_flag, cudaStream_t stream) {
+                              const uint8_t* hold, int rows_per_flag, cudaStream_t stream,
+                              const TrigArgs* trig = nullptr) {
   const int G = h->dims.input_size, H = h->dims.hidden_size, L = h->dims.n_layers;
   const int hk = H / 64, RT = ceil_div(rows, TC_ROWS), kbx = ceil_div(G, 64);
   const int groups = ceil_div(RT, 2);
@@ -1410,7 +1503,13 @@ static int lstm_tc_step_fused(dvg_lstm_s* h, int nsplit, int rows, const float* 
   a.rows = rows; a.row_tiles = RT; a.groups = groups; a.nsplit = nsplit; a.H = H;
   a.hold = hold; a.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
   int* flags = h->fused_flags;
-  DVG_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)(L + 1) * h->fused_flag_stride, stream));
+  // one memset node per step: the dependency counters plus (last word) the trigger's mask_ready flag
+  DVG_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)(L + 1) * h->fused_flag_stride + 1), stream));
+  if (trig != nullptr) {
+    a.trig = *trig;
+    a.trig.enabled = 1;
+    a.trig.mask_ready = flags + (size_t)(L + 1) * h->fused_flag_stride;
+  }
   int np = 0, item = 0;
   {  // PACKX
     FusedPhase& f = a.ph[np];
@@ -1504,6 +1603,30 @@ static int lstm_tc_step_fused(dvg_lstm_s* h, int nsplit, int rows, const float* 
   }
 #endif
   return DVG_OK;
+}
+
+bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows) {
+  const int RT = ceil_div(rows, TC_ROWS);
+  const size_t need = sizeof(float) * ((size_t)2 * g->mp * g->mp + g->mp);
+  int pairs = h->sm_count / 2;
+  return h->tc_ok && use_fused() && use_pairs() && RT >= 2 && need <= (size_t)EPI_WARPS * 4096 &&
+         g->dims.num_dims <= pairs * 2;
+}
+
+// trigger + LSTM step in one launch (see TrigArgs); caller guarantees lstm_tc_can_fuse_trigger().
+int lstm_tc_rollout_step(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
+                         const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
+                         float* y, int ldy, int S, const int32_t* stat_rows, float* window, int W, int32_t* count,
+                         int warmup, float factor, float* value, float* thr, uint8_t* mask, cudaStream_t stream) {
+  TrigArgs t{};
+  t.S = S; t.D = g->dims.num_dims; t.mp = g->mp; t.ldx = ldx; t.W = W; t.warmup = warmup; t.factor = factor;
+  t.x = x; t.stat_rows = stat_rows; t.z = g->z; t.linv = g->linv; t.lqt = g->lqt; t.hyp = g->hyp;
+  t.var_rows = g->var_rows; t.ticket = g->ticket; t.window = window; t.count = count;
+  t.value = value; t.thr = thr; t.mask = mask; t.trig_list = g->trig_list; t.trig_count = g->trig_count;
+  g->last_mask = mask;
+  g->last_mask_rollouts = S;
+  return lstm_tc_step_fused(h, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, nullptr, nullptr,
+                            nullptr, nullptr, warmup ? nullptr : mask, rows / S, stream, &t);
 }
 
 int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in,

@@ -135,8 +135,16 @@ class RolloutEngine:
     def step_trigger_mode(self, h, eps, out, warmup: bool):
         """One GPtrigger_gen step (generate_frames.py:266-298) for all rollouts: ``out`` [S*B, G] receives
         the decoder input (LSTM prediction, or the GP sample for triggered rollouts)."""
-        self.trigger(h, warmup)
-        self.advance(h, out, hold=not warmup)
+        rows = self.stat_rows_warmup if warmup else self.stat_rows
+        nxt = 1 - self.cur
+        _capi.check(self.lib.dvg_rollout_step(self.lrt.handle, self.grt.handle, self.variant, self.R, _capi.ptr(h),
+                                              self._ld(h), _capi.ptr(self.blocks[self.cur]),
+                                              _capi.ptr(self.blocks[nxt]), _capi.ptr(out), self._ld(out), self.S,
+                                              _capi.ptr(rows), _capi.ptr(self.window), self.cfg.window,
+                                              _capi.ptr(self.count), 1 if warmup else 0, TRIGGER_FACTOR,
+                                              _capi.ptr(self.value), _capi.ptr(self.thr), _capi.ptr(self.mask),
+                                              _capi.stream_ptr()), "dvg_rollout_step")
+        self.cur = nxt
         if not warmup:
             self.resample(h, eps, out, masked=True)
 

@@ -201,6 +201,16 @@ DVG_API int dvg_gp_export(dvg_gp_t h, float* linv, float* lqt, float* alpha, flo
 /* ------------------------------------------------------------------------------------------------
  * N-diverse-futures bookkeeping
  * ---------------------------------------------------------------------------------------------- */
+/* One GPtrigger_gen time step (generate_frames.py:266-298) for S = n_rollouts rollouts of rows/S points each:
+ * dvg_gp_trigger(x) followed by dvg_lstm_step(x, hold = warmup ? none : mask) -- same arguments, same results --
+ * issued as ONE persistent kernel when the tensor-core variants apply (the trigger runs on the step kernel's
+ * epilogue warps while the first gate GEMM tiles are in flight; the hold mask never leaves the device).
+ * Follow with dvg_gp_rsample(mask) to substitute the GP sample for the rollouts that fired. */
+DVG_API int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows,
+                     const float* x, int ldx, const void* state_in, void* state_out, float* y, int ldy,
+                     int n_rollouts, const int32_t* stat_rows, float* window, int window_len, int32_t* count,
+                     int warmup, float factor, float* value, float* thr, uint8_t* mask, dvg_stream_t stream);
+
 /* Device-side scoring pass of the best-of-N selection (the reference scores every sample on the host after a
  * D2H copy per frame, generate_frames.py:175-178,185-190): scores[s, b] = mean over (t, g) of
  * (latents[t, s*B + b, g] - target[t, b, g])^2.  latents [T, S*B, dim] dense, target [T, B, dim], scores [S, B]. */
