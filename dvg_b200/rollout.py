@@ -189,6 +189,80 @@ class RolloutEngine:
         return g
 
 
+class LatentRolloutPipeline:
+    """Host-facing streaming driver for ``RolloutEngine``: ``submit(lat_host, eps_host)`` enqueues one complete
+    latent rollout whose inputs live in pinned HOST memory and returns a ticket; ``result(ticket)`` yields the
+    pinned host output (and the trigger masks).  Three CUDA streams and two buffer sets overlap the H2D copy of
+    rollout k+1 and the D2H copy of rollout k-1 with the compute graph of rollout k (the per-step D2H + host numpy
+    of the reference, generate_frames.py:175-176,230, is what this replaces)."""
+
+    def __init__(self, engine: "RolloutEngine", T: int):
+        self.eng = engine
+        dev, R, G, S, D, B = engine.dev, engine.R, engine.G, engine.S, engine.D, engine.B
+        self.T = T
+        self.lat = torch.empty(T, R, G, device=dev)
+        self.eps = torch.empty(T, S, D, B, device=dev)
+        self.out = torch.empty(T, R, G, device=dev)
+        self.masks = torch.zeros(T, S, dtype=torch.uint8, device=dev)
+        self.graph = engine.capture_latent_rollout(self.lat, self.eps, self.out, masks=self.masks)
+        self.stage_in = [(torch.empty_like(self.lat), torch.empty_like(self.eps)) for _ in range(2)]
+        self.stage_out = [(torch.empty_like(self.out), torch.empty_like(self.masks)) for _ in range(2)]
+        self.host_out = [(torch.empty(T, R, G).pin_memory(), torch.empty(T, S, dtype=torch.uint8).pin_memory())
+                         for _ in range(2)]
+        self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.ev_free_in = [torch.cuda.Event() for _ in range(2)]
+        self.n = 0
+        for e in self.ev_out + self.ev_free_in:
+            e.record()
+
+    def submit(self, lat_host: torch.Tensor, eps_host: Optional[torch.Tensor] = None, post=None):
+        """Enqueue one rollout.  ``eps_host`` None: the rsample noise is drawn on the device (torch.randn on the
+        compute stream, like gpytorch's rsample does in the reference) instead of being shipped from the host.
+        ``post(out_dev)`` (optional) runs on the compute stream after the graph (e.g. the best-of-N scoring) and
+        its result is returned by ``result``."""
+        k = self.n & 1
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_free_in[k])           # staging buffer consumed by an earlier rollout
+            self.stage_in[k][0].copy_(lat_host, non_blocking=True)
+            if eps_host is not None:
+                self.stage_in[k][1].copy_(eps_host, non_blocking=True)
+            self.ev_in[k].record()
+        with torch.cuda.stream(self.s_cmp):
+            self.s_cmp.wait_event(self.ev_in[k])
+            self.lat.copy_(self.stage_in[k][0], non_blocking=True)
+            if eps_host is not None:
+                self.eps.copy_(self.stage_in[k][1], non_blocking=True)
+            else:
+                self.eps.normal_()
+            self.ev_free_in[k].record()
+            self.graph.replay()
+            extra = post(self.out) if post is not None else None
+            self.s_cmp.wait_event(self.ev_out[k])              # host_out/stage_out[k] drained by the D2H stream
+            self.stage_out[k][0].copy_(self.out, non_blocking=True)
+            self.stage_out[k][1].copy_(self.masks, non_blocking=True)
+            self.ev_cmp[k].record()
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_cmp[k])
+            self.host_out[k][0].copy_(self.stage_out[k][0], non_blocking=True)
+            self.host_out[k][1].copy_(self.stage_out[k][1], non_blocking=True)
+            self.ev_out[k].record()
+        self.n += 1
+        return (self.n - 1, extra)
+
+    def result(self, ticket):
+        idx, extra = ticket
+        k = idx & 1
+        self.ev_out[k].synchronize()
+        return self.host_out[k][0], self.host_out[k][1], extra
+
+    def drain(self):
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.synchronize()
+
+
 def score_rollouts(out: torch.Tensor, target: torch.Tensor, n_rollouts: int, n_points: int) -> torch.Tensor:
     """Latent-space best-of-N scoring on the device (one pass, ``dvg_rollout_score``): ``out`` [T, S*B, G],
     ``target`` [T, B, G] -> mean-squared-error scores [S, B] (lower is better)."""
