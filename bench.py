@@ -41,6 +41,11 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+# capture (profiles/r01_lstm_fused.md); keyed by (workload, variant).
+NCU_TRAFFIC_BYTES = {("kth_s100", "bf16x3"): 27.9e6}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -62,7 +67,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -295,6 +300,20 @@ def measure_roofline(eng, w, R, lat, args):
                 acc[i] += ms[i]
             reps += 1
     per = [a / reps for a in acc]
+    other = {}
+    for name, vid in (("bf16", _capi.DVG_BF16), ("fp32", _capi.DVG_FP32)):
+        if vid == eng.variant:
+            continue
+        tot, n = 0.0, 0
+        for t in range(min(T, 6)):
+            nxt = 1 - eng.cur
+            _capi.check(lib.dvg_lstm_profile(eng.lrt.handle, vid, R, _capi.ptr(lat[t]), w["G"],
+                                             _capi.ptr(eng.blocks[eng.cur]), _capi.ptr(eng.blocks[nxt]), _capi.ptr(out),
+                                             w["G"], ms, 16, _capi.stream_ptr()), "dvg_lstm_profile")
+            eng.cur = nxt
+            if t >= 2:
+                tot += sum(ms[i] for i in range(n_slots)); n += 1
+        other[name] = tot / max(n, 1)
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     issued = 3 if args.variant == "bf16x3" else 1
     f_row, b_row, f_layer = flops_bytes(w, R)
@@ -316,12 +335,15 @@ def measure_roofline(eng, w, R, lat, args):
     return {"bound": "tensor", "kernel": kernel,
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % how,
-            "traffic": None,
+            "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant)),
+            "traffic_source": "profiles/r01_lstm_fused.md (ncu --set full, dram read+write bytes per launch)",
+            "algorithmic_bytes_per_launch": b_row * R,
             "tensor_issue_frac": achieved * issued / peak,
             "hbm_frac_of_state_io": (b_row * R / (step_ms * 1e-3) / 1e9) / hbm,
             "note": "achieved counts " + flops_note + "; the bf16x3 variant issues 3 tcgen05.mma per algorithmic "
                     "MMA (tensor_issue_frac = tensor-pipe work actually issued / peak)",
-            "kernel_ms": kernel_ms, "lstm_step_ms": step_ms}
+            "kernel_ms": kernel_ms, "lstm_step_ms": step_ms,
+            "other_variants_lstm_step_ms": other}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -399,7 +421,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])

@@ -125,7 +125,8 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
     if (h->fused_flags) cudaFree(h->fused_flags);
     h->fused_flags = nullptr;
     h->fused_flag_stride = (int)align_up((size_t)ceil_div(ceil_div(rows, 128), 2), 32);
-    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * ((size_t)(h->dims.n_layers + 1) * h->fused_flag_stride + 1)));
+    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * ((size_t)(h->dims.n_layers + 1) * h->fused_flag_stride + 2)));
+    DVG_CUDA(cudaMemset(h->fused_flags, 0, sizeof(int) * ((size_t)(h->dims.n_layers + 1) * h->fused_flag_stride + 2)));
   }
   h->reserved_rows = rows;
   return DVG_OK;

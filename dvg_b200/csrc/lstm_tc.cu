@@ -676,6 +676,7 @@ struct FusedArgs {
   uint32_t stage_bytes;
   const uint8_t* hold;
   unsigned long long* trace;
+  int* flag_words; int n_flag_words;   // all dependency counters (+ mask_ready); last word = exit counter
   TrigArgs trig;
   FusedPhase ph[MAX_PHASES];
 };
@@ -1169,6 +1170,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_
     ptx::tc_fence_after();
     ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
   }
+  // Self-resetting dependency counters: the last CTA to get here (every CTA has finished reading them) zeroes
+  // them for the next launch -- no cudaMemset node per step.
+  if (threadIdx.x == 0) {
+    int* exit_ctr = p.flag_words + p.n_flag_words;
+    __threadfence();
+    if (atomicAdd(exit_ctr, 1) == (int)gridDim.x - 1) {
+      for (int i = 0; i < p.n_flag_words; ++i) p.flag_words[i] = 0;
+      __threadfence();
+      *exit_ctr = 0;
+    }
+  }
 }
 
 // W_x = W_ih0 W_e  ([4H, G]),  b_x = W_ih0 b_e + b_ih0 + b_hh0  -- the embed Linear folded into layer 0 (fp64 accumulate).
@@ -1503,8 +1515,10 @@ static int lstm_tc_step_fused(dvg_lstm_s* h, int nsplit, int rows, const float* 
   a.rows = rows; a.row_tiles = RT; a.groups = groups; a.nsplit = nsplit; a.H = H;
   a.hold = hold; a.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
   int* flags = h->fused_flags;
-  // one memset node per step: the dependency counters plus (last word) the trigger's mask_ready flag
-  DVG_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)(L + 1) * h->fused_flag_stride + 1), stream));
+  // dependency counters + (last word) the trigger's mask_ready flag + exit counter: zeroed at allocation and reset
+  // by the kernel itself at exit
+  a.flag_words = flags;
+  a.n_flag_words = (L + 1) * h->fused_flag_stride + 1;
   if (trig != nullptr) {
     a.trig = *trig;
     a.trig.enabled = 1;
