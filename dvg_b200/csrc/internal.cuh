@@ -127,6 +127,8 @@ int gp_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const 
                       float* out, int ldo, cudaStream_t stream);
 
 // rollout.cu
+int eval_seq_finn_launch(int T, int S, int B, int C, int H, int W, const float* gt, const float* gen, float* ssim,
+                         float* psnr, cudaStream_t stream);
 int rollout_score_launch(int T, int S, int B, int G, const float* out, const float* target, float* scores,
                          cudaStream_t stream);
 

@@ -275,6 +275,19 @@ def score_rollouts(out: torch.Tensor, target: torch.Tensor, n_rollouts: int, n_p
     return scores
 
 
+def eval_seq_finn(gt: torch.Tensor, gen: torch.Tensor):
+    """``utils.finn_eval_seq`` for all S samples at once, on the device: ``gt`` [T, B, C, H, W], ``gen``
+    [T, S, B, C, H, W] -> (ssim, psnr) each [S, B, T].  Best-of-N as in generate_frames.py:188-189,207:
+    ``shard.select_best(ssim.mean(2), higher_is_better=True)``."""
+    T, S, B, C, H, W = gen.shape
+    assert gt.shape == (T, B, C, H, W) and gt.is_cuda and gen.is_cuda
+    gt, gen = gt.contiguous().float(), gen.contiguous().float()
+    out = torch.empty(2, S, B, T, device=gen.device, dtype=torch.float32)
+    _capi.check(_capi.load().dvg_eval_seq_finn(T, S, B, C, H, W, _capi.ptr(gt), _capi.ptr(gen), _capi.ptr(out[0]),
+                                               _capi.ptr(out[1]), _capi.stream_ptr()), "dvg_eval_seq_finn")
+    return out[0], out[1]
+
+
 # -------------------------------------------------------------------------------------------------------
 # Pixel-space drivers (encoder / decoder are the reference conv nets on the stock PyTorch path)
 # -------------------------------------------------------------------------------------------------------

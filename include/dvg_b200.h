@@ -211,6 +211,13 @@ DVG_API int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows,
                      int n_rollouts, const int32_t* stat_rows, float* window, int window_len, int32_t* count,
                      int warmup, float factor, float* value, float* thr, uint8_t* mask, dvg_stream_t stream);
 
+/* finn_eval_seq on the device (utils.py:237-301): channel-mean SSIM (11x11 Gaussian window,
+ * sigma 1.5, K1=.01, K2=.03, L=1, NaN -> -1) and PSNR = 10 log10(1/mse) of every generated frame against the
+ * ground truth, without the per-frame D2H copy of generate_frames.py:175-176.
+ *   gt [T, B, C, H, W], gen [T, S, B, C, H, W] dense fp32  ->  ssim, psnr [S, B, T]. */
+DVG_API int dvg_eval_seq_finn(int n_frames, int n_samples, int n_seq, int channels, int height, int width,
+                      const float* gt, const float* gen, float* ssim, float* psnr, dvg_stream_t stream);
+
 /* Device-side scoring pass of the best-of-N selection (the reference scores every sample on the host after a
  * D2H copy per frame, generate_frames.py:175-178,185-190): scores[s, b] = mean over (t, g) of
  * (latents[t, s*B + b, g] - target[t, b, g])^2.  latents [T, S*B, dim] dense, target [T, B, dim], scores [S, B]. */
