@@ -408,3 +408,27 @@ def trigger_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x0,
         gen_seq.append(xs.view(S, B, *xs.shape[1:]))
         latents.append(out.clone().view(S, B, D))
     return {"gen_seq": gen_seq, "values": values, "triggers": trig, "latents": latents}
+
+
+@torch.no_grad()
+def make_gifs(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample,
+              eps: Optional[Dict] = None, resample_every: Optional[int] = 15, last_frame_skip=False,
+              variant="bf16x3"):
+    """The computational part of ``make_gifs`` (generate_frames.py:107-217) with everything on the device:
+    pass A (approximate posterior, GP mean), pass B (``nsample`` diverse futures, batched), SSIM / PSNR of every
+    generated frame against the ground truth and the best-of-N choice per sequence (the gif writing is out of scope).
+
+    Returns dict(posterior [n_eval][B,...], samples [n_eval][S,B,...], ssim [B,S,T_f], psnr [B,S,T_f], best [B]).
+    Metrics are the reference's self-contained ``finn_eval_seq`` variant (utils.py:237-301); the skimage-based
+    ``eval_seq`` the script calls is not reproducible here (skimage absent)."""
+    from . import shard
+    posterior = posterior_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval,
+                                  last_frame_skip)
+    samples = diverse_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample,
+                              eps=eps, resample_every=resample_every, last_frame_skip=last_frame_skip, variant=variant)
+    gt = torch.stack([x[t] for t in range(n_past, n_eval)])                    # [T_f, B, C, H, W]
+    gen = torch.stack([samples[t] for t in range(n_past, n_eval)])             # [T_f, S, B, C, H, W]
+    ssim, psnr = eval_seq_finn(gt, gen)                                        # [S, B, T_f]
+    best = shard.select_best(ssim.mean(2), higher_is_better=True)              # generate_frames.py:188-189,207
+    return {"posterior": posterior, "samples": samples, "ssim": ssim.permute(1, 0, 2), "psnr": psnr.permute(1, 0, 2),
+            "best": best}

@@ -157,3 +157,48 @@ def test_score_rollouts_matches_torch():
     got = score_rollouts(out, target, S, B)
     want = (out.view(T, S, B, G) - target.view(T, 1, B, G)).double().pow(2).mean(dim=(0, 3))
     assert relerr(got, want) < 1e-5
+
+
+def test_make_gifs_pixel_space_with_reference_convnets():
+    """Whole make_gifs computation in pixel space with the dcgan_64 encoder/decoder (stock PyTorch path, eval mode)
+    against the sequential CPU oracle using the same nets, weights and injected noise; then SSIM-based best-of-N."""
+    import numpy as np
+    from dvg_b200.convnets import make_codec
+    from dvg_b200.rollout import make_gifs
+    from oracle import metrics_ref
+    torch.manual_seed(0)
+    g_dim, B, S, n_past, n_eval = 90, 3, 3, 2, 7
+    enc, dec = make_codec("dcgan_64", g_dim, 1)
+    for m in (enc, dec):
+        for mod in m.modules():
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                mod.weight.data.normal_(0.0, 0.02); mod.bias.data.zero_()
+            elif isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.data.normal_(1.0, 0.02); mod.bias.data.zero_()
+                mod.running_mean.normal_(0, 0.05); mod.running_var.uniform_(0.5, 1.5)
+        m.eval()
+    sd = lstm_ref.random_lstm_state_dict(g_dim, g_dim, H, L, seed=12)
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(g_dim, M, seed=12, trained_like=True, smooth_mean=True)
+    g = torch.Generator().manual_seed(5)
+    x = [torch.rand(B, 1, 64, 64, generator=g) for _ in range(n_eval)]
+    eps = {(s, i): torch.randn(g_dim, B, generator=g) for s in range(S) for i in range(n_eval)}
+    with torch.no_grad():
+        om = rollout_ref.OracleModels(sd, gp_sd, lik_sd, enc, dec, gp_mode="direct")
+        ref = rollout_ref.diverse_rollout(om, x, n_past, n_eval, S, eps, resample_every=3)
+        ref_post = rollout_ref.posterior_rollout(om, x, n_past, n_eval)
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    enc_g, dec_g = enc.cuda(), dec.cuda()
+    out = make_gifs(fp, gp, lik, enc_g, dec_g, [t.cuda() for t in x], n_past, n_eval, S, eps=eps, resample_every=3)
+    for t in range(n_eval):
+        assert relerr(out["posterior"][t], ref_post[t]) < 2e-3, t
+        for s in range(S):
+            assert relerr(out["samples"][t][s], ref[s][t]) < 2e-3, (t, s)
+    # metrics + selection against the oracle metrics evaluated on the oracle frames
+    want = np.zeros((B, S, n_eval - n_past))
+    for s in range(S):
+        a, _ = metrics_ref.finn_eval_seq([x[t].numpy() for t in range(n_past, n_eval)],
+                                         [ref[s][t].numpy() for t in range(n_past, n_eval)])
+        want[:, s] = a
+    assert np.abs(out["ssim"].cpu().numpy() - want).max() < 2e-3
+    enc.cpu(); dec.cpu()
