@@ -119,14 +119,18 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
   h->reserved_rows = 0;
   DVG_CUDA(cudaMalloc(&h->scratch_e, sizeof(float) * (size_t)rows * h->dims.hidden_size));
   if (h->tc_ok) {
-    DVG_CUDA(cudaMalloc(&h->tc_xp, lstm_tc_scratch_bytes_xp(h, rows)));
+    const size_t xpb = lstm_step_xp_bytes(h, rows) > lstm_tc_scratch_bytes_xp(h, rows) ? lstm_step_xp_bytes(h, rows)
+                                                                                        : lstm_tc_scratch_bytes_xp(h, rows);
+    DVG_CUDA(cudaMalloc(&h->tc_xp, xpb));
+    DVG_CUDA(cudaMemset(h->tc_xp, 0, xpb));
     DVG_CUDA(cudaMalloc(&h->tc_ep, lstm_tc_scratch_bytes_ep(h, rows)));
     DVG_CUDA(cudaMemset(h->tc_ep, 0, lstm_tc_scratch_bytes_ep(h, rows)));
     if (h->fused_flags) cudaFree(h->fused_flags);
     h->fused_flags = nullptr;
-    h->fused_flag_stride = (int)align_up((size_t)ceil_div(ceil_div(rows, 128), 2), 32);
-    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * ((size_t)(h->dims.n_layers + 1) * h->fused_flag_stride + 2)));
-    DVG_CUDA(cudaMemset(h->fused_flags, 0, sizeof(int) * ((size_t)(h->dims.n_layers + 1) * h->fused_flag_stride + 2)));
+    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * lstm_step_flag_words(h, rows)));
+    DVG_CUDA(cudaMemset(h->fused_flags, 0, sizeof(int) * lstm_step_flag_words(h, rows)));
+    int rc = lstm_step_build_schedule(h, rows);
+    if (rc) return rc;
   }
   h->reserved_rows = rows;
   return DVG_OK;

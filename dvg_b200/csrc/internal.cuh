@@ -43,8 +43,9 @@ struct dvg_lstm_s {
   dvg::TcGemmPlan tc_layer0f;    // layer 0 with the embed Linear folded in (fused step kernel)
   float* fold_wx = nullptr;      // [4H][G]  W_ih0 W_e
   float* fold_bx = nullptr;      // [4H]     W_ih0 b_e + b_ih0 + b_hh0
-  int* fused_flags = nullptr;    // [(L+1)][fused_flag_stride] per-row-group dependency counters
-  int fused_flag_stride = 0;
+  int* fused_flags = nullptr;    // dependency counters of the persistent step kernel (lstm_step.cu), self-resetting
+  int* sched_dev = nullptr;      // optional item order of the step kernel for (sched_rows, sched_pairs)
+  int sched_len = 0, sched_rows = 0, sched_pairs = 0;
 
   // --- scratch, grown by reserve() ----------------------------------------------------------------
   int reserved_rows = 0;
@@ -108,6 +109,21 @@ void lstm_tc_free(dvg_lstm_s* h);
 size_t lstm_tc_scratch_bytes_xp(const dvg_lstm_s* h, int rows);
 size_t lstm_tc_scratch_bytes_ep(const dvg_lstm_s* h, int rows);
 
+// lstm_step.cu: the persistent whole-step kernel
+struct StepTrigHost {
+  int S, W, warmup;
+  float factor;
+  const int32_t* stat_rows;
+  float* window; int32_t* count; float* value; float* thr; uint8_t* mask;
+};
+bool lstm_step_usable(const dvg_lstm_s* h, int rows);
+size_t lstm_step_flag_words(const dvg_lstm_s* h, int rows);
+size_t lstm_step_xp_bytes(const dvg_lstm_s* h, int rows);
+int lstm_step_build_schedule(dvg_lstm_s* h, int rows);
+int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
+                     const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out, float* y,
+                     int ldy, const float* eps, float* z, float* mu, float* logvar, const uint8_t* hold,
+                     int rows_per_flag, cudaStream_t stream, const StepTrigHost* trig);
 bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows);
 int lstm_tc_rollout_step(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
                          const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,

@@ -1,0 +1,947 @@
+// One LSTM time step (models/lstm.py:65-72, gaussian_lstm :166-175) in ONE persistent launch, tensor-core variants.
+//
+// Grid: one CTA per SM, clusters of 2 (cta_group::2 pairs).  A pair owns work items of 256 rows x n_tile columns:
+//   LSTM_l(rg, nt)  layer l, row group rg (256 rows), N tile nt = [i|f|g|o] x 64 hidden units.
+//                   K order: recurrent k-blocks (packed h_l of the previous step) first -- they depend on nothing
+//                   produced in this launch -- then the input k-blocks (layer 0: x with the embed Linear folded in;
+//                   layer l > 0: the packed h'_{l-1} written by this launch).
+//   HEAD(rg)        tanh(h'_{L-1} W_o^T + b_o)  or  mu / logvar / z.
+// Dependencies are per (layer, rg, nt) counters in global memory: the epilogue of LSTM_l(rg, nt) publishes one packed
+// k-block image of h'_l, and a consumer waits for exactly the k-block it is about to load (target 2 = both CTAs of the
+// producing pair).  Items are processed in a global order in which every dependency precedes its consumer and all pairs
+// are co-resident, so the schedule cannot deadlock.
+//
+// Warp roles (352 threads):
+//   warp 0      TMA producer (one lane): dependency polls, cp.async.bulk of the k-block stages
+//   warp 1      leader CTA: tcgen05.mma issuer;  peer CTA: relays "my stage landed" to the leader
+//   warps 2-9   x-pack prologue, GP trigger partial sums (CTAs < D), tile epilogues
+//   warp 10     auxiliary: in the last CTA it finalises the GP trigger (window / threshold / decision) once the D
+//               trigger CTAs have delivered their variances
+//
+// What changed against the first fused kernel (profiles/r01_lstm_fused.md, ncu + timestamp traces):
+//   * the x operand is packed by the consuming pair itself into a private scratch slab (no all-CTA pre-pass, no
+//     cross-CTA flag on the way to the first MMA);
+//   * k-block granular dependencies instead of "all N tiles of the row group";
+//   * the LSTM epilogue is a compact loop over 8 hidden units (the fully unrolled version was 36 KB of straight-line
+//     code and ~70 % of its issue slots were instruction-fetch stalls); results are parked in already consumed TMEM
+//     columns (tcgen05.st) so no register array needs dynamic indexing;
+//   * nobody waits for the trigger mask: the LSTM always advances and, in the rare step where rollouts fired, their
+//     state rows are restored from the input block at the end of the launch (generate_frames.py:289-295: a triggered
+//     rollout does not advance its LSTM);
+//   * the trigger is finalised by a dedicated warp instead of stalling one CTA's epilogue warps.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "gp_trigger.cuh"
+#include "tc_common.cuh"
+
+namespace dvg {
+
+enum { PH_LSTM = 1, PH_TANH = 2, PH_GAUSS = 3 };
+constexpr int STEP_MAX_PHASES = MAX_LAYERS + 1;
+constexpr int STEP_THREADS = 64 + EPI_WARPS * 32 + 32;
+constexpr int AUX_WARP = 2 + EPI_WARPS;
+constexpr int STEP_MAX_STAGES = 6;
+constexpr int STEP_XMAX = 8;            // layer-0 items per pair (one x-ready mbarrier each)
+constexpr int STEP_BAR_BYTES = 384;     // mbarriers + tmem slot + misc words
+
+struct StepPhase {
+  int type, n_tile, n_tiles, kb_in, kb_rec, item_begin, in_ksteps;
+  const uint8_t* a_in;    // layer 0: packed-x scratch [n_tiles][RT][kb_in]; else h' images of the layer below [RT][kb_in]
+  const uint8_t* a_rec;   // packed h of the previous step [RT][kb_rec]
+  const uint8_t* w; const float* bias;
+  const int* wait_flags;  // [groups][kb_in] counters of the producing phase (nullptr: layer 0, local x-ready barrier)
+  int* done_flags;        // [groups][n_tiles]
+  const float* c_in; const float* h_in; float* h_out; float* c_out; uint8_t* hp_out;   // LSTM
+  float* y; int ldy; int n_valid;                                                       // TANH
+  const float* eps; float* z; float* mu; float* logvar; int Z;                          // GAUSS
+};
+struct StepTrig {
+  int enabled, S, D, mp, W, warmup;
+  float factor;
+  const int32_t* stat_rows;
+  const float* z; const float* linv; const float* lqt; const float* hyp;
+  float* var_rows; unsigned int* ticket; float* window; int32_t* count;
+  float* value; float* thr; uint8_t* mask; int* trig_list; int* trig_count;
+};
+struct StepArgs {
+  int rows, row_tiles, groups, nsplit, stages, n_phases, total_items, H, L, G, ldx, kbx, rows_per_flag, restore;
+  uint32_t stage_bytes;
+  const float* x; uint8_t* xp;
+  const uint8_t* hold;            // mask known BEFORE the launch (plain dvg_lstm_step); nullptr in trigger-fused steps
+  const int* sched; int sched_len;   // optional host-built item order: pair p runs sched[p], sched[p + pairs], ...
+  int* flag_words; int n_flag_words;     // dependency counters, then [mask_ready][done_ctr]; exit counter follows
+  int* mask_ready; int* done_ctr;
+  unsigned long long* trace;
+  StepTrig trig;
+  StepPhase ph[STEP_MAX_PHASES];
+};
+
+// Spin with relaxed loads (an acquire load drags a CCTL.IVALL -- an L1 invalidate -- through the SM on every
+// iteration); one acquire load after the condition holds orders the subsequent reads.
+__device__ __forceinline__ void poll_ge(const int* flag, int target, int item) {
+  if (ptx::ld_relaxed_gpu(flag) < target) {
+    const long long t0 = clock64();
+    while (ptx::ld_relaxed_gpu(flag) < target) {
+      if (clock64() - t0 > 4000000000LL) {
+        printf("dvg_b200: dependency wait timed out (block %d item %d)\n", (int)blockIdx.x, item);
+        __trap();
+      }
+    }
+  }
+  (void)ptx::ld_acquire_gpu(flag);
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid_constant__ StepArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = ptx::smem_u32(smem_raw);
+  if ((base & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("dvg_b200: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int CM = 2;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t stage_bytes = p.stage_bytes;
+  const uint32_t nparts = p.nsplit == 1 ? 1u : 2u;
+  const uint32_t a_bytes = nparts * (uint32_t)TC_A_IMG;
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STEP_MAX_STAGES + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * STEP_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STEP_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STEP_MAX_STAGES + 2 + a); };
+  auto xready_bar = [&](int j) { return bar_base + 8u * (3 * STEP_MAX_STAGES + 4 + j); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STEP_MAX_STAGES + 4 + STEP_XMAX);
+  uint8_t* tail = smem_raw + (size_t)p.stages * stage_bytes;
+  int* s_misc = reinterpret_cast<int*>(tail + 8 * (3 * STEP_MAX_STAGES + 4 + STEP_XMAX) + 16);
+  float* s_bias = reinterpret_cast<float*>(tail + STEP_BAR_BYTES);                // [2][256] floats
+  uint8_t* s_ebuf = tail + STEP_BAR_BYTES + 2 * 256 * sizeof(float);             // [EPI_WARPS][4 KB]
+
+  const int cid = (int)ptx::cluster_id_x();
+  const int ncl = (int)ptx::cluster_count_x();
+  // k-th item of this pair (-1: none)
+  auto item_at = [&](int k) -> int {
+    const int pos = cid + k * ncl;
+    if (p.sched != nullptr) return pos < p.sched_len ? __ldg(p.sched + pos) : -1;
+    return pos < p.total_items ? pos : -1;
+  };
+  auto phase_of = [&](int item) {
+    int k = 0;
+    while (k + 1 < p.n_phases && item >= p.ph[k + 1].item_begin) ++k;
+    return k;
+  };
+  // x-pack (epilogue warps): a layer-0 item gets its x rows (this CTA's row tile) as bf16 hi/lo operand images in
+  // the item's private scratch slab.  fp32 [rows, G] row-major in, zero padded to the k-steps the MMA reads;
+  // (row, 8-column chunk) units are spread so that a warp reads contiguous memory, and all loads of a thread are
+  // in flight before the first use (the latents come from HBM).  Ends with the generic->async proxy fence and a
+  // barrier of the epilogue warps; the caller then arrives on the item's x-ready mbarrier.
+  constexpr int XB = 8;                      // (row, chunk) units per thread and batch
+  auto x_load = [&](int item, int u0, float (&v)[XB][8]) {
+    const StepPhase& f = p.ph[0];
+    const int etid = threadIdx.x - 64;
+    const int nchunks = f.in_ksteps * 2;
+    const int units = TC_ROWS * nchunks;
+    const bool vec2 = (p.ldx & 1) == 0 && (p.G & 1) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 7) == 0;
+    const int rg = item / f.n_tiles;
+    const int rt = rg * CM + (int)rank;
+#pragma unroll
+    for (int i = 0; i < XB; ++i) {
+      const int u = u0 + etid + i * (EPI_WARPS * 32);
+      const int r = u / nchunks, chunk = u - r * nchunks;
+      const int row = rt * TC_ROWS + r;
+      const float* src = p.x + (size_t)row * p.ldx + chunk * 8;
+      const bool ok = u < units && row < p.rows;
+      if (vec2) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          float2 t = make_float2(0.f, 0.f);
+          if (ok && chunk * 8 + e < p.G) t = __ldg(reinterpret_cast<const float2*>(src + e));
+          v[i][e] = t.x; v[i][e + 1] = t.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] = (ok && chunk * 8 + e < p.G) ? __ldg(src + e) : 0.f;
+      }
+    }
+  };
+  auto x_store = [&](int item, int u0, const float (&v)[XB][8]) {
+    const StepPhase& f = p.ph[0];
+    const int etid = threadIdx.x - 64;
+    const int nchunks = f.in_ksteps * 2;
+    const int units = TC_ROWS * nchunks;
+    const int rg = item / f.n_tiles, nt = item - rg * f.n_tiles;
+    const int rt = rg * CM + (int)rank;
+    if (rt >= p.row_tiles) return;
+    uint8_t* slab = p.xp + (size_t)(nt * p.row_tiles + rt) * f.kb_in * (2u * TC_A_IMG);
+#pragma unroll
+    for (int i = 0; i < XB; ++i) {
+      const int u = u0 + etid + i * (EPI_WARPS * 32);
+      if (u < units) {
+        const int r = u / nchunks, chunk = u - r * nchunks;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2_bf16(v[i][2 * e], v[i][2 * e + 1], hi[e], lo[e]);
+        uint8_t* img = slab + (size_t)(chunk >> 3) * (2u * TC_A_IMG);
+        const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)(chunk & 7));
+        *reinterpret_cast<uint4*>(img + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (nparts == 2) *reinterpret_cast<uint4*>(img + TC_A_IMG + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  };
+  const int x_units = TC_ROWS * p.ph[0].in_ksteps * 2;
+  // pack batches [u_begin, units) of an item, then the generic->async proxy fence and a barrier of the epilogue warps
+  auto pack_x = [&](int item, int u_begin) {
+    for (int u0 = u_begin; u0 < x_units; u0 += XB * EPI_WARPS * 32) {
+      float v[XB][8];
+      x_load(item, u0, v);
+      x_store(item, u0, v);
+    }
+    ptx::fence_proxy_async_all();
+    ptx::named_bar_sync(1, EPI_WARPS * 32);
+  };
+  if (threadIdx.x == 0) {
+    TRACE(0);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(pfull_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), 2 * EPI_WARPS);
+    }
+    for (int j = 0; j < STEP_XMAX; ++j) ptx::mbar_init(xready_bar(j), 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) TRACE(1);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs of the pair) =====================
+    if (lane == 0) {
+      int s = 0, pm = 0, xj = 0;
+      uint32_t phs = 0;
+      for (int k = 0;; ++k) {
+        const int item = item_at(k);
+        if (item < 0) break;
+        const int pi = phase_of(item);
+        const StepPhase& f = p.ph[pi];
+        if (pm < 3) TRACE(2 + pm * 8 + 0);
+        const int j = item - f.item_begin;
+        const int rg = j / f.n_tiles, nt = j % f.n_tiles;
+        int rt = rg * CM + (int)rank;
+        if (rt >= p.row_tiles) rt = p.row_tiles - 1;      // padding CTA of an odd last group: loads stay in bounds
+        const int KB = f.kb_rec + f.kb_in;
+        const uint32_t b_half = (uint32_t)f.n_tile * 64u, b_part = (uint32_t)f.n_tile * 128u;
+        const bool layer0 = f.wait_flags == nullptr;
+        const uint8_t* a_in = f.a_in;
+        if (layer0) a_in += (size_t)nt * p.row_tiles * f.kb_in * (2u * TC_A_IMG);
+        for (int i = 0; i < KB; ++i) {
+          const bool rec = i < f.kb_rec;
+          const int kb = rec ? i : i - f.kb_rec;
+          if (!rec) {
+            if (!layer0) {
+              poll_ge(f.wait_flags + rg * f.kb_in + kb, 2, item);
+              ptx::fence_proxy_async_all();       // generic-proxy writes of the producing pair -> visible to our TMA
+            } else if (kb == 0) {
+              ptx::mbar_wait(xready_bar(xj), 0);   // our own epilogue warps packed this item's x rows
+              ptx::fence_proxy_async_all();
+              ++xj;
+            }
+            if (pm < 3 && kb == 0) TRACE(2 + pm * 8 + 1);
+          }
+          ptx::mbar_wait(empty_bar(s), phs ^ 1u);
+          const uint8_t* asrc = rec ? f.a_rec + (size_t)(rt * f.kb_rec + kb) * (2u * TC_A_IMG)
+                                    : a_in + (size_t)(rt * f.kb_in + kb) * (2u * TC_A_IMG);
+          const int wk = rec ? f.kb_in + kb : kb;          // weight K order: [input | recurrent]
+          const uint8_t* bsrc = f.w + (size_t)(nt * KB + wk) * (2u * b_part) + rank * b_half;
+          const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+          ptx::mbar_expect_tx(full_bar(s), a_bytes + nparts * b_half);
+          ptx::bulk_g2s(sa, asrc, a_bytes, full_bar(s));
+          ptx::bulk_g2s(sb, bsrc, b_half, full_bar(s));
+          if (nparts == 2) ptx::bulk_g2s(sb + b_half, bsrc + b_part, b_half, full_bar(s));
+          if (++s == p.stages) { s = 0; phs ^= 1u; }
+        }
+        if (pm < 3) TRACE(2 + pm * 8 + 7);
+        ++pm;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0, mit = 0;
+      uint32_t phs = 0;
+      for (int k = 0;; ++k, ++mit) {
+        const int item = item_at(k);
+        if (item < 0) break;
+        const StepPhase& f = p.ph[phase_of(item)];
+        const int KB = f.kb_rec + f.kb_in;
+        if (rank == 0) {
+          // ===================== MMA issuer (leader CTA) =====================
+          const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, f.n_tile);
+          const uint32_t b_half = (uint32_t)f.n_tile * 64u;
+          const int acc = mit & 1;
+          const uint32_t aph = (uint32_t)(mit >> 1) & 1u;
+          ptx::mbar_wait(tempty_bar(acc), aph ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+          uint32_t accum = 0;
+          for (int i = 0; i < KB; ++i) {
+            int ks = TC_KBLK / 16;
+            if (i >= f.kb_rec) {
+              const int left = f.in_ksteps - (i - f.kb_rec) * (TC_KBLK / 16);
+              ks = left < ks ? left : ks;
+            }
+            ptx::mbar_wait(full_bar(s), phs);
+            ptx::mbar_wait(pfull_bar(s), phs);
+            if (mit < 3 && i == 0) TRACE(2 + mit * 8 + 2);
+            ptx::tc_fence_after();
+            const uint32_t sa = base + (uint32_t)s * stage_bytes;
+            const uint64_t a_hi = ptx::make_sw128_desc(sa);
+            const uint64_t a_lo = ptx::make_sw128_desc(sa + TC_A_IMG);
+            const uint64_t b_hi = ptx::make_sw128_desc(sa + a_bytes);
+            const uint64_t b_lo = ptx::make_sw128_desc(sa + a_bytes + b_half);
+            for (int kk = 0; kk < ks; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 2);
+              ptx::umma2_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
+              accum = 1u;
+              if (nparts == 2) {
+                ptx::umma2_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                ptx::umma2_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+            ptx::umma2_commit_mcast(empty_bar(s), 3);
+            if (++s == p.stages) { s = 0; phs ^= 1u; }
+          }
+          ptx::umma2_commit_mcast(tfull_bar(acc), 3);
+          if (mit < 3) TRACE(2 + mit * 8 + 3);
+        } else {
+          // ===================== relay (peer CTA): "my stage landed" -> leader's pfull =====================
+          for (int i = 0; i < KB; ++i) {
+            ptx::mbar_wait(full_bar(s), phs);
+            ptx::mbar_arrive_remote(pfull_bar(s), 0);
+            if (++s == p.stages) { s = 0; phs ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == AUX_WARP) {
+    // ===================== GP trigger finalisers (generate_frames.py:283-289) =====================
+    // The auxiliary warps of the last NF CTAs take one rollout per lane (window slide, threshold, decision) once
+    // the D trigger CTAs have delivered their variances; the last of them publishes mask_ready.
+    if (p.trig.enabled) {
+      const StepTrig& g = p.trig;
+      const int nblk = (g.S + 31) / 32;
+      const int NF = nblk < (int)gridDim.x ? nblk : (int)gridDim.x;
+      const int fi = (int)gridDim.x - 1 - (int)blockIdx.x;
+      if (fi < NF) {
+        if (lane == 0) {
+          const long long t0 = clock64();
+          while (ptx::ld_relaxed_gpu(reinterpret_cast<const int*>(g.ticket)) < g.D) {
+            __nanosleep(100);
+            if (clock64() - t0 > 4000000000LL) {
+              printf("dvg_b200: trigger ticket wait timed out\n");
+              __trap();
+            }
+          }
+          (void)ptx::ld_acquire_gpu(reinterpret_cast<const int*>(g.ticket));
+        }
+        __syncwarp();
+        __threadfence();
+        const int cnt = *reinterpret_cast<volatile int32_t*>(g.count);
+        for (int sidx = fi * 32 + lane; sidx < g.S; sidx += NF * 32) {
+          if (g.W <= 16)
+            gp_trig_finalize_rollout16(sidx, g.S, g.D, g.var_rows, g.window, g.W, cnt, g.warmup, g.factor, g.value,
+                                       g.thr, g.mask, g.trig_list, g.trig_count);
+          else
+            gp_trig_finalize_rollout(sidx, g.S, g.D, g.var_rows, g.window, g.W, cnt, g.warmup, g.factor, g.value,
+                                     g.thr, g.mask, g.trig_list, g.trig_count);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0 && atomicAdd(g.ticket + 1, 1u) == (unsigned)NF - 1u) {
+          g.ticket[0] = 0;
+          g.ticket[1] = 0;
+          if (g.warmup && cnt < g.W) g.count[0] = cnt + 1;
+          __threadfence();
+          atomicExch(p.mask_ready, 1);
+          TRACE(31);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue / SIMT worker warps (2 .. 2+EPI_WARPS-1) =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t r_in_tile = (uint32_t)(q * 32 + lane);
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const int etid = ew * 32 + lane;
+    // x-pack of every layer-0 item of this pair, in item order
+    {
+      int xj = 0;
+      for (int k = 0; xj < STEP_XMAX; ++k) {
+        const int item = item_at(k);
+        if (item < 0) break;
+        if (item >= p.groups * p.ph[0].n_tiles) continue;     // not a layer-0 item
+        pack_x(item, 0);
+        if (etid == 0) ptx::mbar_arrive(xready_bar(xj));
+        ++xj;
+      }
+      if (etid == 0) TRACE(27);
+    }
+    int mit = 0;
+    for (int k = 0;; ++k, ++mit) {
+      const int item = item_at(k);
+      if (item < 0) break;
+      const StepPhase& f = p.ph[phase_of(item)];
+      const int j = item - f.item_begin;
+      const int rg = j / f.n_tiles, nt = j % f.n_tiles;
+      const int rt = rg * CM + (int)rank;
+      const int acc = mit & 1;
+      const uint32_t aph = (uint32_t)(mit >> 1) & 1u;
+      const int tm = mit;
+      const int row = rt * TC_ROWS + (int)r_in_tile;
+      const bool valid = row < p.rows;
+      float* sb = s_bias + acc * 256;
+      if (etid < f.n_tile) {
+        float bv = __ldg(f.bias + (size_t)nt * f.n_tile + etid);
+        if (f.type == PH_LSTM) bv *= (etid >> 6) == 2 ? -2.f * kLog2e : -kLog2e;
+        else if (f.type == PH_TANH) bv *= -2.f * kLog2e;
+        sb[etid] = bv;
+      }
+      // All fp32 state I/O goes through a warp-private 32 x 128 B transpose buffer so that every global access is
+      // a full 128-byte line per 8 lanes.
+      uint8_t* eb = s_ebuf + ew * 4096;
+      const int er = lane >> 3, ec = lane & 7;           // coalesced mapping: 4 rows x 8 chunks per instruction
+      const int row_w0 = rt * TC_ROWS + q * 32;          // first row of this warp
+      if (f.type == PH_LSTM) {
+        float4 cin[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + er;
+          cin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_w0 + rr < p.rows)
+            cin[i] = __ldg(reinterpret_cast<const float4*>(f.c_in + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32) + ec);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + er;
+          *reinterpret_cast<float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4)) = cin[i];
+        }
+        __syncwarp();
+      }
+      ptx::named_bar_sync(1, EPI_WARPS * 32);
+      ptx::mbar_wait(tfull_bar(acc), aph);
+      if (etid == 0 && tm < 3) TRACE(2 + tm * 8 + 4);
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + tlane + (uint32_t)(acc * ACC_STRIDE);
+      if (f.type == PH_LSTM) {
+        const bool held = valid && p.hold != nullptr && p.hold[row / p.rows_per_flag] != 0;
+        const size_t idx0 = (size_t)row * p.H + nt * 64 + half * 32;
+        // tile columns: [i: 64 units][f: 64][g: 64][o: 64]; this warp handles units half*32 .. half*32+31 of its 32
+        // rows, 4 units per trip (the loop body must fit the ~6 KB L0 instruction cache: with a larger body the
+        // four SM partitions were instruction-fetch bound at ~0.5 IPC).  The next group's accumulators are fetched
+        // from TMEM while the current group is computed.  h' (fp32) is parked in the consumed i columns, its bf16
+        // hi/lo words in the consumed f columns.
+        uint32_t rc[16];
+        ptx::tmem_ld4x4(tacc + half * 32, tacc + 64 + half * 32, tacc + 128 + half * 32, tacc + 192 + half * 32, rc);
+        ptx::tmem_ld_wait16(rc);
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+          const int cb = half * 32 + u * 4;
+          uint32_t rn[16];
+          const int cbn = u < 7 ? cb + 4 : cb;      // last trip: harmless re-read
+          ptx::tmem_ld4x4(tacc + cbn, tacc + 64 + cbn, tacc + 128 + cbn, tacc + 192 + cbn, rn);
+          float4* cslot = reinterpret_cast<float4*>(eb + lane * 128 + ((u ^ (lane & 7)) << 4));
+          const float4 c4 = *cslot;
+          const float cp[4] = {c4.x, c4.y, c4.z, c4.w};
+          float hn[4], cn[4];
+          if (held) {
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(f.h_in + idx0 + u * 4));
+            hn[0] = h4.x; hn[1] = h4.y; hn[2] = h4.z; hn[3] = h4.w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cn[i] = cp[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              lstm_cell_fast(__uint_as_float(rc[i]), __uint_as_float(rc[4 + i]), __uint_as_float(rc[8 + i]),
+                             __uint_as_float(rc[12 + i]), sb[cb + i], sb[64 + cb + i], sb[128 + cb + i],
+                             sb[192 + cb + i], cp[i], hn[i], cn[i]);
+          }
+          *cslot = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          uint32_t hw[4], sw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hw[i] = __float_as_uint(hn[i]);
+          split2_bf16(hn[0], hn[1], sw[0], sw[2]);
+          split2_bf16(hn[2], hn[3], sw[1], sw[3]);
+          ptx::tmem_ld_wait16(rn);                 // rn landed; also orders the stores below after our loads of cb
+          ptx::tmem_st4(tacc + cb, hw);
+          ptx::tmem_st4(tacc + 64 + cb, sw);       // {hi(0,1), hi(2,3), lo(0,1), lo(2,3)}
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rc[i] = rn[i];
+        }
+        ptx::tmem_st_wait();
+        {
+          // packed h' image of this CTA's 128 rows x 64 units (one k-block of the next GEMM's A operand)
+          uint8_t* img = f.hp_out + (size_t)(rt * (p.H / 64) + nt) * (2u * TC_A_IMG);
+          uint32_t w[32];
+          ptx::tmem_ld32_wait(tacc + 64 + half * 32, w);
+          if (valid) {
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+              // units pr*16 .. pr*16+15 -> 16-byte chunks (half*4 + 2pr, half*4 + 2pr + 1): one aligned 32-byte
+              // sector per image, chunk order swapped when bit 0 of (row & 7) is set.  Chunk c (8 units) is made of
+              // trips 2c, 2c+1: hi words w[8c+0], w[8c+1], w[8c+4], w[8c+5]; lo words w[8c+2], w[8c+3], w[8c+6], w[8c+7].
+              const uint32_t chunk0 = (uint32_t)(half * 4 + 2 * pr);
+              const uint32_t o0 = sw128_offset(r_in_tile, chunk0), o1 = sw128_offset(r_in_tile, chunk0 + 1);
+              const bool swap = o1 < o0;
+              const uint32_t ob = swap ? o1 : o0;
+              const int b0 = 16 * pr, b1 = 16 * pr + 8;
+              const uint32_t h0[4] = {w[b0], w[b0 + 1], w[b0 + 4], w[b0 + 5]};
+              const uint32_t l0[4] = {w[b0 + 2], w[b0 + 3], w[b0 + 6], w[b0 + 7]};
+              const uint32_t h1[4] = {w[b1], w[b1 + 1], w[b1 + 4], w[b1 + 5]};
+              const uint32_t l1[4] = {w[b1 + 2], w[b1 + 3], w[b1 + 6], w[b1 + 7]};
+              uint32_t th[8], tl[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                th[i] = swap ? h1[i] : h0[i]; th[4 + i] = swap ? h0[i] : h1[i];
+                tl[i] = swap ? l1[i] : l0[i]; tl[4 + i] = swap ? l0[i] : l1[i];
+              }
+              st256u(img + ob, th);
+              if (nparts == 2) st256u(img + TC_A_IMG + ob, tl);
+            }
+          }
+        }
+        // publish the k-block: consumers (next layer / head) only read the packed image
+        __threadfence();
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+        if (etid == 0) {
+          atomicAdd(f.done_flags + rg * f.n_tiles + nt, 1);
+          if (tm == 0) TRACE(28);
+        }
+        uint32_t hv[32];
+        ptx::tmem_ld32_wait(tacc + half * 32, hv);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+          else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {      // c' tile -> global, 128-byte lines
+          const int rr = i * 4 + er;
+          const float4 t = *reinterpret_cast<const float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4));
+          if (row_w0 + rr < p.rows)
+            reinterpret_cast<float4*>(f.c_out + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32)[ec] = t;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8)
+          *reinterpret_cast<uint4*>(eb + lane * 128 + ((c8 ^ (lane & 7)) << 4)) =
+              make_uint4(hv[c8 * 4], hv[c8 * 4 + 1], hv[c8 * 4 + 2], hv[c8 * 4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {      // h' tile -> global
+          const int rr = i * 4 + er;
+          const float4 t = *reinterpret_cast<const float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4));
+          if (row_w0 + rr < p.rows)
+            reinterpret_cast<float4*>(f.h_out + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32)[ec] = t;
+        }
+        __syncwarp();
+        if (etid == 0 && tm == 0) TRACE(29);
+      } else if (f.type == PH_TANH) {
+        // y = tanh(acc + b): this warp owns rows q*32.. and columns half*n_tile/2 ..; groups of <= 32 columns go
+        // through the transpose buffer so the [rows, G] output is written in full row segments.
+        const int ncol_half = f.n_tile / 2;
+        const int c_begin = half * ncol_half;
+        const bool vec2 = (f.ldy & 1) == 0 && (f.n_valid & 1) == 0;
+        for (int g0 = 0; g0 < ncol_half; g0 += 32) {
+          const int gw = ncol_half - g0 < 32 ? ncol_half - g0 : 32;   // 32 or 16
+          for (int c16 = 0; c16 < gw; c16 += 16) {
+            float v[16];
+            ptx::tmem_ld16_wait(tacc + c_begin + g0 + c16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = tanh_fast_prescaled(v[i], sb[c_begin + g0 + c16 + i]);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)
+              *reinterpret_cast<float4*>(eb + lane * 128 + ((((c16 >> 2) + c4) ^ (lane & 7)) << 4)) =
+                  make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+          }
+          __syncwarp();
+          const int lpr = gw >> 1;              // lanes per row (one float2 each)
+          const int rpi = 32 / lpr;             // rows per instruction
+          for (int i = 0; i < 32 / rpi; ++i) {
+            const int rr = i * rpi + lane / lpr;
+            const int cc = (lane % lpr) * 2;
+            const float2 t = *reinterpret_cast<const float2*>(eb + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4);
+            const int col = c_begin + g0 + cc;
+            const int grow = row_w0 + rr;
+            if (grow < p.rows && col < f.n_valid) {
+              float* dst = f.y + (size_t)grow * f.ldy + col;
+              if (vec2) *reinterpret_cast<float2*>(dst) = t;
+              else { dst[0] = t.x; if (col + 1 < f.n_valid) dst[1] = t.y; }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        const int nchunks = f.n_tile / 16;
+#pragma unroll 1
+        for (int jc = half; jc < nchunks; jc += 2) {
+          float v[16];
+          ptx::tmem_ld16_wait(tacc + jc * 16, v);
+          if (valid) {
+            const int col0 = nt * f.n_tile + jc * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += sb[jc * 16 + i];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const int zi = (col0 + i) >> 1;
+              if (zi < f.Z) {
+                const size_t idx = (size_t)row * f.Z + zi;
+                f.mu[idx] = v[i];
+                f.logvar[idx] = v[i + 1];
+                f.z[idx] = fmaf(f.eps[idx], expf(0.5f * v[i + 1]), v[i]);
+              }
+            }
+          }
+        }
+      }
+      if (f.type != PH_LSTM) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+          else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
+        }
+      }
+      if (etid == 0 && tm < 3) {
+        TRACE(2 + tm * 8 + 5);
+#ifdef DVG_TRACE
+        if (p.trace) p.trace[(size_t)blockIdx.x * 32 + 2 + tm * 8 + 6] = 1000000ull + item;
+#endif
+      }
+      // ---- GP variance trigger (generate_frames.py:227-232,275): after their first tile the epilogue warps wait
+      //      for the next layer's accumulator anyway, so the last D CTAs (two items or fewer each) evaluate one latent
+      //      dim for every rollout there: two threads per (rollout, dim) task -- |Linv k|^2 and |L_q^T k|^2 -- with the
+      //      factors staged in the (now idle) transpose buffers.  Nobody in this launch waits for the result except
+      //      the finalisers and the end-of-kernel restore.
+      if (k == 0 && p.trig.enabled && (int)blockIdx.x >= (int)gridDim.x - p.trig.D) {
+        const StepTrig& g = p.trig;
+        const int d = (int)gridDim.x - 1 - (int)blockIdx.x, MP = g.mp;
+        float* s_linv = reinterpret_cast<float*>(s_ebuf);
+        float* s_lqt = s_linv + MP * MP;
+        float* s_z = s_lqt + MP * MP;
+        float* s_part = s_z + MP;
+        ptx::named_bar_sync(1, EPI_WARPS * 32);     // every warp is done with its transpose buffer
+        {
+          const float4* g1 = reinterpret_cast<const float4*>(g.linv + (size_t)d * MP * MP);
+          const float4* g2 = reinterpret_cast<const float4*>(g.lqt + (size_t)d * MP * MP);
+          for (int e = etid; e < MP * MP / 4; e += EPI_WARPS * 32) {
+            reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
+            reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
+          }
+          for (int e = etid; e < MP; e += EPI_WARPS * 32) s_z[e] = g.z[(size_t)d * MP + e];
+        }
+        const float ell = g.hyp[d * 4 + 0], sc = g.hyp[d * 4 + 1], noise = g.hyp[d * 4 + 3];
+        const int hf = etid >> 7, li = etid & 127;
+        float xv[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {               // latents come from HBM: issue the loads of up to 512 rollouts first
+          const int i = b * 128 + li;
+          xv[b] = i < g.S ? __ldg(p.x + (size_t)g.stat_rows[i] * p.ldx + d) : 0.f;
+        }
+        ptx::named_bar_sync(1, EPI_WARPS * 32);
+        for (int base_s = 0; base_s < g.S; base_s += 128) {
+          const int i = base_s + li;
+          const int b = base_s >> 7;
+          float xi = b < 4 ? (b == 0 ? xv[0] : b == 1 ? xv[1] : b == 2 ? xv[2] : xv[3])
+                           : (i < g.S ? __ldg(p.x + (size_t)g.stat_rows[i] * p.ldx + d) : 0.f);
+          float pv = 0.f, pw = 0.f;
+          if (i < g.S) {
+            if (MP == 40) {
+              gp_trig_partial_rolled<40>(xi, sc, 1.0f / ell, hf == 0 ? s_linv : nullptr, hf == 0 ? nullptr : s_lqt, s_z,
+                                         pv, pw);
+            } else {
+              const float part = gp_trig_partial<0>(xi, sc, 1.0f / ell, MP, hf == 0 ? s_linv : s_lqt, s_z, hf != 0);
+              pv = part; pw = part;
+            }
+          }
+          if (hf == 1) s_part[li] = pw;
+          ptx::named_bar_sync(1, EPI_WARPS * 32);
+          if (hf == 0 && i < g.S) g.var_rows[(size_t)d * g.S + i] = (sc - pv) + s_part[li] + noise;
+          ptx::named_bar_sync(1, EPI_WARPS * 32);
+        }
+        if (d == 0 && etid == 0) *g.trig_count = 0;   // ordered before the finalisers by the ticket below
+        __threadfence();
+        ptx::named_bar_sync(1, EPI_WARPS * 32);      // also: the transpose buffers go back to the tile epilogues
+        if (etid == 0) {
+          atomicAdd(g.ticket, 1u);
+          TRACE(26);
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------------------
+  ptx::tc_fence_before();
+  if (p.restore) __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) TRACE(30);
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+  // Decision step of the fused trigger: rollouts that fired keep their LSTM state (generate_frames.py:289-295).
+  // Rare, so it is handled after the fact: once every CTA has finished its items, the state rows of the fired
+  // rollouts are copied back from the input block (fp32 h, c and the packed h images), spread over all CTAs.
+  if (p.restore) {
+    if (threadIdx.x == 0) {
+      atomicAdd(p.done_ctr, 1);
+      poll_ge(p.mask_ready, 1, -1);
+      s_misc[0] = *reinterpret_cast<volatile int*>(p.trig.trig_count);
+    }
+    __syncthreads();
+    const int n_fired = s_misc[0];
+    if (n_fired > 0) {
+      if (threadIdx.x == 0) {
+        poll_ge(p.done_ctr, (int)gridDim.x, -2);
+        __threadfence();
+      }
+      __syncthreads();
+      const int chunks = 3 * p.L;
+      const int hk = p.H / 64;
+      for (int wi = blockIdx.x; wi < n_fired * chunks; wi += gridDim.x) {
+        const int s = p.trig.trig_list[wi / chunks];
+        const int c = wi % chunks, l = c / 3, kind = c % 3;
+        const StepPhase& f = p.ph[l];
+        const int r0 = s * p.rows_per_flag;
+        const int r1 = r0 + p.rows_per_flag < p.rows ? r0 + p.rows_per_flag : p.rows;
+        if (kind < 2) {
+          const float4* src = reinterpret_cast<const float4*>((kind == 0 ? f.h_in : f.c_in) + (size_t)r0 * p.H);
+          float4* dst = reinterpret_cast<float4*>((kind == 0 ? f.h_out : f.c_out) + (size_t)r0 * p.H);
+          const int n4 = (r1 - r0) * p.H / 4;
+          for (int i = threadIdx.x; i < n4; i += STEP_THREADS) dst[i] = __ldg(src + i);
+        } else {
+          const int per_row = hk * 2 * 8;       // 16-byte units per row: k-blocks x (hi, lo) x 8 chunks
+          for (int i = threadIdx.x; i < (r1 - r0) * per_row; i += STEP_THREADS) {
+            const int r = r0 + i / per_row, e = i % per_row;
+            const int kb = e >> 4, part = (e >> 3) & 1, qd = e & 7;
+            const size_t off = ((size_t)((r / TC_ROWS) * hk + kb) * 2 + part) * TC_A_IMG + (size_t)(r % TC_ROWS) * 128 + qd * 16;
+            *reinterpret_cast<uint4*>(f.hp_out + off) = __ldg(reinterpret_cast<const uint4*>(f.a_rec + off));
+          }
+        }
+      }
+    }
+  }
+  // Self-resetting dependency counters: the last CTA to get here (every CTA has finished reading them) zeroes
+  // them for the next launch -- no cudaMemset node per step.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* exit_ctr = p.flag_words + p.n_flag_words;
+    __threadfence();
+    if (atomicAdd(exit_ctr, 1) == (int)gridDim.x - 1) {
+      for (int i = 0; i < p.n_flag_words; ++i) p.flag_words[i] = 0;
+      __threadfence();
+      *exit_ctr = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------
+static bool use_fused() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVG_TC_FUSED");     // developer switch: 0 = one launch per GEMM
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+size_t lstm_step_flag_words(const dvg_lstm_s* h, int rows) {
+  const int groups = ceil_div(ceil_div(rows, TC_ROWS), 2), hk = h->dims.hidden_size / 64;
+  return (size_t)h->dims.n_layers * align_up((size_t)groups * hk, 32) + 8;
+}
+size_t lstm_step_xp_bytes(const dvg_lstm_s* h, int rows) {
+  return (size_t)(h->dims.hidden_size / 64) * ceil_div(rows, TC_ROWS) * ceil_div(h->dims.input_size, 64) * 2 * TC_A_IMG;
+}
+
+// Item order of the step kernel (position i runs on pair i % pairs as its (i / pairs)-th item).  Every item's
+// dependencies must sit at smaller positions.  nullptr = identity order (layer-major).
+int lstm_step_build_schedule(dvg_lstm_s* h, int rows) {
+  (void)h; (void)rows;
+  return DVG_OK;
+}
+
+bool lstm_step_usable(const dvg_lstm_s* h, int rows) {
+  if (!h->tc_ok || !use_fused()) return false;
+  const int RT = ceil_div(rows, TC_ROWS), groups = ceil_div(RT, 2), hk = h->dims.hidden_size / 64;
+  const int pairs = h->sm_count / 2;
+  if (RT < 2 || pairs < 1) return false;
+  return ceil_div(groups * hk, pairs) <= STEP_XMAX;
+}
+
+int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
+                     const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out, float* y,
+                     int ldy, const float* eps, float* z, float* mu, float* logvar, const uint8_t* hold,
+                     int rows_per_flag, cudaStream_t stream, const StepTrigHost* trig) {
+  const int G = h->dims.input_size, H = h->dims.hidden_size, L = h->dims.n_layers;
+  const int hk = H / 64, RT = ceil_div(rows, TC_ROWS), kbx = ceil_div(G, 64);
+  const int groups = ceil_div(RT, 2);
+  const size_t lsz = (size_t)rows * H;
+  const size_t lpk = (size_t)RT * hk * 2 * TC_A_IMG;
+  StepArgs a{};
+  a.rows = rows; a.row_tiles = RT; a.groups = groups; a.nsplit = nsplit; a.H = H; a.L = L; a.G = G; a.ldx = ldx;
+  a.kbx = kbx; a.x = x; a.xp = h->tc_xp;
+  a.hold = hold; a.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
+  const int fstride = (int)align_up((size_t)groups * hk, 32);
+  int* flags = h->fused_flags;
+  a.flag_words = flags;
+  a.n_flag_words = L * fstride + 2;
+  a.mask_ready = flags + (size_t)L * fstride;
+  a.done_ctr = a.mask_ready + 1;
+  if (trig != nullptr) {
+    StepTrig& t = a.trig;
+    t.enabled = 1; t.S = trig->S; t.D = g->dims.num_dims; t.mp = g->mp; t.W = trig->W; t.warmup = trig->warmup;
+    t.factor = trig->factor; t.stat_rows = trig->stat_rows;
+    t.z = g->z; t.linv = g->linv; t.lqt = g->lqt; t.hyp = g->hyp;
+    t.var_rows = g->var_rows; t.ticket = g->ticket; t.window = trig->window; t.count = trig->count;
+    t.value = trig->value; t.thr = trig->thr; t.mask = trig->mask; t.trig_list = g->trig_list;
+    t.trig_count = g->trig_count;
+    a.restore = trig->warmup ? 0 : 1;
+    a.rows_per_flag = rows / trig->S;
+    a.hold = nullptr;
+  }
+  int np = 0, item = 0;
+  for (int l = 0; l < L; ++l) {
+    StepPhase& f = a.ph[np];
+    const TcGemmPlan& pl = l == 0 ? h->tc_layer0f : h->tc_layer[l];
+    f.type = PH_LSTM; f.n_tile = 256; f.n_tiles = hk; f.item_begin = item;
+    f.kb_in = l == 0 ? kbx : hk; f.kb_rec = hk;
+    f.in_ksteps = l == 0 ? ceil_div(G, 16) : hk * 4;
+    f.a_in = l == 0 ? h->tc_xp : hp_out + (l - 1) * lpk;
+    f.a_rec = hp_in + l * lpk;
+    f.w = pl.w; f.bias = pl.bias;
+    f.wait_flags = l == 0 ? nullptr : flags + (size_t)(l - 1) * fstride;
+    f.done_flags = flags + (size_t)l * fstride;
+    f.c_in = c_in + l * lsz; f.h_in = h_in + l * lsz; f.h_out = h_out + l * lsz; f.c_out = c_out + l * lsz;
+    f.hp_out = hp_out + l * lpk;
+    item += groups * hk; ++np;
+  }
+  {  // head
+    StepPhase& f = a.ph[np];
+    const bool gauss = h->dims.kind == DVG_GAUSSIAN_LSTM;
+    f.type = gauss ? PH_GAUSS : PH_TANH; f.n_tile = h->tc_head.n_tile; f.n_tiles = 1; f.item_begin = item;
+    f.kb_in = hk; f.kb_rec = 0; f.in_ksteps = hk * 4;
+    f.a_in = hp_out + (L - 1) * lpk; f.a_rec = nullptr;
+    f.w = h->tc_head.w; f.bias = h->tc_head.bias;
+    f.wait_flags = flags + (size_t)(L - 1) * fstride;
+    f.done_flags = nullptr;
+    f.y = y; f.ldy = ldy; f.n_valid = h->dims.output_size;
+    f.eps = eps; f.z = z; f.mu = mu; f.logvar = logvar; f.Z = h->dims.output_size;
+    item += groups; ++np;
+  }
+  a.n_phases = np; a.total_items = item;
+  const uint32_t nparts = nsplit == 1 ? 1 : 2;
+  const size_t stage_bytes = nparts * ((size_t)TC_A_IMG + (size_t)256 * 64);
+  const size_t tail = STEP_BAR_BYTES + 2 * 256 * sizeof(float) + (size_t)EPI_WARPS * 4096;
+  int stages = (int)((227 * 1024 - tail) / stage_bytes);
+  if (stages > STEP_MAX_STAGES) stages = STEP_MAX_STAGES;
+  a.stages = stages; a.stage_bytes = (uint32_t)stage_bytes;
+  const size_t smem = stages * stage_bytes + tail;
+  static bool configured = false;
+  if (!configured) {
+    DVG_CUDA(cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  int pairs = h->sm_count / 2;
+  if (pairs > a.total_items) pairs = a.total_items;
+  if (h->sched_dev != nullptr && h->sched_rows == rows && h->sched_pairs == pairs) {
+    a.sched = h->sched_dev; a.sched_len = h->sched_len;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pairs * 2);
+  cfg.blockDim = dim3(STEP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef DVG_TRACE
+  static unsigned long long* tbuf = nullptr;
+  const bool tr = getenv("DVG_TC_TRACE") != nullptr;
+  if (tr) {
+    if (!tbuf) cudaMalloc(&tbuf, 256 * 32 * 8);
+    cudaMemsetAsync(tbuf, 0, 256 * 32 * 8, stream);
+    a.trace = tbuf;
+  }
+#endif
+  h->prof_mark(stream);
+  DVG_CUDA(cudaLaunchKernelEx(&cfg, lstm_step_kernel, (const StepArgs)a));
+  h->prof_mark(stream);
+#ifdef DVG_TRACE
+  if (tr) {
+    static int n_dump = 0;
+    const char* which = getenv("DVG_TC_TRACE_LAUNCH");
+    const int want = which ? atoi(which) : 4;
+    cudaStreamSynchronize(stream);
+    if (n_dump++ == want) {
+      std::vector<unsigned long long> hbuf(256 * 32);
+      cudaMemcpy(hbuf.data(), tbuf, 256 * 32 * 8, cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull;
+      for (int b = 0; b < (int)cfg.gridDim.x; ++b) if (hbuf[b * 32] && hbuf[b * 32] < t0) t0 = hbuf[b * 32];
+      fprintf(stderr, "STEP TRACE grid=%d items=%d stages=%d restore=%d: start setup | per item: pstart depok stage0 mma_issued acc_ready epi_done item requested | trigdone xpack published stored end finalizer\n",
+              (int)cfg.gridDim.x, a.total_items, stages, a.restore);
+      for (int b = 0; b < (int)cfg.gridDim.x; ++b) {
+        fprintf(stderr, "cta %3d:", b);
+        for (int i = 0; i < 32; ++i) {
+          unsigned long long v = hbuf[b * 32 + i];
+          if (i == 2 || i == 10 || i == 18 || i == 26) fprintf(stderr, " |");
+          if (v >= 1000000ull && v < 2000000ull) fprintf(stderr, " #%lld", (long long)(v - 1000000ull));
+          else fprintf(stderr, " %lld", v ? (long long)(v - t0) : -1ll);
+        }
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+#endif
+  return DVG_OK;
+}
+
+bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows) {
+  const size_t need = sizeof(float) * ((size_t)2 * g->mp * g->mp + g->mp + 128);
+  const int pairs = h->sm_count / 2;
+  return lstm_step_usable(h, rows) && need <= (size_t)EPI_WARPS * 4096 && g->dims.num_dims <= pairs * 2;
+}
+
+// trigger + LSTM step in one launch; caller guarantees lstm_tc_can_fuse_trigger().
+int lstm_tc_rollout_step(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
+                         const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
+                         float* y, int ldy, int S, const int32_t* stat_rows, float* window, int W, int32_t* count,
+                         int warmup, float factor, float* value, float* thr, uint8_t* mask, cudaStream_t stream) {
+  StepTrigHost t{};
+  t.S = S; t.W = W; t.warmup = warmup; t.factor = factor; t.stat_rows = stat_rows; t.window = window; t.count = count;
+  t.value = value; t.thr = thr; t.mask = mask;
+  g->last_mask = mask;
+  g->last_mask_rollouts = S;
+  return lstm_step_launch(h, g, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, rows / S, stream, &t);
+}
+
+}  // namespace dvg

@@ -25,9 +25,7 @@
 // Two TMEM accumulator buffers (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <stdlib.h>
 
-#include "gp_trigger.cuh"
-#include "internal.cuh"
-#include "ptx.cuh"
+#include "tc_common.cuh"
 
 namespace dvg {
 
@@ -52,82 +50,6 @@ struct TcArgs {
   unsigned long long* trace;  // DVG_TRACE builds only: per-CTA timestamps
 };
 
-#ifdef DVG_TRACE
-#define TRACE(slot)                                                                   \
-  do {                                                                                \
-    if (p.trace) {                                                                    \
-      unsigned long long _t;                                                          \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                          \
-      p.trace[(size_t)blockIdx.x * 32 + (slot)] = _t;                                 \
-    }                                                                                 \
-  } while (0)
-#else
-#define TRACE(slot) do {} while (0)
-#endif
-constexpr int EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
-constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;  // TMEM columns per accumulator buffer
-
-// Thread-per-row accesses touch 32 different 128-byte lines per warp instruction, and the L1TEX cost is per
-// line touched, not per byte: use the 256-bit LDG/STG of sm_100 so each line is visited as rarely as possible.
-__device__ __forceinline__ void ld256(const float* p, float* v) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void st256(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void st256u(void* p, const uint32_t* v) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
-  ld256(p, v);
-  ld256(p + 8, v + 8);
-}
-__device__ __forceinline__ void store16(float* p, const float (&v)[16]) {
-  st256(p, v);
-  st256(p + 8, v + 8);
-}
-
-__device__ __forceinline__ void store_split16(uint8_t* img_hi, uint32_t r_in_tile, uint32_t chunk0, const float (&v)[16]) {
-  // 16 consecutive K elements of one row -> two 16-byte chunks in the hi image and two in the lo image.
-  uint32_t hi[8], lo[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) split2_bf16(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-  uint8_t* img_lo = img_hi + TC_A_IMG;
-  // chunk0 is even: the swizzled positions of chunks {chunk0, chunk0+1} form one aligned 32-byte sector,
-  // in swapped order when bit 0 of (row & 7) is set -> one 256-bit store per image.
-  const uint32_t o0 = sw128_offset(r_in_tile, chunk0), o1 = sw128_offset(r_in_tile, chunk0 + 1);
-  const bool swap = o1 < o0;
-  const uint32_t ob = swap ? o1 : o0;
-  uint32_t th[8], tl[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    th[i] = swap ? hi[4 + i] : hi[i];
-    th[4 + i] = swap ? hi[i] : hi[4 + i];
-    tl[i] = swap ? lo[4 + i] : lo[i];
-    tl[4 + i] = swap ? lo[i] : lo[4 + i];
-  }
-  st256u(img_hi + ob, th);
-  st256u(img_lo + ob, tl);
-}
-
-// LSTM pointwise math for 16 hidden units of one row (i,f,g,o pre-activations in r[0..63]).
-__device__ __forceinline__ void lstm_pointwise16(const uint32_t (&r)[64], const float* sb, int cb, const float (&cp)[16],
-                                                 float (&hn)[16], float (&cn)[16]) {
-  // sb holds the biases pre-scaled by -log2e (i, f, o) / -2 log2e (g): see lstm_cell_fast
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    lstm_cell_fast(__uint_as_float(r[i]), __uint_as_float(r[16 + i]), __uint_as_float(r[32 + i]),
-                   __uint_as_float(r[48 + i]), sb[cb + i], sb[64 + cb + i], sb[128 + cb + i], sb[192 + cb + i], cp[i],
-                   hn[i], cn[i]);
-}
 // Cluster of CM CTAs along the row-tile axis: the CM CTAs of a cluster work on CM consecutive row tiles
 // and the SAME N tile, so the weight k-block images are identical for all of them -- each CTA fetches
 // 1/CM of every weight image and TMA-multicasts it into all CM shared memories (L2 -> SM traffic for the
@@ -633,556 +555,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm2_kernel(const TcArgs p)
 }
 
 
-// ---------------------------------------------------------------------------------------------------
-// Whole LSTM time step in ONE persistent launch (cta_group::2 pairs).
-//
-// Work items, in dependency order (item index = scheduling order, pair p runs items p, p+P, p+2P, ...):
-//   PACKX(rg)        x rows of row group rg (256 rows) -> bf16 hi/lo operand images        (epilogue warps only)
-//   LSTM_0(rg, nt)   layer 0 with the embed folded in: A = [x | h_0], K = G' + H           needs PACKX(rg)
-//   LSTM_l(rg, nt)   A = [h'_{l-1} | h_l]                                                   needs LSTM_{l-1}(rg, *)
-//   HEAD(rg)         tanh(h'_{L-1} W_o^T + b_o)  or  mu/logvar/z                            needs LSTM_{L-1}(rg, *)
-// A dependency is a per-row-group counter in global memory: the epilogue publishes with
-// (st.global ... ; __threadfence ; bar ; atomicAdd), the TMA producer acquires it, issues fence.proxy.async and
-// only then lets the async proxy read the images the other pair wrote.  All pairs are co-resident (one CTA per
-// SM, grid <= #SMs) and every item only waits on items with a smaller index, so the schedule cannot deadlock.
-// Versus one launch per GEMM this removes 4 launches + prologues per step and lets the second wave of one
-// layer (160 tiles on 148 SMs) overlap the first wave of the next.
-// ---------------------------------------------------------------------------------------------------
-enum { PH_PACKX = 0, PH_LSTM = 1, PH_TANH = 2, PH_GAUSS = 3 };
-constexpr int MAX_PHASES = MAX_LAYERS + 2;
-
-struct FusedPhase {
-  int type, n_tile, n_tiles, kb0, kb1, item_begin;
-  const uint8_t* a0; const uint8_t* a1; const uint8_t* w; const float* bias;
-  const int* wait_flags; int wait_target; int* done_flags;
-  const float* c_in; const float* h_in; float* h_out; float* c_out; uint8_t* hp_out;   // LSTM
-  float* y; int ldy; int n_valid;                                                       // TANH
-  const float* eps; float* z; float* mu; float* logvar; int Z;                          // GAUSS
-  const float* x; int ldx; int G; uint8_t* xp; int kbx;                                 // PACKX
-};
-// GP variance trigger folded into the step kernel: it only needs the step's input latents, and the epilogue warps
-// of every CTA are idle until the first accumulator is ready (~10 us), so the trigger runs there for free; the
-// LSTM epilogues read its mask (hold flags) after `mask_ready` is published.
-struct TrigArgs {
-  int enabled, S, D, mp, ldx, W, warmup;
-  float factor;
-  const float* x; const int32_t* stat_rows;
-  const float* z; const float* linv; const float* lqt; const float* hyp;
-  float* var_rows; unsigned int* ticket; float* window; int32_t* count;
-  float* value; float* thr; uint8_t* mask; int* trig_list; int* trig_count; int* mask_ready;
-};
-struct FusedArgs {
-  int rows, row_tiles, groups, nsplit, stages, n_phases, total_items, H, rows_per_flag;
-  uint32_t stage_bytes;
-  const uint8_t* hold;
-  unsigned long long* trace;
-  int* flag_words; int n_flag_words;   // all dependency counters (+ mask_ready); last word = exit counter
-  TrigArgs trig;
-  FusedPhase ph[MAX_PHASES];
-};
-
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__global__ void __launch_bounds__(TC_THREADS, 1) lstm_fused_kernel(const __grid_constant__ FusedArgs p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t raw = ptx::smem_u32(smem_raw);
-  const uint32_t base = raw;   // declared __align__(1024); checked below (SWIZZLE_128B images need it)
-  if ((raw & 1023u) != 0) {
-    if (threadIdx.x == 0) printf("dvg_b200: dynamic shared memory base is not 1024-byte aligned\n");
-    __trap();
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int CM = 2;
-  const uint32_t rank = ptx::cluster_ctarank();
-  const uint32_t stage_bytes = p.stage_bytes;
-  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-  auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * p.stages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * p.stages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * p.stages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * p.stages + 4);
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base - raw) + 128);  // [2][256] floats
-  uint8_t* s_ebuf = smem_raw + (bar_base - raw) + 128 + 2 * 256 * sizeof(float);  // [EPI_WARPS][4 KB]
-
-  if (threadIdx.x == 0) {
-    TRACE(0);
-    for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
-      ptx::mbar_init(pfull_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 2 * EPI_WARPS);
-    }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc2(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish2();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::cluster_sync_all();
-  ptx::tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (threadIdx.x == 0) TRACE(1);
-  const int cid = (int)ptx::cluster_id_x();
-  const int ncl = (int)ptx::cluster_count_x();
-  auto phase_of = [&](int item) {
-    int k = 0;
-    while (k + 1 < p.n_phases && item >= p.ph[k + 1].item_begin) ++k;
-    return k;
-  };
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      const uint32_t a_copy = p.nsplit == 1 ? (uint32_t)TC_A_IMG : 2u * TC_A_IMG;
-      const uint32_t nparts = p.nsplit == 1 ? 1u : 2u;
-      int s = 0;
-      uint32_t phs = 0;
-      int pm = 0;
-      for (int item = cid; item < p.total_items; item += ncl) {
-        const FusedPhase& f = p.ph[phase_of(item)];
-        if (f.type == PH_PACKX) continue;
-        if (pm < 3) TRACE(2 + pm * 8 + 0);
-        const int j = item - f.item_begin;
-        const int rg = j / f.n_tiles, nt = j % f.n_tiles;
-        int rt = rg * CM + (int)rank;
-        if (rt >= p.row_tiles) rt = p.row_tiles - 1;
-        const int KB = f.kb0 + f.kb1;
-        const uint32_t b_half = (uint32_t)f.n_tile * 64u, b_part = (uint32_t)f.n_tile * 128u;
-        bool dep_ok = f.wait_flags == nullptr;
-        for (int i = 0; i < KB; ++i) {
-          // recurrent (a1 / h) k-blocks first: they never depend on the previous phase of this step
-          const int kb = i < f.kb1 ? f.kb0 + i : i - f.kb1;
-          if (kb < f.kb0 && !dep_ok) {
-            int target = f.wait_target;   // < 0: x-pack units of this row group (1 or 2 row tiles x kbx k-blocks)
-            if (target < 0) target = p.ph[0].kbx * (p.row_tiles - rg * CM >= CM ? CM : p.row_tiles - rg * CM);
-            const long long t0 = clock64();
-            while (ld_acquire(f.wait_flags + rg) < target) {
-              if (clock64() - t0 > 4000000000LL) {
-                printf("dvg_b200: dependency wait timed out (item %d)\n", item);
-                __trap();
-              }
-            }
-            ptx::fence_proxy_async_all();   // generic-proxy writes of the producer pairs -> visible to our TMA reads
-            dep_ok = true;
-            if (pm <= 3) TRACE(2 + (pm - 1) * 8 + 1);
-          }
-          ptx::mbar_wait(empty_bar(s), phs ^ 1u);
-          const uint8_t* asrc = kb < f.kb0 ? f.a0 + (size_t)(rt * f.kb0 + kb) * (2u * TC_A_IMG)
-                                           : f.a1 + (size_t)(rt * f.kb1 + (kb - f.kb0)) * (2u * TC_A_IMG);
-          const uint8_t* bsrc = f.w + (size_t)(nt * KB + kb) * (2u * b_part) + rank * b_half;
-          const uint32_t sa = base + (uint32_t)s * stage_bytes;
-          const uint32_t sb = sa + 2u * TC_A_IMG;
-          ptx::mbar_expect_tx(full_bar(s), a_copy + nparts * b_half);
-          ptx::bulk_g2s(sa, asrc, a_copy, full_bar(s));
-          ptx::bulk_g2s(sb, bsrc, b_half, full_bar(s));
-          if (nparts == 2) ptx::bulk_g2s(sb + b_half, bsrc + b_part, b_half, full_bar(s));
-          if (++s == p.stages) { s = 0; phs ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t phs = 0;
-      int mit = 0;
-      for (int item = cid; item < p.total_items; item += ncl) {
-        const FusedPhase& f = p.ph[phase_of(item)];
-        if (f.type == PH_PACKX) continue;
-        const int KB = f.kb0 + f.kb1;
-        if (rank == 0) {
-          // ===================== MMA issuer (leader CTA) =====================
-          const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, f.n_tile);
-          const uint32_t b_half = (uint32_t)f.n_tile * 64u;
-          const int acc = mit & 1;
-          const uint32_t aph = (uint32_t)(mit >> 1) & 1u;
-          ptx::mbar_wait(tempty_bar(acc), aph ^ 1u);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(full_bar(s), phs);
-            ptx::mbar_wait(pfull_bar(s), phs);
-            if (mit < 3 && kb == 0) TRACE(2 + mit * 8 + 2);
-            ptx::tc_fence_after();
-            const uint32_t sa = base + (uint32_t)s * stage_bytes;
-            const uint64_t a_hi = ptx::make_sw128_desc(sa);
-            const uint64_t a_lo = ptx::make_sw128_desc(sa + TC_A_IMG);
-            const uint64_t b_hi = ptx::make_sw128_desc(sa + 2u * TC_A_IMG);
-            const uint64_t b_lo = ptx::make_sw128_desc(sa + 2u * TC_A_IMG + b_half);
-#pragma unroll
-            for (int k = 0; k < TC_KBLK / 16; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);
-              ptx::umma2_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-              if (p.nsplit != 1) {
-                ptx::umma2_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                ptx::umma2_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-              }
-            }
-            ptx::umma2_commit_mcast(empty_bar(s), 3);
-            if (++s == p.stages) { s = 0; phs ^= 1u; }
-          }
-          ptx::umma2_commit_mcast(tfull_bar(acc), 3);
-          if (mit < 3) TRACE(2 + mit * 8 + 3);
-        } else {
-          // ===================== relay (peer CTA): "my stage landed" -> leader's pfull =====================
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(full_bar(s), phs);
-            ptx::mbar_arrive_remote(pfull_bar(s), 0);
-            if (++s == p.stages) { s = 0; phs ^= 1u; }
-          }
-        }
-        ++mit;
-      }
-    }
-  } else {
-    // ===================== epilogue / SIMT worker warps (2 .. 2+EPI_WARPS-1) =====================
-    const int ew = warp - 2;
-    const int q = warp & 3;
-    const int half = ew >> 2;
-    const uint32_t r_in_tile = (uint32_t)(q * 32 + lane);
-    const uint32_t tlane = (uint32_t)(q * 32) << 16;
-    const int etid = ew * 32 + lane;
-    // ---- x-pack prologue: x [rows, G] fp32 -> bf16 hi/lo operand images.  (row tile, k-block) units are spread
-    //      over ALL CTAs; all 32 loads of a thread are issued before the first use (DRAM-latency bound otherwise).
-    {
-      const FusedPhase& f = p.ph[0];
-      const int units = p.row_tiles * f.kbx;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int prt = u / f.kbx, kb = u % f.kbx;
-        uint8_t* img = f.xp + (size_t)(prt * f.kbx + kb) * (2u * TC_A_IMG);
-        float v[4][8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int qd = etid + i * 256;
-          const int r = qd >> 3, chunk = qd & 7;
-          const int row = prt * TC_ROWS + r;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int kk = kb * 64 + chunk * 8 + e;
-            v[i][e] = (row < p.rows && kk < f.G) ? __ldg(f.x + (size_t)row * f.ldx + kk) : 0.f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int qd = etid + i * 256;
-          const int r = qd >> 3, chunk = qd & 7;
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[i][2 * e], h0, l0);
-            split_bf16(v[i][2 * e + 1], h1, l1);
-            hi[e] = pack2_bf16(h0, h1);
-            lo[e] = pack2_bf16(l0, l1);
-          }
-          const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)chunk);
-          *reinterpret_cast<uint4*>(img + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(img + TC_A_IMG + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        __threadfence();
-        ptx::named_bar_sync(1, EPI_WARPS * 32);
-        if (etid == 0) atomicAdd(f.done_flags + (prt >> 1), 1);
-      }
-    }
-    // ---- GP variance trigger (generate_frames.py:227-232,275,283-289) on the otherwise idle epilogue warps:
-    //      CTA c < D evaluates latent dim c for every rollout (two threads per task, factors staged in the
-    //      transpose-buffer region); the last of those CTAs finalises all rollouts and publishes the mask.
-    if (p.trig.enabled && (int)blockIdx.x < p.trig.D) {
-      const TrigArgs& g = p.trig;
-      const int d = blockIdx.x, MP = g.mp;
-      float* s_linv = reinterpret_cast<float*>(s_ebuf);
-      float* s_lqt = s_linv + MP * MP;
-      float* s_z = s_lqt + MP * MP;
-      int* s_flag = reinterpret_cast<int*>(smem_raw + (bar_base - raw) + 120);
-      {
-        const float4* g1 = reinterpret_cast<const float4*>(g.linv + (size_t)d * MP * MP);
-        const float4* g2 = reinterpret_cast<const float4*>(g.lqt + (size_t)d * MP * MP);
-        for (int e = etid; e < MP * MP / 4; e += 256) {
-          reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
-          reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
-        }
-        for (int e = etid; e < MP; e += 256) s_z[e] = g.z[(size_t)d * MP + e];
-      }
-      ptx::named_bar_sync(1, EPI_WARPS * 32);
-      const float ell = g.hyp[d * 4 + 0], sc = g.hyp[d * 4 + 1], noise = g.hyp[d * 4 + 3];
-      const int hf = etid >> 7, li = etid & 127;
-      for (int base_s = 0; base_s < g.S; base_s += 128) {
-        const int i = base_s + li;
-        float part = 0.f;
-        if (i < g.S) {
-          const float xv = __ldg(g.x + (size_t)g.stat_rows[i] * g.ldx + d);
-          const float* mat = hf == 0 ? s_linv : s_lqt;
-          part = MP == 40 ? gp_trig_partial<40>(xv, sc, 1.0f / ell, MP, mat, s_z, hf != 0)
-                          : gp_trig_partial<0>(xv, sc, 1.0f / ell, MP, mat, s_z, hf != 0);
-        }
-        if (hf == 1) s_bias[li] = part;
-        ptx::named_bar_sync(1, EPI_WARPS * 32);
-        if (hf == 0 && i < g.S) g.var_rows[(size_t)d * g.S + i] = (sc - part) + s_bias[li] + noise;
-        ptx::named_bar_sync(1, EPI_WARPS * 32);
-      }
-      if (etid == 0) TRACE(26);
-      __threadfence();
-      ptx::named_bar_sync(1, EPI_WARPS * 32);
-      if (etid == 0) *s_flag = atomicAdd(g.ticket, 1u) == (unsigned)g.D - 1u ? 1 : 0;
-      ptx::named_bar_sync(1, EPI_WARPS * 32);
-      if (*s_flag) {
-        __threadfence();
-        if (etid == 0) *g.trig_count = 0;
-        const int cnt = g.count[0];
-        ptx::named_bar_sync(1, EPI_WARPS * 32);
-        for (int sidx = etid; sidx < g.S; sidx += 256)
-          gp_trig_finalize_rollout(sidx, g.S, g.D, g.var_rows, g.window, g.W, cnt, g.warmup, g.factor, g.value, g.thr,
-                                   g.mask, g.trig_list, g.trig_count);
-        __threadfence();
-        ptx::named_bar_sync(1, EPI_WARPS * 32);
-        if (etid == 0) {
-          *g.ticket = 0;
-          if (g.warmup && cnt < g.W) g.count[0] = cnt + 1;
-          __threadfence();
-          atomicExch(g.mask_ready, 1);
-        }
-      }
-      ptx::named_bar_sync(1, EPI_WARPS * 32);    // the transpose buffers are reused by the tile epilogues
-    }
-    int mit = 0;
-    for (int item = cid; item < p.total_items; item += ncl) {
-      const FusedPhase& f = p.ph[phase_of(item)];
-      const int j = item - f.item_begin;
-      const int rg = j / f.n_tiles, nt = j % f.n_tiles;
-      const int rt = rg * CM + (int)rank;
-      if (f.type == PH_PACKX) {
-        // (done in the prologue below by all CTAs; the phase only exists to carry the flags)
-      } else {
-        const int acc = mit & 1;
-        const uint32_t aph = (uint32_t)(mit >> 1) & 1u;
-        const int tm = mit;
-        ++mit;
-        const int row = rt * TC_ROWS + (int)r_in_tile;
-        const bool valid = row < p.rows;
-        float* sb = s_bias + acc * 256;
-        if (etid < f.n_tile) {
-          float bv = __ldg(f.bias + (size_t)nt * f.n_tile + etid);
-          if (f.type == PH_LSTM) bv *= (etid >> 6) == 2 ? -2.f * kLog2e : -kLog2e;
-          else if (f.type == PH_TANH) bv *= -2.f * kLog2e;
-          sb[etid] = bv;
-        }
-        // LSTM items: all fp32 state I/O goes through a warp-private 32 x 128 B transpose buffer so that every
-        // global access is a full 128-byte line per 8 lanes (thread-per-row accesses cost one L1TEX pass per
-        // line per instruction and made the epilogue the critical path).
-        uint8_t* eb = s_ebuf + ew * 4096;
-        const int er = lane >> 3, ec = lane & 7;           // coalesced mapping: 4 rows x 8 chunks per instruction
-        const int row_w0 = rt * TC_ROWS + q * 32;          // first row of this warp
-        bool held = false;
-        size_t idx0 = 0;
-        float4 cin[8];
-        if (f.type == PH_LSTM) {
-          idx0 = (size_t)row * p.H + nt * 64 + half * 32;
-          if (p.trig.enabled && p.hold != nullptr) {
-            while (ld_acquire(p.trig.mask_ready) == 0) {
-            }
-            if (etid == 0 && tm == 0) TRACE(27);
-          }
-          held = valid && p.hold != nullptr && p.hold[row / p.rows_per_flag] != 0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + er;
-            cin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_w0 + rr < p.rows)
-              cin[i] = __ldg(reinterpret_cast<const float4*>(f.c_in + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32) + ec);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + er;
-            *reinterpret_cast<float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4)) = cin[i];
-          }
-          __syncwarp();
-        }
-        ptx::named_bar_sync(1, EPI_WARPS * 32);
-        ptx::mbar_wait(tfull_bar(acc), aph);
-        if (etid == 0 && tm < 3) TRACE(2 + tm * 8 + 4);
-        ptx::tc_fence_after();
-        const uint32_t tacc = tmem_base + tlane + (uint32_t)(acc * ACC_STRIDE);
-        if (f.type == PH_LSTM) {
-          uint8_t* img = f.hp_out + (size_t)(rt * (p.H / 64) + nt) * (2u * TC_A_IMG);
-          float hn[32];
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int cb = half * 32 + jj * 16;
-            uint32_t r[64];
-            ptx::tmem_ld16x4_wait(tacc + cb, tacc + 64 + cb, tacc + 128 + cb, tacc + 192 + cb, r);
-            float cp[16], cn[16], hc[16];
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 t = *reinterpret_cast<const float4*>(eb + lane * 128 + (((jj * 4 + c4) ^ (lane & 7)) << 4));
-              cp[c4 * 4 + 0] = t.x; cp[c4 * 4 + 1] = t.y; cp[c4 * 4 + 2] = t.z; cp[c4 * 4 + 3] = t.w;
-            }
-            if (held) {
-              load16(f.h_in + idx0 + jj * 16, hc);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) cn[i] = cp[i];
-            } else {
-              lstm_pointwise16(r, sb, cb, cp, hc, cn);
-            }
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)   // c' replaces c in place (same thread, same addresses)
-              *reinterpret_cast<float4*>(eb + lane * 128 + (((jj * 4 + c4) ^ (lane & 7)) << 4)) =
-                  make_float4(cn[c4 * 4], cn[c4 * 4 + 1], cn[c4 * 4 + 2], cn[c4 * 4 + 3]);
-            if (valid) store_split16(img, r_in_tile, (uint32_t)(cb >> 3), hc);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) hn[jj * 16 + i] = hc[i];
-          }
-          if (etid == 0 && tm == 0) TRACE(28);
-          // The accumulator is drained and this CTA's slice of the packed h' image is written: release the TMEM
-          // buffer and publish the dependency NOW -- consumers (next layer / head) only read the packed images,
-          // so the fp32 state stores below are off the critical path.
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
-            else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
-          }
-          if (f.done_flags != nullptr) {
-            __threadfence();
-            ptx::named_bar_sync(1, EPI_WARPS * 32);
-            if (etid == 0) atomicAdd(f.done_flags + rg, 1);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {      // c' tile -> global, 128-byte lines
-            const int rr = i * 4 + er;
-            const float4 t = *reinterpret_cast<const float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4));
-            if (row_w0 + rr < p.rows)
-              reinterpret_cast<float4*>(f.c_out + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32)[ec] = t;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            *reinterpret_cast<float4*>(eb + lane * 128 + ((c8 ^ (lane & 7)) << 4)) =
-                make_float4(hn[c8 * 4], hn[c8 * 4 + 1], hn[c8 * 4 + 2], hn[c8 * 4 + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {      // h' tile -> global
-            const int rr = i * 4 + er;
-            const float4 t = *reinterpret_cast<const float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4));
-            if (row_w0 + rr < p.rows)
-              reinterpret_cast<float4*>(f.h_out + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32)[ec] = t;
-          }
-          __syncwarp();
-          if (etid == 0 && tm == 0) TRACE(29);
-        } else if (f.type == PH_TANH) {
-          // y = tanh(acc + b): this warp owns rows q*32.. and columns half*n_tile/2 ..; groups of <= 32 columns go
-          // through the transpose buffer so the [rows, G] output is written in full row segments.
-          const int ncol_half = f.n_tile / 2;
-          const int c_begin = half * ncol_half;
-          const bool vec2 = (f.ldy & 1) == 0 && (f.n_valid & 1) == 0;
-          for (int g0 = 0; g0 < ncol_half; g0 += 32) {
-            const int gw = ncol_half - g0 < 32 ? ncol_half - g0 : 32;   // 32 or 16
-            for (int c16 = 0; c16 < gw; c16 += 16) {
-              float v[16];
-              ptx::tmem_ld16_wait(tacc + c_begin + g0 + c16, v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = tanh_fast_prescaled(v[i], sb[c_begin + g0 + c16 + i]);
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4)
-                *reinterpret_cast<float4*>(eb + lane * 128 + ((((c16 >> 2) + c4) ^ (lane & 7)) << 4)) =
-                    make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-            }
-            __syncwarp();
-            const int lpr = gw >> 1;              // lanes per row (one float2 each)
-            const int rpi = 32 / lpr;             // rows per instruction
-            for (int i = 0; i < 32 / rpi; ++i) {
-              const int rr = i * rpi + lane / lpr;
-              const int cc = (lane % lpr) * 2;
-              const float2 t = *reinterpret_cast<const float2*>(eb + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4);
-              const int col = c_begin + g0 + cc;
-              const int grow = row_w0 + rr;
-              if (grow < p.rows && col < f.n_valid) {
-                float* dst = f.y + (size_t)grow * f.ldy + col;
-                if (vec2) *reinterpret_cast<float2*>(dst) = t;
-                else { dst[0] = t.x; if (col + 1 < f.n_valid) dst[1] = t.y; }
-              }
-            }
-            __syncwarp();
-          }
-        } else {
-          const int nchunks = f.n_tile / 16;
-#pragma unroll 1
-          for (int jc = half; jc < nchunks; jc += 2) {
-            float v[16];
-            ptx::tmem_ld16_wait(tacc + jc * 16, v);
-            if (valid) {
-              const int col0 = nt * f.n_tile + jc * 16;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += sb[jc * 16 + i];
-#pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                const int zi = (col0 + i) >> 1;
-                if (zi < f.Z) {
-                  const size_t idx = (size_t)row * f.Z + zi;
-                  f.mu[idx] = v[i];
-                  f.logvar[idx] = v[i + 1];
-                  f.z[idx] = fmaf(f.eps[idx], expf(0.5f * v[i + 1]), v[i]);
-                }
-              }
-            }
-          }
-        }
-        if (f.type != PH_LSTM) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
-            else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
-          }
-        }
-        if (etid == 0 && tm < 3) {
-          TRACE(2 + tm * 8 + 5);
-#ifdef DVG_TRACE
-          if (p.trace) p.trace[(size_t)blockIdx.x * 32 + 2 + tm * 8 + 6] = 1000000ull + item;
-#endif
-        }
-      }
-      // publish: everything this CTA wrote for the item is visible before the counter moves
-      if (f.done_flags != nullptr && f.type != PH_PACKX && f.type != PH_LSTM) {
-        __threadfence();
-        ptx::named_bar_sync(1, EPI_WARPS * 32);
-        if (etid == 0) atomicAdd(f.done_flags + rg, 1);
-      }
-    }
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) TRACE(30);
-  ptx::cluster_sync_all();
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc2(tmem_base, TMEM_COLS);
-  }
-  // Self-resetting dependency counters: the last CTA to get here (every CTA has finished reading them) zeroes
-  // them for the next launch -- no cudaMemset node per step.
-  if (threadIdx.x == 0) {
-    int* exit_ctr = p.flag_words + p.n_flag_words;
-    __threadfence();
-    if (atomicAdd(exit_ctr, 1) == (int)gridDim.x - 1) {
-      for (int i = 0; i < p.n_flag_words; ++i) p.flag_words[i] = 0;
-      __threadfence();
-      *exit_ctr = 0;
-    }
-  }
-}
-
 // W_x = W_ih0 W_e  ([4H, G]),  b_x = W_ih0 b_e + b_ih0 + b_hh0  -- the embed Linear folded into layer 0 (fp64 accumulate).
 __global__ void fold_embed_kernel(const float* __restrict__ w_ih0, const float* __restrict__ embed_w,
                                   const float* __restrict__ embed_b, const float* __restrict__ b_ih0,
@@ -1376,8 +748,10 @@ void lstm_tc_free(dvg_lstm_s* h) {
   if (h->fold_wx) cudaFree(h->fold_wx);
   if (h->fold_bx) cudaFree(h->fold_bx);
   if (h->fused_flags) cudaFree(h->fused_flags);
+  if (h->sched_dev) cudaFree(h->sched_dev);
   h->fold_wx = h->fold_bx = nullptr;
   h->fused_flags = nullptr;
+  h->sched_dev = nullptr;
   for (int l = 0; l < MAX_LAYERS; ++l) fr(h->tc_layer[l]);
 }
 
@@ -1492,157 +866,6 @@ static int launch_tc(const dvg_lstm_s* h, TcArgs& a, cudaStream_t stream) {
 }
 
 
-static bool use_fused() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DVG_TC_FUSED");     // developer switch: 0 = one launch per GEMM
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
-}
-
-static int lstm_tc_step_fused(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in,
-                              const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
-                              float* y, int ldy, const float* eps, float* z, float* mu, float* logvar,
-                              const uint8_t* hold, int rows_per_flag, cudaStream_t stream,
-                              const TrigArgs* trig = nullptr) {
-  const int G = h->dims.input_size, H = h->dims.hidden_size, L = h->dims.n_layers;
-  const int hk = H / 64, RT = ceil_div(rows, TC_ROWS), kbx = ceil_div(G, 64);
-  const int groups = ceil_div(RT, 2);
-  const size_t lsz = (size_t)rows * H;
-  const size_t lpk = (size_t)RT * hk * 2 * TC_A_IMG;
-  FusedArgs a{};
-  a.rows = rows; a.row_tiles = RT; a.groups = groups; a.nsplit = nsplit; a.H = H;
-  a.hold = hold; a.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
-  int* flags = h->fused_flags;
-  // dependency counters + (last word) the trigger's mask_ready flag + exit counter: zeroed at allocation and reset
-  // by the kernel itself at exit
-  a.flag_words = flags;
-  a.n_flag_words = (L + 1) * h->fused_flag_stride + 1;
-  if (trig != nullptr) {
-    a.trig = *trig;
-    a.trig.enabled = 1;
-    a.trig.mask_ready = flags + (size_t)(L + 1) * h->fused_flag_stride;
-  }
-  int np = 0, item = 0;
-  {  // PACKX
-    FusedPhase& f = a.ph[np];
-    f.type = PH_PACKX; f.n_tile = 0; f.n_tiles = 1; f.item_begin = item;
-    f.x = x; f.ldx = ldx; f.G = G; f.xp = h->tc_xp; f.kbx = kbx;
-    f.done_flags = flags;
-    ++np;   // no items: the x-pack runs as a prologue spread over all CTAs
-  }
-  for (int l = 0; l < L; ++l) {
-    FusedPhase& f = a.ph[np];
-    const TcGemmPlan& pl = l == 0 ? h->tc_layer0f : h->tc_layer[l];
-    f.type = PH_LSTM; f.n_tile = 256; f.n_tiles = hk; f.item_begin = item;
-    f.a0 = l == 0 ? h->tc_xp : hp_out + (l - 1) * lpk; f.kb0 = l == 0 ? kbx : hk;
-    f.a1 = hp_in + l * lpk; f.kb1 = hk;
-    f.w = pl.w; f.bias = pl.bias;
-    f.wait_flags = flags + (size_t)l * h->fused_flag_stride; f.wait_target = l == 0 ? -1 : 2 * hk;   // l == 0: per-group target set below
-    f.done_flags = flags + (size_t)(l + 1) * h->fused_flag_stride;
-    f.c_in = c_in + l * lsz; f.h_in = h_in + l * lsz; f.h_out = h_out + l * lsz; f.c_out = c_out + l * lsz;
-    f.hp_out = hp_out + l * lpk;
-    item += groups * hk; ++np;
-  }
-  {  // head
-    FusedPhase& f = a.ph[np];
-    const bool gauss = h->dims.kind == DVG_GAUSSIAN_LSTM;
-    f.type = gauss ? PH_GAUSS : PH_TANH; f.n_tile = h->tc_head.n_tile; f.n_tiles = 1; f.item_begin = item;
-    f.a0 = hp_out + (L - 1) * lpk; f.kb0 = hk; f.a1 = nullptr; f.kb1 = 0;
-    f.w = h->tc_head.w; f.bias = h->tc_head.bias;
-    f.wait_flags = flags + (size_t)L * h->fused_flag_stride; f.wait_target = 2 * hk;
-    f.done_flags = nullptr;
-    f.y = y; f.ldy = ldy; f.n_valid = h->dims.output_size;
-    f.eps = eps; f.z = z; f.mu = mu; f.logvar = logvar; f.Z = h->dims.output_size;
-    item += groups; ++np;
-  }
-  a.n_phases = np; a.total_items = item;
-  const size_t stage_bytes = 2 * (size_t)TC_A_IMG + 2 * (size_t)256 * 64;
-  const size_t tail = 128 + 2 * 256 * sizeof(float) + (size_t)EPI_WARPS * 4096;   // barriers, bias, transpose buffers
-  int stages = (int)((227 * 1024 - tail) / stage_bytes);
-  if (stages > 4) stages = 4;
-  a.stages = stages; a.stage_bytes = (uint32_t)stage_bytes;
-  const size_t smem = stages * stage_bytes + tail;
-  static bool configured = false;
-  if (!configured) {
-    DVG_CUDA(cudaFuncSetAttribute(lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
-  int pairs = h->sm_count / 2;
-  if (pairs > a.total_items) pairs = a.total_items;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(pairs * 2);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-#ifdef DVG_TRACE
-  static unsigned long long* tbuf = nullptr;
-  const bool tr = getenv("DVG_TC_TRACE") != nullptr;
-  if (tr) {
-    if (!tbuf) cudaMalloc(&tbuf, 256 * 32 * 8);
-    cudaMemsetAsync(tbuf, 0, 256 * 32 * 8, stream);
-    a.trace = tbuf;
-  }
-#endif
-  h->prof_mark(stream);
-  DVG_CUDA(cudaLaunchKernelEx(&cfg, lstm_fused_kernel, (const FusedArgs)a));
-  h->prof_mark(stream);
-#ifdef DVG_TRACE
-  if (tr) {
-    static int n_dump = 0;
-    cudaStreamSynchronize(stream);
-    if (n_dump++ == 4) {
-      std::vector<unsigned long long> hbuf(256 * 32);
-      cudaMemcpy(hbuf.data(), tbuf, 256 * 32 * 8, cudaMemcpyDeviceToHost);
-      unsigned long long t0 = ~0ull;
-      for (int b = 0; b < (int)cfg.gridDim.x; ++b) if (hbuf[b * 32] && hbuf[b * 32] < t0) t0 = hbuf[b * 32];
-      fprintf(stderr, "FUSED TRACE grid=%d items=%d stages=%d: start setup | per MMA item: depwait depok stage0 mma_issued acc_ready epi_done item | end\n",
-              (int)cfg.gridDim.x, a.total_items, stages);
-      for (int b = 0; b < (int)cfg.gridDim.x; b += (b < 4 ? 1 : (b < 60 ? 6 : 8))) {
-        fprintf(stderr, "cta %3d:", b);
-        for (int i = 0; i < 31; ++i) {
-          unsigned long long v = hbuf[b * 32 + i];
-          if (i == 2 || i == 10 || i == 18 || i == 26) fprintf(stderr, " |");
-          if (v >= 1000000ull && v < 2000000ull) fprintf(stderr, " #%lld", (long long)(v - 1000000ull));
-          else fprintf(stderr, " %lld", v ? (long long)(v - t0) : -1ll);
-        }
-        fprintf(stderr, "\n");
-      }
-    }
-  }
-#endif
-  return DVG_OK;
-}
-
-bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows) {
-  const int RT = ceil_div(rows, TC_ROWS);
-  const size_t need = sizeof(float) * ((size_t)2 * g->mp * g->mp + g->mp);
-  int pairs = h->sm_count / 2;
-  return h->tc_ok && use_fused() && use_pairs() && RT >= 2 && need <= (size_t)EPI_WARPS * 4096 &&
-         g->dims.num_dims <= pairs * 2;
-}
-
-// trigger + LSTM step in one launch (see TrigArgs); caller guarantees lstm_tc_can_fuse_trigger().
-int lstm_tc_rollout_step(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
-                         const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
-                         float* y, int ldy, int S, const int32_t* stat_rows, float* window, int W, int32_t* count,
-                         int warmup, float factor, float* value, float* thr, uint8_t* mask, cudaStream_t stream) {
-  TrigArgs t{};
-  t.S = S; t.D = g->dims.num_dims; t.mp = g->mp; t.ldx = ldx; t.W = W; t.warmup = warmup; t.factor = factor;
-  t.x = x; t.stat_rows = stat_rows; t.z = g->z; t.linv = g->linv; t.lqt = g->lqt; t.hyp = g->hyp;
-  t.var_rows = g->var_rows; t.ticket = g->ticket; t.window = window; t.count = count;
-  t.value = value; t.thr = thr; t.mask = mask; t.trig_list = g->trig_list; t.trig_count = g->trig_count;
-  g->last_mask = mask;
-  g->last_mask_rollouts = S;
-  return lstm_tc_step_fused(h, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, nullptr, nullptr,
-                            nullptr, nullptr, warmup ? nullptr : mask, rows / S, stream, &t);
-}
-
 int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in,
                  const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out, float* y,
                  int ldy, const float* eps, float* z, float* mu, float* logvar, const uint8_t* hold,
@@ -1652,9 +875,9 @@ int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, c
   const size_t lsz = (size_t)rows * H;
   const size_t lpk = (size_t)RT * hk * 2 * TC_A_IMG;
   int rc;
-  if (use_fused() && use_pairs() && RT >= 2)
-    return lstm_tc_step_fused(h, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, eps, z, mu,
-                              logvar, hold, rows_per_flag, stream);
+  if (lstm_step_usable(h, rows))
+    return lstm_step_launch(h, nullptr, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, eps, z,
+                            mu, logvar, hold, rows_per_flag, stream, nullptr);
   h->prof_mark(stream);
   tc_pack_rows_kernel<<<dim3(RT, kbx), 256, 0, stream>>>(h->tc_xp, x, ldx, rows, G, kbx);
   DVG_LAUNCH_CHECK();
