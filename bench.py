@@ -124,9 +124,9 @@ def synth_latents(w, T, R, device, seed):
 
 
 def launches_per_rollout(w, T):
-    # per time step: ONE persistent kernel (GP trigger + whole LSTM step; a cudaMemset node for its counters is
-    # not counted) + the list-driven rsample kernel on decision steps; + one scoring kernel per rollout
-    return sum(1 + (0 if t < w["window"] else 1) for t in range(T)) + 1
+    # per time step ONE persistent kernel (GP trigger + whole LSTM step + restore/resample of fired rollouts), plus one
+    # scoring kernel per rollout
+    return T + 1
 
 
 def flops_bytes(w, R):
@@ -274,75 +274,73 @@ def run_ours(args):
 
 
 def measure_roofline(eng, w, R, lat, args):
-    """Per-kernel device times of one LSTM step, CUDA events recorded between the launches on the
-    launching stream (dvg_lstm_profile), averaged over the bench's K steps x T time steps."""
+    """Device time of the dominant kernel, ``lstm_step_kernel`` (one launch = one whole LSTM time step of all R rows
+    with the GP trigger fused, exactly the launch the timed rollout issues): a CUDA graph holding ONLY the T step
+    launches of one rollout (no rsample, no scoring) is replayed and timed with CUDA events on the launching stream;
+    average launch duration = replay time / T (it includes the ~1 us launch gaps between dependent kernels, not host
+    launch overhead).  The other variants are timed the same way."""
     from dvg_b200 import _capi
+    from dvg_b200.rollout import RolloutConfig, RolloutEngine
     pk, how = peaks()
-    lib = eng.lib
-    if not hasattr(lib, "dvg_lstm_profile"):
-        return None
-    import ctypes
-    n_slots = 3 + w["L"]
-    acc = [0.0] * n_slots
-    reps = 0
-    out = torch.empty(R, w["G"], device=lat.device)
-    ms = (ctypes.c_float * 16)()
     T = lat.shape[0]
-    for it in range(max(1, min(args.steps, 5))):
-        for t in range(T):
-            nxt = 1 - eng.cur
-            rc = lib.dvg_lstm_profile(eng.lrt.handle, eng.variant, R, _capi.ptr(lat[t]), w["G"],
-                                      _capi.ptr(eng.blocks[eng.cur]), _capi.ptr(eng.blocks[nxt]), _capi.ptr(out), w["G"],
-                                      ms, 16, _capi.stream_ptr())
-            _capi.check(rc, "dvg_lstm_profile")
-            eng.cur = nxt
-            for i in range(n_slots):
-                acc[i] += ms[i]
-            reps += 1
-    per = [a / reps for a in acc]
+    out = torch.empty(R, w["G"], device=lat.device)
+
+    def step_time(engine, reps):
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            engine.reset()
+            for t in range(2):
+                engine.step_trigger_mode(lat[t], None, out, warmup=t < 1, resample=False)
+            engine.reset()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            engine.reset()
+            for t in range(T):
+                engine.step_trigger_mode(lat[t], None, out, warmup=t < w["window"], resample=False)
+        engine.cur = 0 if T % 2 == 0 else 1
+        for _ in range(3):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (reps * T)
+
+    reps = max(3, min(args.steps, 20))
+    step_ms = step_time(eng, reps)
     other = {}
-    for name, vid in (("bf16", _capi.DVG_BF16), ("fp32", _capi.DVG_FP32)):
-        if vid == eng.variant:
+    for name in ("bf16x3", "bf16", "fp32"):
+        if name == args.variant:
             continue
-        tot, n = 0.0, 0
-        for t in range(min(T, 6)):
-            nxt = 1 - eng.cur
-            _capi.check(lib.dvg_lstm_profile(eng.lrt.handle, vid, R, _capi.ptr(lat[t]), w["G"],
-                                             _capi.ptr(eng.blocks[eng.cur]), _capi.ptr(eng.blocks[nxt]), _capi.ptr(out),
-                                             w["G"], ms, 16, _capi.stream_ptr()), "dvg_lstm_profile")
-            eng.cur = nxt
-            if t >= 2:
-                tot += sum(ms[i] for i in range(n_slots)); n += 1
-        other[name] = tot / max(n, 1)
+        fp2, gp2, lik2 = build_models(w, lat.device, name)
+        e2 = RolloutEngine(fp2, gp2, lik2, RolloutConfig(n_points=w["B"], n_rollouts=w["S"], window=w["window"], variant=name))
+        other[name] = step_time(e2, 3)
+        del e2, fp2, gp2, lik2
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     issued = 3 if args.variant == "bf16x3" else 1
-    f_row, b_row, f_layer = flops_bytes(w, R)
-    fused = sum(per[1:]) == 0.0          # one persistent launch for the whole step: only slot 0 is populated
-    if fused:
-        step_ms = per[0]
-        achieved = f_row * R / (step_ms * 1e-3) / 1e12
-        kernel = "lstm_fused_kernel (whole LSTM step: x-pack, %d layers with embed folded, head; %d rows)" % (w["L"], R)
-        kernel_ms = {"lstm_fused_kernel": step_ms}
-        flops_note = "ALGORITHMIC flops of the reference step, 2*(G*H + L*2H*4H + H*G) per row"
-    else:
-        step_ms = sum(per)
-        layer_ms = sum(per[2:2 + w["L"]]) / w["L"]
-        achieved = f_layer / (layer_ms * 1e-3) / 1e12
-        kernel = "tc_gemm_kernel<EPI_LSTM> (one LSTM layer, %d rows)" % R
-        kernel_ms = {"pack_x": per[0], "embed": per[1], "layers": per[2:2 + w["L"]], "head": per[2 + w["L"]]}
-        flops_note = "ALGORITHMIC flops 2*R*2H*4H per launch"
+    f_row, b_row, _ = flops_bytes(w, R)
+    achieved = f_row * R / (step_ms * 1e-3) / 1e12
     hbm = pk["hbm_gbs"]
-    return {"bound": "tensor", "kernel": kernel,
+    return {"bound": "tensor",
+            "kernel": "lstm_step_kernel (whole LSTM time step in one persistent launch: x-pack, %d layers with the embed "
+                      "folded in, head, GP trigger; %d rows)" % (w["L"], R),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % how,
             "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant)),
-            "traffic_source": "profiles/r01_lstm_fused.md (ncu --set full, dram read+write bytes per launch)",
+            "traffic_source": "profiles/r01_lstm_step.md (ncu --set full, dram read+write bytes per launch)",
             "algorithmic_bytes_per_launch": b_row * R,
             "tensor_issue_frac": achieved * issued / peak,
             "hbm_frac_of_state_io": (b_row * R / (step_ms * 1e-3) / 1e9) / hbm,
-            "note": "achieved counts " + flops_note + "; the bf16x3 variant issues 3 tcgen05.mma per algorithmic "
-                    "MMA (tensor_issue_frac = tensor-pipe work actually issued / peak)",
-            "kernel_ms": kernel_ms, "lstm_step_ms": step_ms,
+            "note": "achieved counts ALGORITHMIC flops of the reference step, 2*(G*H + L*2H*4H + H*G) per row; the bf16x3 "
+                    "variant issues 3 tcgen05.mma per algorithmic MMA (tensor_issue_frac = tensor-pipe work actually "
+                    "issued / peak); launch duration = CUDA-graph replay of the T step launches / T",
+            "kernel_ms": {"lstm_step_kernel": step_ms}, "lstm_step_ms": step_ms,
             "other_variants_lstm_step_ms": other}
 
 

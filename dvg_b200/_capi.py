@@ -87,7 +87,7 @@ def load():
     lib.dvg_gp_rsample.argtypes = [P, c_int, c_int, P, c_int, P, P, P, c_int, P]
     lib.dvg_gp_export.argtypes = [P, P, P, P, P, P]
     lib.dvg_rollout_step.argtypes = [P, P, c_int, c_int, P, c_int, P, P, P, c_int, c_int, P, P, c_int, P, c_int, c_float,
-                                     P, P, P, P]
+                                     P, P, P, P, P]
     lib.dvg_eval_seq_finn.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]
     lib.dvg_rollout_score.argtypes = [c_int, c_int, c_int, c_int, P, P, P, P]
     for name in EXPORTS:

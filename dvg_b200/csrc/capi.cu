@@ -352,13 +352,15 @@ int dvg_gp_export(dvg_gp_t h, float* linv, float* lq, float* alpha, float* hyp, 
 int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows, const float* x, int ldx, const void* state_in,
                      void* state_out, float* y, int ldy, int n_rollouts, const int32_t* stat_rows, float* window,
                      int window_len, int32_t* count, int warmup, float factor, float* value, float* thr, uint8_t* mask,
-                     dvg_stream_t stream) {
+                     const float* rs_eps, dvg_stream_t stream) {
   DVG_REQUIRE(h && g && x && state_in && state_out && y && stat_rows && window && count && mask, "null argument");
   DVG_REQUIRE(h->dims.kind == DVG_LSTM, "handle is not an lstm");
   DVG_REQUIRE(n_rollouts > 0 && rows % n_rollouts == 0, "rows must be a multiple of n_rollouts");
   DVG_REQUIRE(h->dims.input_size == g->dims.num_dims, "latent size mismatch between LSTM and GP");
+  if (rs_eps) DVG_REQUIRE(h->dims.output_size == g->dims.num_dims, "rsample into y needs output_size == GP dims");
   cudaStream_t s = (cudaStream_t)stream;
   const bool tc = variant == DVG_BF16X3 || variant == DVG_BF16;
+  const int n_points = rows / n_rollouts;
   if (tc && rows <= h->reserved_rows && n_rollouts <= g->var_rows_cap && window_len >= 1 && window_len <= 128 &&
       ldx >= h->dims.input_size && ldy >= h->dims.output_size && state_in != state_out &&
       lstm_tc_can_fuse_trigger(h, g, rows)) {
@@ -366,16 +368,21 @@ int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows, const floa
     const size_t poff = dvg_lstm_state_packed_offset(h, rows);
     const float* h_in = (const float*)state_in;
     float* h_out = (float*)state_out;
-    return lstm_tc_rollout_step(h, g, variant == DVG_BF16 ? 1 : 3, rows, x, ldx, h_in, h_in + lsz,
-                                (const uint8_t*)state_in + poff, h_out, h_out + lsz, (uint8_t*)state_out + poff, y, ldy,
-                                n_rollouts, stat_rows, window, window_len, count, warmup, factor, value, thr, mask, s);
+    const bool rs_in_kernel = rs_eps != nullptr && !warmup && lstm_tc_can_fuse_rsample(g, n_points);
+    int rc = lstm_tc_rollout_step(h, g, variant == DVG_BF16 ? 1 : 3, rows, x, ldx, h_in, h_in + lsz,
+                                  (const uint8_t*)state_in + poff, h_out, h_out + lsz, (uint8_t*)state_out + poff, y, ldy,
+                                  n_rollouts, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,
+                                  rs_in_kernel ? rs_eps : nullptr, s);
+    if (rc || rs_in_kernel || rs_eps == nullptr || warmup) return rc;
+    return dvg_gp_rsample(g, n_rollouts, n_points, x, ldx, rs_eps, mask, y, ldy, stream);
   }
-  // not fusable (fp32 variant, single row tile, large inducing set, scratch not reserved): two calls, same semantics
+  // not fusable (fp32 variant, single row tile, large inducing set, scratch not reserved): separate calls, same semantics
   int rc = dvg_gp_trigger(g, n_rollouts, x, ldx, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,
                           stream);
   if (rc) return rc;
-  return dvg_lstm_step(h, variant, rows, x, ldx, state_in, state_out, y, ldy, warmup ? nullptr : mask,
-                       rows / n_rollouts, stream);
+  rc = dvg_lstm_step(h, variant, rows, x, ldx, state_in, state_out, y, ldy, warmup ? nullptr : mask, n_points, stream);
+  if (rc || rs_eps == nullptr || warmup) return rc;
+  return dvg_gp_rsample(g, n_rollouts, n_points, x, ldx, rs_eps, mask, y, ldy, stream);
 }
 
 int dvg_eval_seq_finn(int n_frames, int n_samples, int n_seq, int channels, int height, int width, const float* gt,

@@ -1,0 +1,194 @@
+// GP posterior sample of one (rollout, latent dim) problem by 256 cooperating threads (gpytorch's .rsample():
+// generate_frames.py:171,292; train.py:284).  Shared by the stand-alone rsample kernels (gp.cu) and the persistent
+// step kernel (lstm_step.cu), which resamples fired rollouts at the end of the same launch.  `sync` is the barrier of
+// the 256 participating threads, `smf` their shared-memory scratch (gp_rsample_smem_floats() floats).
+#pragma once
+#include "common.cuh"
+
+namespace dvg {
+
+__host__ __device__ inline size_t gp_rsample_smem_floats(int N, int mp) {
+  return (size_t)2 * mp * mp + 3 * (size_t)N * (mp + 1) + (size_t)N * (N + 1) + 4 * (size_t)N + 2 * (size_t)mp;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rsample: one CTA per (rollout s, latent dim d); full [N,N] predictive covariance in shared memory,
+// Cholesky, y = mean + L eps.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+
+// One (rollout, dim) problem per call, all RS_THREADS threads of the CTA: full [N,N] predictive covariance in
+// shared memory, Cholesky, y = mean + L eps.  Every global operand (factors, z, beta, eps, x) is staged into
+// shared memory first with batched coalesced loads: the first version read beta / eps / z from global inside
+// dependent inner loops and spent ~45 of its 70 us waiting on L2.
+template <class Sync>
+__device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync sync, int s_idx, int d, int N, int D,
+                                                int mp, const float* __restrict__ x, int ldx,
+                                                const float* __restrict__ eps,
+                                                const float* __restrict__ zall, const float* __restrict__ linv_all,
+                                                const float* __restrict__ lqt_all,
+                                                const float* __restrict__ alpha_all, const float* __restrict__ hyp,
+                                                float* __restrict__ out, int ldo) {
+#ifdef DVG_TRACE
+  long long tq[8]; int nq = 0;
+#define RSQ() do { sync(); tq[nq++] = clock64(); } while (0)
+#else
+#define RSQ() do {} while (0)
+#endif
+  RSQ();
+  const int MP = mp;
+  const int ldk = MP + 1, lds = N + 1;
+  float* s_linv = smf;                 // [MP][MP]
+  float* s_lqt = s_linv + MP * MP;     // [MP][MP]
+  float* s_k = s_lqt + MP * MP;        // [N][MP+1]  K_xz
+  float* s_u = s_k + N * ldk;          // [N][MP+1]  (Linv k_n)
+  float* s_r = s_u + N * ldk;          // [N][MP+1]  (L_q^T k_n)
+  float* s_sig = s_r + N * ldk;        // [N][N+1]   Sigma_y -> L
+  float* s_x = s_sig + N * lds;        // [N]
+  float* s_mean = s_x + N;             // [N]
+  float* s_t = s_mean + N;             // [N]
+  float* s_eps = s_t + N;              // [N]
+  float* s_z = s_eps + N;              // [MP]
+  float* s_beta = s_z + MP;            // [MP]
+  {
+    const float4* g1 = reinterpret_cast<const float4*>(linv_all + (size_t)d * MP * MP);
+    const float4* g2 = reinterpret_cast<const float4*>(lqt_all + (size_t)d * MP * MP);
+    const int n4 = MP * MP / 4;
+    for (int e0 = 0; e0 < n4; e0 += RS_THREADS * 2) {       // 4 independent 16-byte loads in flight per thread
+      float4 t[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = e0 + u * RS_THREADS + tid;
+        if (e < n4) { t[u][0] = __ldg(g1 + e); t[u][1] = __ldg(g2 + e); }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = e0 + u * RS_THREADS + tid;
+        if (e < n4) {
+          reinterpret_cast<float4*>(s_linv)[e] = t[u][0];
+          reinterpret_cast<float4*>(s_lqt)[e] = t[u][1];
+        }
+      }
+    }
+    for (int e = tid; e < MP; e += RS_THREADS) {
+      s_z[e] = __ldg(zall + (size_t)d * MP + e);
+      s_beta[e] = __ldg(alpha_all + (size_t)d * MP + e);
+    }
+    for (int n = tid; n < N; n += RS_THREADS) {
+      s_x[n] = __ldg(x + (size_t)(s_idx * N + n) * ldx + d);
+      s_eps[n] = __ldg(eps + ((size_t)s_idx * D + d) * N + n);
+    }
+  }
+  const float ell = hyp[d * 4 + 0], sc = hyp[d * 4 + 1], c = hyp[d * 4 + 2], noise = hyp[d * 4 + 3];
+  const float inv_ell = 1.0f / ell;
+  sync();
+  RSQ();
+  for (int e = tid; e < N * MP; e += RS_THREADS) {
+    const int n = e / MP, m = e % MP;
+    const float t = (s_x[n] - s_z[m]) * inv_ell;
+    s_k[n * ldk + m] = sc * expf(-0.5f * t * t);
+  }
+  sync();
+  RSQ();
+  // Thread mapping for the O(N M^2) / O(N^2 M) / O(N^3) phases: the point index (n or b) is the FAST thread index
+  // (row stride ldk / lds is odd -> conflict-free), the matrix row (j or a) is shared by a whole warp (broadcast
+  // reads), and there are no runtime integer divisions.  (First version: 4-way bank conflicts + unpipelined LDS
+  // chains + idiv -> 140 k cycles per problem.)
+  const int lg = N <= 32 ? 5 : (N <= 64 ? 6 : 7);       // N <= 128 (shared-memory bound)
+  const int fi = tid & ((1 << lg) - 1);                 // point index
+  const int grp = tid >> lg, ngrp = RS_THREADS >> lg;   // which matrix rows this thread visits
+  if (fi < N) {
+    const float* kr = s_k + fi * ldk;
+    for (int j = grp; j < MP; j += ngrp) {
+      const float* lr = s_linv + j * MP;
+      const float* qr = s_lqt + j * MP;
+      float v0 = 0.f, v1 = 0.f, w0 = 0.f, w1 = 0.f;
+      const int jm = j & ~1;
+#pragma unroll 4
+      for (int m = 0; m < jm; m += 2) {                 // Linv row j: m <= j
+        v0 = fmaf(lr[m], kr[m], v0);
+        v1 = fmaf(lr[m + 1], kr[m + 1], v1);
+      }
+      for (int m = jm; m <= j; ++m) v0 = fmaf(lr[m], kr[m], v0);
+#pragma unroll 4
+      for (int m = jm; m + 1 < MP; m += 2) {            // L_q^T row j: m >= j (entries below j are zero)
+        w0 = fmaf(qr[m], kr[m], w0);
+        w1 = fmaf(qr[m + 1], kr[m + 1], w1);
+      }
+      s_u[fi * ldk + j] = v0 + v1;
+      s_r[fi * ldk + j] = w0 + w1;
+    }
+  }
+  sync();
+  RSQ();
+  for (int n = tid; n < N; n += RS_THREADS) {
+    float mu0 = 0.f, mu1 = 0.f;
+    for (int j = 0; j + 1 < MP; j += 2) {
+      mu0 = fmaf(s_beta[j], s_u[n * ldk + j], mu0);
+      mu1 = fmaf(s_beta[j + 1], s_u[n * ldk + j + 1], mu1);
+    }
+    s_mean[n] = c + (mu0 + mu1);       // MP is a multiple of 4
+  }
+  if (fi < N) {
+    const float* rb = s_r + fi * ldk;
+    const float* ub = s_u + fi * ldk;
+    for (int a = grp; a < N; a += ngrp) {
+      if (fi > a) continue;                             // lower triangle: b = fi <= a
+      const float* ra = s_r + a * ldk;
+      const float* ua = s_u + a * ldk;
+      float rr0 = 0.f, rr1 = 0.f, uu0 = 0.f, uu1 = 0.f;
+#pragma unroll 4
+      for (int m = 0; m < MP; m += 2) {
+        rr0 = fmaf(ra[m], rb[m], rr0);
+        uu0 = fmaf(ua[m], ub[m], uu0);
+        rr1 = fmaf(ra[m + 1], rb[m + 1], rr1);
+        uu1 = fmaf(ua[m + 1], ub[m + 1], uu1);
+      }
+      const float t = (s_x[a] - s_x[fi]) * inv_ell;
+      const float kxx = a == fi ? sc : sc * expf(-0.5f * t * t);
+      s_sig[a * lds + fi] = (rr0 + rr1) + (kxx - (uu0 + uu1)) + (a == fi ? noise : 0.f);
+    }
+  }
+  sync();
+  RSQ();
+  // Cholesky as LDL^T, right-looking with UNSCALED columns (one barrier per column): after step j the trailing
+  // block holds S - sum_{k<=j} c_k c_k^T / d_k with c_k the unscaled column k and d_k its diagonal;
+  // L[i][j] = c_j[i] / sqrt(d_j) is applied in one pass at the end.
+  for (int j = 0; j + 1 < N; ++j) {
+    const float inv_d = __fdividef(1.0f, s_sig[j * lds + j]);
+    const int a = j + 1 + fi;                             // this thread's ROW (consecutive threads -> stride lds, odd:
+    if (a < N) {                                          // conflict-free; columns b are warp-uniform -> broadcast)
+      const float ca = s_sig[a * lds + j] * inv_d;
+#pragma unroll 4
+      for (int b = j + 1 + grp; b <= a; b += ngrp)
+        s_sig[a * lds + b] = fmaf(-ca, s_sig[b * lds + j], s_sig[a * lds + b]);
+    }
+    sync();
+  }
+  for (int j = grp; j < N; j += ngrp) {
+    const float rs = rsqrtf(s_sig[j * lds + j]);
+    if (fi > j && fi < N) s_sig[fi * lds + j] *= rs;
+  }
+  sync();
+  for (int j = tid; j < N; j += RS_THREADS) s_sig[j * lds + j] = sqrtf(s_sig[j * lds + j]);
+  sync();
+  RSQ();
+  for (int n = tid; n < N; n += RS_THREADS) {
+    float a0 = 0.f, a1 = 0.f;
+    int k = 0;
+    for (; k + 1 <= n; k += 2) {
+      a0 = fmaf(s_sig[n * lds + k], s_eps[k], a0);
+      a1 = fmaf(s_sig[n * lds + k + 1], s_eps[k + 1], a1);
+    }
+    if (k <= n) a0 = fmaf(s_sig[n * lds + k], s_eps[k], a0);
+    out[(size_t)(s_idx * N + n) * ldo + d] = s_mean[n] + (a0 + a1);
+  }
+  RSQ();
+#ifdef DVG_TRACE
+  if (tid == 0 && d == 0) printf("rsample phases (cycles): stage %lld K %lld UR %lld meanSig %lld chol %lld Leps %lld\n", tq[1]-tq[0], tq[2]-tq[1], tq[3]-tq[2], tq[4]-tq[3], tq[5]-tq[4], tq[6]-tq[5]);
+#endif
+#undef RSQ
+}
+
+
+}  // namespace dvg

@@ -115,6 +115,7 @@ struct StepTrigHost {
   float factor;
   const int32_t* stat_rows;
   float* window; int32_t* count; float* value; float* thr; uint8_t* mask;
+  const float* rs_eps;   // non-null: fired rollouts are resampled inside the launch
 };
 bool lstm_step_usable(const dvg_lstm_s* h, int rows);
 size_t lstm_step_flag_words(const dvg_lstm_s* h, int rows);
@@ -128,7 +129,9 @@ bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows);
 int lstm_tc_rollout_step(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
                          const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
                          float* y, int ldy, int S, const int32_t* stat_rows, float* window, int W, int32_t* count,
-                         int warmup, float factor, float* value, float* thr, uint8_t* mask, cudaStream_t stream);
+                         int warmup, float factor, float* value, float* thr, uint8_t* mask, const float* rs_eps,
+                         cudaStream_t stream);
+bool lstm_tc_can_fuse_rsample(const dvg_gp_s* g, int n_points);
 
 // gp.cu
 int gp_prepare_launch(dvg_gp_s* h, const float* inducing, const float* var_mean, const float* chol_var,

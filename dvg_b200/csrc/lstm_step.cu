@@ -31,8 +31,10 @@
 //   * the trigger is finalised by a dedicated warp instead of stalling one CTA's epilogue warps.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
+#include "gp_rsample.cuh"
 #include "gp_trigger.cuh"
 #include "tc_common.cuh"
 
@@ -64,6 +66,7 @@ struct StepTrig {
   const float* z; const float* linv; const float* lqt; const float* hyp;
   float* var_rows; unsigned int* ticket; float* window; int32_t* count;
   float* value; float* thr; uint8_t* mask; int* trig_list; int* trig_count;
+  const float* rs_eps; const float* alpha; float* rs_out; int rs_ldo; int n_points;   // in-kernel rsample of fired rollouts
 };
 struct StepArgs {
   int rows, row_tiles, groups, nsplit, stages, n_phases, total_items, H, L, G, ldx, kbx, rows_per_flag, restore;
@@ -493,6 +496,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           for (int i = 0; i < 16; ++i) rc[i] = rn[i];
         }
         ptx::tmem_st_wait();
+        if (etid == 0 && tm == 0) TRACE(32);
         {
           // packed h' image of this CTA's 128 rows x 64 units (one k-block of the next GEMM's A operand)
           uint8_t* img = f.hp_out + (size_t)(rt * (p.H / 64) + nt) * (2u * TC_A_IMG);
@@ -525,9 +529,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           }
         }
         // publish the k-block: consumers (next layer / head) only read the packed image
-        __threadfence();
+        // (CTA barrier, then ONE thread fences at gpu scope and bumps the counter: the release is cumulative over
+        // the stores the barrier ordered before it -- no per-thread membar)
+        if (etid == 0 && tm == 0) TRACE(33);
         ptx::named_bar_sync(1, EPI_WARPS * 32);
         if (etid == 0) {
+          if (tm == 0) TRACE(34);
+          __threadfence();
           atomicAdd(f.done_flags + rg * f.n_tiles + nt, 1);
           if (tm == 0) TRACE(28);
         }
@@ -630,7 +638,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       if (etid == 0 && tm < 3) {
         TRACE(2 + tm * 8 + 5);
 #ifdef DVG_TRACE
-        if (p.trace) p.trace[(size_t)blockIdx.x * 32 + 2 + tm * 8 + 6] = 1000000ull + item;
+        if (p.trace) p.trace[(size_t)blockIdx.x * TRACE_SLOTS + 2 + tm * 8 + 6] = 1000000ull + item;
 #endif
       }
       // ---- GP variance trigger (generate_frames.py:227-232,275): after their first tile the epilogue warps wait
@@ -697,7 +705,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
 
   // ---- teardown ----------------------------------------------------------------------------------------------
   ptx::tc_fence_before();
-  if (p.restore) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) TRACE(30);
   ptx::cluster_sync_all();
@@ -710,6 +717,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
   // rollouts are copied back from the input block (fp32 h, c and the packed h images), spread over all CTAs.
   if (p.restore) {
     if (threadIdx.x == 0) {
+      __threadfence();                 // cumulative over this CTA's stores (ordered by the barrier above)
       atomicAdd(p.done_ctr, 1);
       poll_ge(p.mask_ready, 1, -1);
       s_misc[0] = *reinterpret_cast<volatile int*>(p.trig.trig_count);
@@ -743,6 +751,20 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
             const size_t off = ((size_t)((r / TC_ROWS) * hk + kb) * 2 + part) * TC_A_IMG + (size_t)(r % TC_ROWS) * 128 + qd * 16;
             *reinterpret_cast<uint4*>(f.hp_out + off) = __ldg(reinterpret_cast<const uint4*>(f.a_rec + off));
           }
+        }
+      }
+      // ... and their decoder input becomes a GP posterior sample of the encoder latent instead of the LSTM
+      // prediction (generate_frames.py:291-292): one (fired rollout, latent dim) problem per CTA trip, solved by the
+      // epilogue warps in the now idle stage buffers.  Every head tile has been written (done_ctr), so the rows are
+      // simply overwritten.
+      if (p.trig.rs_eps != nullptr && warp >= 2 && warp < 2 + EPI_WARPS) {
+        const StepTrig& g = p.trig;
+        float* smf = reinterpret_cast<float*>(smem_raw);
+        for (int wi = blockIdx.x; wi < n_fired * g.D; wi += gridDim.x) {
+          const int s = g.trig_list[wi / g.D], d = wi % g.D;
+          gp_rsample_body(smf, (int)threadIdx.x - 64, [] { ptx::named_bar_sync(1, EPI_WARPS * 32); }, s, d, g.n_points, g.D,
+                          g.mp, p.x, p.ldx, g.rs_eps, g.z, g.linv, g.lqt, g.alpha, g.hyp, g.rs_out, g.rs_ldo);
+          ptx::named_bar_sync(1, EPI_WARPS * 32);   // shared memory is reused by the next problem
         }
       }
     }
@@ -781,10 +803,141 @@ size_t lstm_step_xp_bytes(const dvg_lstm_s* h, int rows) {
   return (size_t)(h->dims.hidden_size / 64) * ceil_div(rows, TC_ROWS) * ceil_div(h->dims.input_size, 64) * 2 * TC_A_IMG;
 }
 
-// Item order of the step kernel (position i runs on pair i % pairs as its (i / pairs)-th item).  Every item's
-// dependencies must sit at smaller positions.  nullptr = identity order (layer-major).
+// ---------------------------------------------------------------------------------------------------
+// Item schedule.  Position i of the order runs on pair i % pairs as its (i / pairs)-th item (-1 = none); every
+// item's dependencies sit at smaller positions of the sequence the lists were built from, so the kernel cannot
+// deadlock.  With 80 + 80 + 20 items on 74 pairs the layer-major order leaves a three-deep tail (late layer-0
+// tiles -> their layer-1 consumers as third items -> heads).  The lists are therefore built by a small list
+// scheduler on a cost model calibrated from the timestamp traces (profiles/): layer-0 tiles go round-robin to all
+// but d pairs, the remaining items are placed one by one on the pair that completes them earliest, and d is
+// chosen by simulating the makespan.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct SchedCost {
+  double t_first = 3.9, kt = 1.0, kt_head = 0.4, te_lstm = 6.3, t_pub = 5.0, te_head = 2.3, t_dep = 1.6;
+};
+struct PairSim {
+  double mma_free = 0.0, epi_free = 0.0, drain[2] = {0.0, 0.0};
+  int n = 0;
+  std::vector<int> items;
+};
+}  // namespace
+
+static double sched_place(PairSim& ps, const SchedCost& c, int layer, int L, int kb_rec, double in_kb, double dep_ready,
+                          bool commit, double* publish) {
+  const bool head = layer == L;
+  double start = ps.n == 0 ? c.t_first : ps.mma_free;
+  if (ps.n >= 2 && ps.drain[ps.n & 1] > start) start = ps.drain[ps.n & 1];   // TMEM buffer still being drained
+  const double kt = head ? c.kt_head : c.kt;
+  const double rec_done = start + kb_rec * kt;
+  double in_start = rec_done;
+  if (dep_ready + c.t_dep > in_start) in_start = dep_ready + c.t_dep;
+  const double acc = in_start + in_kb * kt;
+  const double epi_start = acc > ps.epi_free ? acc : ps.epi_free;
+  const double te = head ? c.te_head : c.te_lstm;
+  const double done = epi_start + te;
+  if (commit) {
+    ps.mma_free = acc;
+    ps.drain[ps.n & 1] = epi_start + (head ? te : c.t_pub);
+    ps.epi_free = done;
+    ++ps.n;
+    if (publish) *publish = epi_start + (head ? te : c.t_pub);
+  }
+  return done;
+}
+
+// returns the makespan; fills lists (per pair) when out != nullptr
+static double sched_build(int P, int L, int groups, int hk, double x_kb, int d, const SchedCost& c,
+                          std::vector<std::vector<int>>* out) {
+  std::vector<PairSim> ps(P);
+  const int per_layer = groups * hk;
+  std::vector<double> pub((size_t)L * per_layer, 0.0);
+  // layer 0: round-robin over pairs d .. P-1
+  for (int i = 0; i < per_layer; ++i) {
+    PairSim& q = ps[d + i % (P - d)];
+    sched_place(q, c, 0, L, hk, x_kb, 0.0, true, &pub[i]);
+    q.items.push_back(i);
+  }
+  auto place_ect = [&](int item, int layer, int kb_rec, double in_kb, double dep) {
+    int best = 0;
+    double bt = 1e30;
+    for (int q = 0; q < P; ++q) {
+      const double t = sched_place(ps[q], c, layer, L, kb_rec, in_kb, dep, false, nullptr);
+      if (t < bt - 1e-9) { bt = t; best = q; }
+    }
+    double pb = 0.0;
+    sched_place(ps[best], c, layer, L, kb_rec, in_kb, dep, true, &pb);
+    ps[best].items.push_back(item);
+    return pb;
+  };
+  for (int l = 1; l <= L; ++l) {
+    // consumers of layer l-1, in the order their dependencies become ready
+    const int n_items = l < L ? per_layer : groups;
+    std::vector<std::pair<double, int>> order;
+    for (int j = 0; j < n_items; ++j) {
+      const int rg = l < L ? j / hk : j;
+      double dep = 0.0;
+      for (int nt = 0; nt < hk; ++nt) dep = std::max(dep, pub[(size_t)(l - 1) * per_layer + rg * hk + nt]);
+      order.push_back({dep, j});
+    }
+    std::stable_sort(order.begin(), order.end());
+    for (auto& o : order) {
+      const int item = l * per_layer + o.second;
+      const double pb = place_ect(item, l, l < L ? hk : 0, hk, o.first);
+      if (l < L) pub[(size_t)l * per_layer + o.second] = pb;
+    }
+  }
+  double mk = 0.0;
+  for (auto& q : ps) mk = std::max(mk, q.epi_free);
+  if (out) {
+    out->clear();
+    for (auto& q : ps) out->push_back(q.items);
+  }
+  return mk;
+}
+
 int lstm_step_build_schedule(dvg_lstm_s* h, int rows) {
-  (void)h; (void)rows;
+  if (h->sched_dev) { cudaFree(h->sched_dev); h->sched_dev = nullptr; }
+  h->sched_len = h->sched_rows = h->sched_pairs = 0;
+  // Experimental: on the kth_s100 workload no list schedule beat the layer-major identity order (2.50 .. 2.73 ms per
+  // rollout against 2.52 ms), so it is opt-in (DVG_STEP_SCHED=1) until the cost model is calibrated better.
+  const char* e = getenv("DVG_STEP_SCHED");
+  if (!(e && e[0] == '1')) return DVG_OK;
+  const int L = h->dims.n_layers, hk = h->dims.hidden_size / 64;
+  const int RT = ceil_div(rows, TC_ROWS), groups = ceil_div(RT, 2);
+  const int total = L * groups * hk + groups;
+  int P = h->sm_count / 2;
+  if (P > total) P = total;
+  if (P < 2 || L < 2 || !h->tc_ok) return DVG_OK;   // single layer: layer-major order is already dependency-free
+  SchedCost c;
+  const double x_kb = ceil_div(h->dims.input_size, 16) / 4.0;
+  int best_d = 0;
+  double best = 1e30;
+  for (int d = 0; d <= P / 3; ++d) {
+    const double mk = sched_build(P, L, groups, hk, x_kb, d, c, nullptr);
+    if (mk < best - 1e-9) { best = mk; best_d = d; }
+  }
+  if (const char* fd = getenv("DVG_STEP_SCHED_D")) best_d = std::max(0, std::min(P / 2, atoi(fd)));   // developer override
+  std::vector<std::vector<int>> lists;
+  best = sched_build(P, L, groups, hk, x_kb, best_d, c, &lists);
+  size_t depth = 0;
+  int l0_max = 0;
+  for (auto& li : lists) {
+    depth = std::max(depth, li.size());
+    int n0 = 0;
+    for (int it : li) n0 += it < groups * hk ? 1 : 0;
+    l0_max = std::max(l0_max, n0);
+  }
+  if (l0_max > STEP_XMAX) return DVG_OK;
+  std::vector<int> flat(depth * P, -1);
+  for (int q = 0; q < P; ++q)
+    for (size_t k = 0; k < lists[q].size(); ++k) flat[k * P + q] = lists[q][k];
+  DVG_CUDA(cudaMalloc(&h->sched_dev, sizeof(int) * flat.size()));
+  DVG_CUDA(cudaMemcpy(h->sched_dev, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice));
+  h->sched_len = (int)flat.size(); h->sched_rows = rows; h->sched_pairs = P;
+  if (getenv("DVG_STEP_SCHED_VERBOSE"))
+    fprintf(stderr, "dvg_b200: step schedule rows=%d pairs=%d d=%d depth=%zu model makespan %.1f us (layer-major %.1f)\n", rows, P,
+            best_d, depth, best, sched_build(P, L, groups, hk, x_kb, 0, c, nullptr));
   return DVG_OK;
 }
 
@@ -823,6 +976,8 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
     t.var_rows = g->var_rows; t.ticket = g->ticket; t.window = trig->window; t.count = trig->count;
     t.value = trig->value; t.thr = trig->thr; t.mask = trig->mask; t.trig_list = g->trig_list;
     t.trig_count = g->trig_count;
+    t.rs_eps = trig->warmup ? nullptr : trig->rs_eps; t.alpha = g->alpha; t.rs_out = y; t.rs_ldo = ldy;
+    t.n_points = rows / trig->S;
     a.restore = trig->warmup ? 0 : 1;
     a.rows_per_flag = rows / trig->S;
     a.hold = nullptr;
@@ -887,8 +1042,8 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   static unsigned long long* tbuf = nullptr;
   const bool tr = getenv("DVG_TC_TRACE") != nullptr;
   if (tr) {
-    if (!tbuf) cudaMalloc(&tbuf, 256 * 32 * 8);
-    cudaMemsetAsync(tbuf, 0, 256 * 32 * 8, stream);
+    if (!tbuf) cudaMalloc(&tbuf, 256 * TRACE_SLOTS * 8);
+    cudaMemsetAsync(tbuf, 0, 256 * TRACE_SLOTS * 8, stream);
     a.trace = tbuf;
   }
 #endif
@@ -902,16 +1057,16 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
     const int want = which ? atoi(which) : 4;
     cudaStreamSynchronize(stream);
     if (n_dump++ == want) {
-      std::vector<unsigned long long> hbuf(256 * 32);
-      cudaMemcpy(hbuf.data(), tbuf, 256 * 32 * 8, cudaMemcpyDeviceToHost);
+      std::vector<unsigned long long> hbuf(256 * TRACE_SLOTS);
+      cudaMemcpy(hbuf.data(), tbuf, 256 * TRACE_SLOTS * 8, cudaMemcpyDeviceToHost);
       unsigned long long t0 = ~0ull;
-      for (int b = 0; b < (int)cfg.gridDim.x; ++b) if (hbuf[b * 32] && hbuf[b * 32] < t0) t0 = hbuf[b * 32];
+      for (int b = 0; b < (int)cfg.gridDim.x; ++b) if (hbuf[b * TRACE_SLOTS] && hbuf[b * TRACE_SLOTS] < t0) t0 = hbuf[b * TRACE_SLOTS];
       fprintf(stderr, "STEP TRACE grid=%d items=%d stages=%d restore=%d: start setup | per item: pstart depok stage0 mma_issued acc_ready epi_done item requested | trigdone xpack published stored end finalizer\n",
               (int)cfg.gridDim.x, a.total_items, stages, a.restore);
       for (int b = 0; b < (int)cfg.gridDim.x; ++b) {
         fprintf(stderr, "cta %3d:", b);
-        for (int i = 0; i < 32; ++i) {
-          unsigned long long v = hbuf[b * 32 + i];
+        for (int i = 0; i < 40; ++i) {
+          unsigned long long v = hbuf[b * TRACE_SLOTS + i];
           if (i == 2 || i == 10 || i == 18 || i == 26) fprintf(stderr, " |");
           if (v >= 1000000ull && v < 2000000ull) fprintf(stderr, " #%lld", (long long)(v - 1000000ull));
           else fprintf(stderr, " %lld", v ? (long long)(v - t0) : -1ll);
@@ -929,13 +1084,19 @@ bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows) 
   const int pairs = h->sm_count / 2;
   return lstm_step_usable(h, rows) && need <= (size_t)EPI_WARPS * 4096 && g->dims.num_dims <= pairs * 2;
 }
+// the in-kernel rsample needs its scratch to fit the stage buffers (3 x 64 KB)
+bool lstm_tc_can_fuse_rsample(const dvg_gp_s* g, int n_points) {
+  return sizeof(float) * gp_rsample_smem_floats(n_points, g->mp) <= (size_t)3 * 65536 && n_points <= 128;
+}
 
 // trigger + LSTM step in one launch; caller guarantees lstm_tc_can_fuse_trigger().
 int lstm_tc_rollout_step(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,
                          const float* c_in, const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out,
                          float* y, int ldy, int S, const int32_t* stat_rows, float* window, int W, int32_t* count,
-                         int warmup, float factor, float* value, float* thr, uint8_t* mask, cudaStream_t stream) {
+                         int warmup, float factor, float* value, float* thr, uint8_t* mask, const float* rs_eps,
+                         cudaStream_t stream) {
   StepTrigHost t{};
+  t.rs_eps = rs_eps;
   t.S = S; t.W = W; t.warmup = warmup; t.factor = factor; t.stat_rows = stat_rows; t.window = window; t.count = count;
   t.value = value; t.thr = thr; t.mask = mask;
   g->last_mask = mask;

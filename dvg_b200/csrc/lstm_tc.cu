@@ -832,8 +832,8 @@ static int launch_tc(const dvg_lstm_s* h, TcArgs& a, cudaStream_t stream) {
   static unsigned long long* tbuf = nullptr;
   const bool tr = EPI == EPI_LSTM && getenv("DVG_TC_TRACE") != nullptr;
   if (tr) {
-    if (!tbuf) cudaMalloc(&tbuf, 256 * 32 * 8);
-    cudaMemsetAsync(tbuf, 0, 256 * 32 * 8, stream);
+    if (!tbuf) cudaMalloc(&tbuf, 256 * TRACE_SLOTS * 8);
+    cudaMemsetAsync(tbuf, 0, 256 * TRACE_SLOTS * 8, stream);
     a.trace = tbuf;
   }
 #endif
@@ -844,16 +844,16 @@ static int launch_tc(const dvg_lstm_s* h, TcArgs& a, cudaStream_t stream) {
     static int n_dump = 0;
     cudaStreamSynchronize(stream);
     if (n_dump++ == 6) {
-      std::vector<unsigned long long> hbuf(256 * 32);
-      cudaMemcpy(hbuf.data(), tbuf, 256 * 32 * 8, cudaMemcpyDeviceToHost);
+      std::vector<unsigned long long> hbuf(256 * TRACE_SLOTS);
+      cudaMemcpy(hbuf.data(), tbuf, 256 * TRACE_SLOTS * 8, cudaMemcpyDeviceToHost);
       unsigned long long t0 = ~0ull;
-      for (int b = 0; b < (int)cfg.gridDim.x; ++b) if (hbuf[b * 32] && hbuf[b * 32] < t0) t0 = hbuf[b * 32];
+      for (int b = 0; b < (int)cfg.gridDim.x; ++b) if (hbuf[b * TRACE_SLOTS] && hbuf[b * TRACE_SLOTS] < t0) t0 = hbuf[b * TRACE_SLOTS];
       fprintf(stderr, "TRACE grid=%d cm=%d pairs=%d stages=%d (ns since first CTA start)\n", (int)cfg.gridDim.x, cm,
               (int)pairs, stages);
       for (int b = 0; b < (int)cfg.gridDim.x; b += (b < 8 ? 1 : 13)) {
         fprintf(stderr, "cta %3d:", b);
         for (int i = 0; i < 31; ++i) {
-          unsigned long long v = hbuf[b * 32 + i];
+          unsigned long long v = hbuf[b * TRACE_SLOTS + i];
           if (i == 2 || i == 14 || i == 26) fprintf(stderr, " |");
           fprintf(stderr, " %lld", v ? (long long)(v - t0) : -1ll);
         }

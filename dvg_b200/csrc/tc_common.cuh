@@ -6,13 +6,14 @@
 
 namespace dvg {
 
+constexpr int TRACE_SLOTS = 64;
 #ifdef DVG_TRACE
 #define TRACE(slot)                                                                   \
   do {                                                                                \
     if (p.trace) {                                                                    \
       unsigned long long _t;                                                          \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t) :: "memory");                          \
-      p.trace[(size_t)blockIdx.x * 32 + (slot)] = _t;                                 \
+      p.trace[(size_t)blockIdx.x * TRACE_SLOTS + (slot)] = _t;                                 \
     }                                                                                 \
   } while (0)
 #else

@@ -70,6 +70,7 @@ class RolloutEngine:
         self.value = torch.zeros(S, device=dev)
         self.thr = torch.zeros(S, device=dev)
         self.mask = torch.zeros(S, dtype=torch.uint8, device=dev)
+        self._mask_buf, self._value_buf = self.mask, self.value     # where the trigger writes (see latent_rollout)
         base = torch.arange(S, dtype=torch.int32) * B
         self.stat_rows = (base + cfg.stat_col).to(dev)
         wcols = cfg.stat_col_warmup if cfg.stat_col_warmup is not None else [cfg.stat_col] * S
@@ -114,39 +115,42 @@ class RolloutEngine:
         _capi.check(self.lib.dvg_gp_trigger(self.grt.handle, self.S, _capi.ptr(h), self._ld(h), _capi.ptr(rows),
                                             _capi.ptr(self.window), self.cfg.window, _capi.ptr(self.count),
                                             1 if warmup else 0, TRIGGER_FACTOR, _capi.ptr(self.value),
-                                            _capi.ptr(self.thr), _capi.ptr(self.mask), _capi.stream_ptr()),
+                                            _capi.ptr(self.thr), _capi.ptr(self._mask_buf), _capi.stream_ptr()),
                     "dvg_gp_trigger")
 
     def advance(self, h, out, hold: bool):
         nxt = 1 - self.cur
         _capi.check(self.lib.dvg_lstm_step(self.lrt.handle, self.variant, self.R, _capi.ptr(h), self._ld(h),
                                            _capi.ptr(self.blocks[self.cur]), _capi.ptr(self.blocks[nxt]),
-                                           _capi.ptr(out), self._ld(out), _capi.ptr(self.mask) if hold else None,
+                                           _capi.ptr(out), self._ld(out), _capi.ptr(self._mask_buf) if hold else None,
                                            self.B, _capi.stream_ptr()), "dvg_lstm_step")
         self.cur = nxt
 
     def resample(self, h, eps, out, masked: bool):
         assert eps.shape == (self.S, self.D, self.B) and eps.is_contiguous()
         _capi.check(self.lib.dvg_gp_rsample(self.grt.handle, self.S, self.B, _capi.ptr(h), self._ld(h),
-                                            _capi.ptr(eps), _capi.ptr(self.mask) if masked else None, _capi.ptr(out),
+                                            _capi.ptr(eps), _capi.ptr(self._mask_buf) if masked else None, _capi.ptr(out),
                                             self._ld(out), _capi.stream_ptr()), "dvg_gp_rsample")
 
     # ---- fused steps -----------------------------------------------------------------------------
-    def step_trigger_mode(self, h, eps, out, warmup: bool):
+    def step_trigger_mode(self, h, eps, out, warmup: bool, resample: bool = True):
         """One GPtrigger_gen step (generate_frames.py:266-298) for all rollouts: ``out`` [S*B, G] receives
         the decoder input (LSTM prediction, or the GP sample for triggered rollouts)."""
         rows = self.stat_rows_warmup if warmup else self.stat_rows
         nxt = 1 - self.cur
+        rs = None
+        if not warmup and resample:
+            assert eps.shape == (self.S, self.D, self.B) and eps.is_contiguous()
+            rs = _capi.ptr(eps)
+        # ONE launch: trigger + LSTM step + (fired rollouts only) state restore and GP resample into `out`
         _capi.check(self.lib.dvg_rollout_step(self.lrt.handle, self.grt.handle, self.variant, self.R, _capi.ptr(h),
                                               self._ld(h), _capi.ptr(self.blocks[self.cur]),
                                               _capi.ptr(self.blocks[nxt]), _capi.ptr(out), self._ld(out), self.S,
                                               _capi.ptr(rows), _capi.ptr(self.window), self.cfg.window,
                                               _capi.ptr(self.count), 1 if warmup else 0, TRIGGER_FACTOR,
-                                              _capi.ptr(self.value), _capi.ptr(self.thr), _capi.ptr(self.mask),
-                                              _capi.stream_ptr()), "dvg_rollout_step")
+                                              _capi.ptr(self._value_buf), _capi.ptr(self.thr),
+                                              _capi.ptr(self._mask_buf), rs, _capi.stream_ptr()), "dvg_rollout_step")
         self.cur = nxt
-        if not warmup:
-            self.resample(h, eps, out, masked=True)
 
     def step_manual_mode(self, h, eps, out, resample: bool):
         """One make_gifs / plot step (generate_frames.py:166-174): LSTM always advances; on a resample step
@@ -162,11 +166,11 @@ class RolloutEngine:
         Optional ``masks`` [T, S] u8 / ``values`` [T, S] record the trigger trace (device copies)."""
         W = self.cfg.window if warmup_steps is None else warmup_steps
         for t in range(lat.shape[0]):
+            # the trigger writes its mask / value straight into row t of the trace buffers (no copy kernels)
+            self._mask_buf = masks[t] if masks is not None else self.mask
+            self._value_buf = values[t] if values is not None else self.value
             self.step_trigger_mode(lat[t], eps[t], out[t], warmup=t < W)
-            if masks is not None:
-                masks[t].copy_(self.mask)
-            if values is not None:
-                values[t].copy_(self.value)
+        self._mask_buf, self._value_buf = self.mask, self.value
 
     def capture_latent_rollout(self, lat, eps, out, masks=None, values=None):
         """CUDA-graph the whole T-step latent rollout (static launch sequence, zero host work per replay).

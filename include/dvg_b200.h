@@ -202,14 +202,18 @@ DVG_API int dvg_gp_export(dvg_gp_t h, float* linv, float* lqt, float* alpha, flo
  * N-diverse-futures bookkeeping
  * ---------------------------------------------------------------------------------------------- */
 /* One GPtrigger_gen time step (generate_frames.py:266-298) for S = n_rollouts rollouts of rows/S points each:
- * dvg_gp_trigger(x) followed by dvg_lstm_step(x, hold = warmup ? none : mask) -- same arguments, same results --
- * issued as ONE persistent kernel when the tensor-core variants apply (the trigger runs on the step kernel's
- * epilogue warps while the first gate GEMM tiles are in flight; the hold mask never leaves the device).
- * Follow with dvg_gp_rsample(mask) to substitute the GP sample for the rollouts that fired. */
+ * dvg_gp_trigger(x), dvg_lstm_step(x, hold = warmup ? none : mask) and -- when rs_eps is given and the step is a
+ * decision step -- dvg_gp_rsample(x, rs_eps, mask) into y: same arguments, same results, issued as ONE persistent
+ * kernel when the tensor-core variants apply.  The trigger runs beside the gate GEMM tiles; nobody waits for its
+ * mask: the LSTM advances every rollout and, in the rare step where rollouts fired, the end of the same launch
+ * restores their state rows from state_in (a triggered rollout does not advance its LSTM, :289-295) and overwrites
+ * their rows of y with the GP posterior sample (:291-292).  The mask never leaves the device.
+ *   rs_eps  [n_rollouts, D, rows/n_rollouts] standard normal noise, or NULL (then follow with dvg_gp_rsample(mask)). */
 DVG_API int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows,
                      const float* x, int ldx, const void* state_in, void* state_out, float* y, int ldy,
                      int n_rollouts, const int32_t* stat_rows, float* window, int window_len, int32_t* count,
-                     int warmup, float factor, float* value, float* thr, uint8_t* mask, dvg_stream_t stream);
+                     int warmup, float factor, float* value, float* thr, uint8_t* mask, const float* rs_eps,
+                     dvg_stream_t stream);
 
 /* finn_eval_seq on the device (utils.py:237-301): channel-mean SSIM (11x11 Gaussian window,
  * sigma 1.5, K1=.01, K2=.03, L=1, NaN -> -1) and PSNR = 10 log10(1/mse) of every generated frame against the

@@ -9,14 +9,14 @@ for line in open(sys.argv[1]):
     toks = line.split(":", 1)[1].replace("|", " ").replace("#", "").split()
     rows.append([int(t) for t in toks])
 a = np.array(rows)
-names = {0: "start", 1: "setup", 26: "trigdone", 27: "xpack", 28: "it0 published", 29: "it0 stored", 30: "end", 31: "finalizer"}
+names = {0: "start", 1: "setup", 26: "trigdone", 27: "xpack", 28: "it0 published", 29: "it0 stored", 30: "end", 31: "finalizer", 32: "it0 loopdone", 33: "it0 hpstored", 34: "it0 fenced"}
 for m in range(3):
     for k, n in enumerate(["pstart", "depok", "stage0", "mmaissued", "accready", "epidone", "item", "requested"]):
         names[2 + m * 8 + k] = f"it{m} {n}"
-for s in range(32):
+for s in range(a.shape[1]):
     col = a[:, s]
     v = col[col >= 0]
-    if len(v):
+    if len(v) and s in names:
         print(f"{s:2d} {names[s]:16s} n={len(v):3d} min={v.min():6d} med={int(np.median(v)):6d} max={v.max():6d}")
 if len(sys.argv) > 2:
     for r in a:
