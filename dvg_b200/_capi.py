@@ -21,7 +21,7 @@ EXPORTS = [
     "dvg_lstm_prepare", "dvg_lstm_refresh", "dvg_lstm_destroy", "dvg_lstm_reserve",
     "dvg_lstm_state_bytes", "dvg_lstm_state_packed_offset", "dvg_lstm_state_repack",
     "dvg_lstm_step", "dvg_lstm_profile", "dvg_gauss_lstm_step",
-    "dvg_gp_prepare", "dvg_gp_refresh", "dvg_gp_destroy", "dvg_gp_predict", "dvg_gp_trigger",
+    "dvg_gp_prepare", "dvg_gp_refresh", "dvg_gp_prepare_factors", "dvg_gp_refresh_factors", "dvg_gp_destroy", "dvg_gp_predict", "dvg_gp_trigger",
     "dvg_gp_rsample", "dvg_gp_export", "dvg_rollout_step", "dvg_eval_seq_finn", "dvg_rollout_score",
 ]
 
@@ -83,6 +83,8 @@ def load():
     lib.dvg_gp_refresh.argtypes = [P, P, P, P, P, P, P, P, P]
     lib.dvg_gp_destroy.argtypes = [P]
     lib.dvg_gp_predict.argtypes = [P, c_int, P, c_int, P, P, c_int, P, c_int, P]
+    lib.dvg_gp_prepare_factors.argtypes = [POINTER(c_void_p), POINTER(GpDims), P, P, P, P, P, P]
+    lib.dvg_gp_refresh_factors.argtypes = [P, P, P, P, P, P, P]
     lib.dvg_gp_trigger.argtypes = [P, c_int, P, c_int, P, P, c_int, P, c_int, c_float, P, P, P, P]
     lib.dvg_gp_rsample.argtypes = [P, c_int, c_int, P, c_int, P, P, P, c_int, P]
     lib.dvg_gp_export.argtypes = [P, P, P, P, P, P]

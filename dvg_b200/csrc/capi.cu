@@ -234,7 +234,7 @@ int dvg_gauss_lstm_step(dvg_lstm_t h, int variant, int rows, const float* x, int
 static void gp_free_all(dvg_gp_s* h) {
   auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
   fr(h->z); fr(h->linv); fr(h->lqt); fr(h->alpha); fr(h->hyp); fr(h->work); fr(h->var_rows);
-  fr(h->ticket); fr(h->trig_list); fr(h->trig_count); fr(h->linvT); fr(h->lq);
+  fr(h->ticket); fr(h->trig_list); fr(h->trig_count); fr(h->linvT); fr(h->lq); fr(h->partial);
 }
 
 int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* var_mean,
@@ -242,6 +242,9 @@ int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing
                    const float* raw_lengthscale, const float* raw_noise, dvg_stream_t stream) {
   DVG_REQUIRE(out && dims, "null argument");
   DVG_REQUIRE(dims->num_dims > 0 && dims->num_inducing > 0, "bad sizes");
+  DVG_REQUIRE(dims->num_inducing <= DVG_GP_MAX_INDUCING_ONDEVICE,
+              "num_inducing=%d: the on-device fp64 factorisation handles at most %d inducing points; factorise on the "
+              "host side and use dvg_gp_prepare_factors", dims->num_inducing, DVG_GP_MAX_INDUCING_ONDEVICE);
   dvg_gp_s* h = new (std::nothrow) dvg_gp_s();
   DVG_REQUIRE(h, "out of host memory");
   h->dims = *dims;
@@ -281,8 +284,50 @@ int dvg_gp_refresh(dvg_gp_t h, const float* inducing, const float* var_mean, con
                    const float* raw_noise, dvg_stream_t stream) {
   DVG_REQUIRE(h && inducing && var_mean && chol_var && mean_const && raw_outputscale && raw_lengthscale && raw_noise,
               "null argument");
+  DVG_REQUIRE(!h->big, "handle holds pre-computed factors: use dvg_gp_refresh_factors");
   return gp_prepare_launch(h, inducing, var_mean, chol_var, mean_const, raw_outputscale, raw_lengthscale, raw_noise,
                            (cudaStream_t)stream);
+}
+
+int dvg_gp_prepare_factors(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* linv,
+                           const float* lq, const float* beta, const float* hyp, dvg_stream_t stream) {
+  DVG_REQUIRE(out && dims && inducing && linv && lq && beta && hyp, "null argument");
+  DVG_REQUIRE(dims->num_dims > 0 && dims->num_inducing > 0, "bad sizes");
+  dvg_gp_s* h = new (std::nothrow) dvg_gp_s();
+  DVG_REQUIRE(h, "out of host memory");
+  h->dims = *dims;
+  h->big = true;
+  h->mp = (int)align_up(dims->num_inducing, 64);
+  const size_t D = dims->num_dims, mp = h->mp;
+  cudaError_t e = cudaGetDevice(&h->device);
+  if (e == cudaSuccess) e = cudaMalloc(&h->z, sizeof(float) * D * mp);
+  if (e == cudaSuccess) e = cudaMalloc(&h->linv, sizeof(float) * D * mp * mp);
+  if (e == cudaSuccess) e = cudaMalloc(&h->lqt, sizeof(float) * D * mp * mp);
+  if (e == cudaSuccess) e = cudaMalloc(&h->alpha, sizeof(float) * D * mp);
+  if (e == cudaSuccess) e = cudaMalloc(&h->hyp, sizeof(float) * D * 4);
+  h->var_rows_cap = 4096;
+  if (e == cudaSuccess) e = cudaMalloc(&h->var_rows, sizeof(float) * D * h->var_rows_cap);
+  if (e == cudaSuccess) e = cudaMalloc(&h->trig_list, sizeof(int) * h->var_rows_cap);
+  if (e == cudaSuccess) e = cudaMalloc(&h->trig_count, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, sizeof(unsigned int) * (1 + h->var_rows_cap / 8 + 1));
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int) * (1 + h->var_rows_cap / 8 + 1));
+  if (e == cudaSuccess) e = cudaMemset(h->trig_count, 0, sizeof(int));
+  if (e != cudaSuccess) {
+    set_error("GP handle allocation failed: %s", cudaGetErrorString(e));
+    gp_free_all(h);
+    delete h;
+    return DVG_ERR_CUDA;
+  }
+  int rc = gp_big_load_factors(h, inducing, linv, lq, beta, hyp, (cudaStream_t)stream);
+  if (rc) { gp_free_all(h); delete h; return rc; }
+  *out = h;
+  return DVG_OK;
+}
+
+int dvg_gp_refresh_factors(dvg_gp_t h, const float* inducing, const float* linv, const float* lq, const float* beta,
+                           const float* hyp, dvg_stream_t stream) {
+  DVG_REQUIRE(h && h->big && inducing && linv && lq && beta && hyp, "bad argument (handle must come from dvg_gp_prepare_factors)");
+  return gp_big_load_factors(h, inducing, linv, lq, beta, hyp, (cudaStream_t)stream);
 }
 
 int dvg_gp_destroy(dvg_gp_t h) {
@@ -298,6 +343,8 @@ int dvg_gp_predict(dvg_gp_t h, int n_rows, const float* x, int ldx, const int32_
   DVG_REQUIRE(n_rows >= 0 && ldx >= h->dims.num_dims, "bad n_rows/ldx");
   if (mean) DVG_REQUIRE(ldm >= h->dims.num_dims, "bad ldm");
   if (var) DVG_REQUIRE(ldv >= h->dims.num_dims, "bad ldv");
+  if (h->big)
+    return gp_big_predict_launch(h, n_rows, x, ldx, row_index, mean, ldm, 1, var, ldv, 1, (cudaStream_t)stream);
   return gp_predict_launch(h, n_rows, x, ldx, row_index, mean, ldm, var, ldv, (cudaStream_t)stream);
 }
 
@@ -325,6 +372,9 @@ int dvg_gp_trigger(dvg_gp_t h, int n_rollouts, const float* x, int ldx, const in
     DVG_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int) * (size_t)(2 + n_rollouts / 8)));
     h->var_rows_cap = n_rollouts;
   }
+  if (h->big)
+    return gp_big_trigger_launch(h, n_rollouts, x, ldx, stat_rows, window, window_len, count, warmup, factor, value, thr,
+                                 mask, (cudaStream_t)stream);
   return gp_trigger_launch(h, n_rollouts, x, ldx, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,
                            (cudaStream_t)stream);
 }
@@ -334,6 +384,8 @@ int dvg_gp_rsample(dvg_gp_t h, int n_rollouts, int n_points, const float* x, int
   DVG_REQUIRE(h && x && eps && out, "null argument");
   DVG_REQUIRE(n_rollouts > 0 && n_points > 0, "bad sizes");
   DVG_REQUIRE(ldx >= h->dims.num_dims && ldo >= h->dims.num_dims, "bad leading dimension");
+  DVG_REQUIRE(!h->big, "rsample with a large inducing set (pre-computed factors, M=%d) is not implemented yet",
+              h->dims.num_inducing);
   return gp_rsample_launch(h, n_rollouts, n_points, x, ldx, eps, mask, out, ldo, (cudaStream_t)stream);
 }
 

@@ -81,6 +81,10 @@ struct dvg_gp_s {
   int* trig_count = nullptr;
   const uint8_t* last_mask = nullptr;  // mask buffer the list corresponds to
   int last_mask_rollouts = 0;
+  // large inducing sets (gp_big.cu): factors loaded pre-computed, mp = M rounded up to 64, tiled FP32 GEMM kernels
+  bool big = false;
+  float* partial = nullptr;   // [D][mp/64][n_pad][3] row-block partial sums
+  size_t partial_cap = 0;
 };
 
 namespace dvg {
@@ -144,6 +148,16 @@ int gp_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t
                       cudaStream_t stream);
 int gp_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const float* eps, const uint8_t* mask,
                       float* out, int ldo, cudaStream_t stream);
+
+// gp_big.cu
+int gp_big_load_factors(dvg_gp_s* h, const float* inducing, const float* linv, const float* lq, const float* beta,
+                        const float* hyp, cudaStream_t stream);
+int gp_big_predict_launch(dvg_gp_s* h, int n_rows, const float* x, int ldx, const int32_t* row_index, float* mean,
+                          long long mean_sn, long long mean_sd, float* var, long long var_sn, long long var_sd,
+                          cudaStream_t stream);
+int gp_big_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t* stat_rows, float* window, int W,
+                          int32_t* count, int warmup, float factor, float* value, float* thr, uint8_t* mask,
+                          cudaStream_t stream);
 
 // rollout.cu
 int eval_seq_finn_launch(int T, int S, int B, int C, int H, int W, const float* gt, const float* gen, float* ssim,

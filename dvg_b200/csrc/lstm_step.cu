@@ -228,6 +228,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // PDL: everything above (barrier init, TMEM allocation, cluster sync) may overlap the tail of the previous kernel
+  // in the stream (normally the previous time step, whose last pairs finish ~10 us after the first); nothing below
+  // may run before that grid has completed: it produced our state, and it resets the dependency counters on exit.
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
   if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
@@ -1034,10 +1039,17 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   cfg.blockDim = dim3(STEP_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("DVG_STEP_PDL");       // developer switch: 0 = plain stream order
+    use_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 2 : 1;
 #ifdef DVG_TRACE
   static unsigned long long* tbuf = nullptr;
   const bool tr = getenv("DVG_TC_TRACE") != nullptr;
@@ -1082,7 +1094,7 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
 bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows) {
   const size_t need = sizeof(float) * ((size_t)2 * g->mp * g->mp + g->mp + 128);
   const int pairs = h->sm_count / 2;
-  return lstm_step_usable(h, rows) && need <= (size_t)EPI_WARPS * 4096 && g->dims.num_dims <= pairs * 2;
+  return lstm_step_usable(h, rows) && !g->big && need <= (size_t)EPI_WARPS * 4096 && g->dims.num_dims <= pairs * 2;
 }
 // the in-kernel rsample needs its scratch to fit the stage buffers (3 x 64 KB)
 bool lstm_tc_can_fuse_rsample(const dvg_gp_s* g, int n_points) {

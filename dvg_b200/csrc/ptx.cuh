@@ -307,5 +307,12 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
                : "memory");
 }
 
+
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining; griddep_wait() blocks until the predecessor grid has
+// completed and its memory is visible, griddep_launch_dependents() lets the successor's CTAs be scheduled early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace ptx
 }  // namespace dvg

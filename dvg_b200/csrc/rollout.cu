@@ -8,7 +8,9 @@
 
 namespace dvg {
 
-// One warp per row (s*B + b): lanes stride over g, loop over t; 8 rows per CTA.
+// One warp per row (s*B + b): lanes stride over g, loop over t; 8 rows per CTA.  The t loop is blocked by 8 with all
+// loads of a block issued before the first use: with one row of 90 floats per (warp, t) the unblocked loop kept ~3
+// loads in flight per lane and ran at 1.6 TB/s.
 __global__ void __launch_bounds__(256) rollout_score_kernel(int T, int S, int B, int G, const float* __restrict__ out,
                                                             const float* __restrict__ target,
                                                             float* __restrict__ scores) {
@@ -18,12 +20,21 @@ __global__ void __launch_bounds__(256) rollout_score_kernel(int T, int S, int B,
   if (row >= R) return;
   const int b = row % B;
   float acc = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float* o = out + ((size_t)t * R + row) * G;
-    const float* g = target + ((size_t)t * B + b) * G;
-    for (int i = lane; i < G; i += 32) {
-      const float dlt = __ldg(o + i) - __ldg(g + i);
-      acc = fmaf(dlt, dlt, acc);
+  constexpr int TB = 8;
+  for (int i = lane; i < G; i += 32) {
+    for (int t0 = 0; t0 < T; t0 += TB) {
+      float o[TB], g[TB];
+#pragma unroll
+      for (int u = 0; u < TB; ++u) {
+        const int t = t0 + u;
+        o[u] = t < T ? __ldg(out + ((size_t)t * R + row) * G + i) : 0.f;
+        g[u] = t < T ? __ldg(target + ((size_t)t * B + b) * G + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < TB; ++u) {
+        const float dlt = o[u] - g[u];
+        acc = fmaf(dlt, dlt, acc);
+      }
     }
   }
 #pragma unroll

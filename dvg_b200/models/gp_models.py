@@ -32,6 +32,7 @@ from .. import _capi
 
 JITTER = 1e-3
 NOISE_LOWER_BOUND = 1e-4
+MAX_INDUCING_ONDEVICE = 128      # include/dvg_b200.h: DVG_GP_MAX_INDUCING_ONDEVICE
 
 
 class _Holder(nn.Module):
@@ -86,19 +87,64 @@ class _GpRuntime:
         else:
             raw_noise = ts[6]
             lb = float(likelihood.noise_lower_bound)
-        args = [_capi.ptr(t.detach().contiguous()) for t in ts[:6]] + [_capi.ptr(raw_noise.detach().contiguous())]
         with torch.cuda.device(dev):
-            if self.handle is None:
-                dims = _capi.GpDims(D, M, JITTER, lb)
-                hd = _capi.c_void_p()
-                _capi.check(self.lib.dvg_gp_prepare(_capi.ctypes.byref(hd), _capi.ctypes.byref(dims), *args,
-                                                    _capi.stream_ptr()), "dvg_gp_prepare")
-                self.handle = hd
+            if M > MAX_INDUCING_ONDEVICE:
+                self._refresh_factors(ts, raw_noise, lb, D, M)
             else:
-                _capi.check(self.lib.dvg_gp_refresh(self.handle, *args, _capi.stream_ptr()), "dvg_gp_refresh")
+                args = [_capi.ptr(t.detach().contiguous()) for t in ts[:6]] + [_capi.ptr(raw_noise.detach().contiguous())]
+                if self.handle is None:
+                    dims = _capi.GpDims(D, M, JITTER, lb)
+                    hd = _capi.c_void_p()
+                    _capi.check(self.lib.dvg_gp_prepare(_capi.ctypes.byref(hd), _capi.ctypes.byref(dims), *args,
+                                                        _capi.stream_ptr()), "dvg_gp_prepare")
+                    self.handle = hd
+                else:
+                    _capi.check(self.lib.dvg_gp_refresh(self.handle, *args, _capi.stream_ptr()), "dvg_gp_refresh")
         self._keep = raw_noise
         self.D, self.M, self.device = D, M, dev
         self.sig = self.signature(layer, likelihood)
+
+    def _refresh_factors(self, ts, raw_noise, lb, D, M):
+        """Large inducing sets (M > 128, BASELINE configs[4]): the eval-mode constants are factorised here in fp64
+        with torch.linalg (cuSOLVER -- the library gpytorch itself calls for this step, once per weight load) and
+        handed to the C ABI, whose tiled kernels own the per-call work.  Same math as gp_prepare_kernel:
+        L = chol(K_ZZ + jitter I), Linv = L^-1, beta = Linv (m_q - c), L_q = tril(chol_variational_covar)."""
+        Z, m_q, chol_var, c_raw, raw_os, raw_ls = [t.detach() for t in ts[:6]]
+        f64 = torch.float64
+        sp = nn.functional.softplus
+        ell = sp(raw_ls.to(f64).reshape(D))
+        s = sp(raw_os.to(f64).reshape(D))
+        c = c_raw.to(f64).reshape(D)
+        noise = sp(raw_noise.detach().to(f64).reshape(D)) + lb
+        hyp = torch.stack([ell, s, c, noise], dim=1).float().contiguous()
+        z = Z.reshape(D, M)
+        linv = torch.empty(D, M, M, dtype=torch.float32, device=z.device)
+        beta = torch.empty(D, M, dtype=torch.float32, device=z.device)
+        eye = torch.eye(M, dtype=f64, device=z.device)
+        step = max(1, min(D, (1 << 28) // (M * M)))           # bound the fp64 temporaries (~2 GB per operand)
+        for d0 in range(0, D, step):
+            d1 = min(D, d0 + step)
+            zz = z[d0:d1].to(f64)
+            t = (zz[:, :, None] - zz[:, None, :]) / ell[d0:d1, None, None]
+            K = s[d0:d1, None, None] * torch.exp(-0.5 * t * t) + JITTER * eye
+            L = torch.linalg.cholesky(K)
+            Li = torch.linalg.solve_triangular(L, eye.expand(d1 - d0, M, M), upper=False)
+            linv[d0:d1] = Li.float()
+            beta[d0:d1] = torch.einsum("dij,dj->di", Li, m_q[d0:d1].to(f64) - c[d0:d1, None]).float()
+            del t, K, L, Li
+        lq = torch.tril(chol_var).float().contiguous()
+        zc = z.float().contiguous()
+        args = [_capi.ptr(zc), _capi.ptr(linv), _capi.ptr(lq), _capi.ptr(beta), _capi.ptr(hyp)]
+        if self.handle is None:
+            dims = _capi.GpDims(D, M, JITTER, lb)
+            hd = _capi.c_void_p()
+            _capi.check(self.lib.dvg_gp_prepare_factors(_capi.ctypes.byref(hd), _capi.ctypes.byref(dims), *args,
+                                                        _capi.stream_ptr()), "dvg_gp_prepare_factors")
+            self.handle = hd
+        else:
+            _capi.check(self.lib.dvg_gp_refresh_factors(self.handle, *args, _capi.stream_ptr()),
+                        "dvg_gp_refresh_factors")
+        torch.cuda.current_stream().synchronize()      # the staging tensors die with this frame
 
     def __del__(self):
         try:

@@ -85,8 +85,7 @@ class RolloutEngine:
     # ---- state -----------------------------------------------------------------------------------
     def reset(self):
         """frame_predictor.hidden = init_hidden() + empty trigger window for every rollout."""
-        for b in self.blocks:
-            b.zero_()
+        self.blocks[0].zero_()      # the other block is fully overwritten by the first step (pad rows are never stored)
         self.cur = 0
         self.window.zero_()
         self.count.zero_()
@@ -172,7 +171,7 @@ class RolloutEngine:
             self.step_trigger_mode(lat[t], eps[t], out[t], warmup=t < W)
         self._mask_buf, self._value_buf = self.mask, self.value
 
-    def capture_latent_rollout(self, lat, eps, out, masks=None, values=None):
+    def capture_latent_rollout(self, lat, eps, out, masks=None, values=None, post=None):
         """CUDA-graph the whole T-step latent rollout (static launch sequence, zero host work per replay).
         T must be even so the ping-pong state returns to block 0; call ``reset()`` semantics are captured
         too (the graph zeroes state and window first)."""
@@ -186,9 +185,16 @@ class RolloutEngine:
             self.reset()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if post is not None:
+            with torch.cuda.stream(s):
+                post()                                          # warm outside capture
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
         with torch.cuda.graph(g):
             self.reset()
             self.latent_rollout(lat, eps, out, masks=masks, values=values)
+            if post is not None:
+                post()          # e.g. the scoring pass of the best-of-N selection: same graph, no host launches
         self.cur = 0 if lat.shape[0] % 2 == 0 else 1
         return g
 

@@ -164,6 +164,20 @@ DVG_API int dvg_gp_refresh(dvg_gp_t h,
                    const float* raw_noise, dvg_stream_t stream);
 DVG_API int dvg_gp_destroy(dvg_gp_t h);
 
+/* Inducing sets larger than DVG_GP_MAX_INDUCING_ONDEVICE (BASELINE configs[4] sweeps M = 128 .. 4096): the per-dimension
+ * fp64 factorisation no longer fits shared memory, so the eval-mode constants are computed by the caller (the Python
+ * host side does it with torch.linalg in fp64, the library the reference itself relies on through gpytorch) and
+ * loaded here; dvg_gp_predict / dvg_gp_trigger then run tiled FP32 GEMM kernels over them (gp_big.cu).  Device
+ * pointers, fp32, dense row-major:
+ *   inducing [D,M], linv [D,M,M] = chol(K_ZZ + jitter I)^-1 (lower), lq [D,M,M] = tril(chol_variational_covar),
+ *   beta [D,M] = linv (m_q - c), hyp [D,4] = (lengthscale, outputscale, mean constant, noise incl. lower bound).
+ * dvg_gp_rsample is not available on such a handle yet. */
+#define DVG_GP_MAX_INDUCING_ONDEVICE 128
+DVG_API int dvg_gp_prepare_factors(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* linv,
+                           const float* lq, const float* beta, const float* hyp, dvg_stream_t stream);
+DVG_API int dvg_gp_refresh_factors(dvg_gp_t h, const float* inducing, const float* linv, const float* lq,
+                           const float* beta, const float* hyp, dvg_stream_t stream);
+
 /* likelihood(gp_layer(x)).mean / .variance for a set of latent rows.
  *   x [*, D] row-major (ldx floats): the [N,D] latent itself -- the reference's
  *   h.transpose(0,1).view(D,N,1) is only a strided view of it.

@@ -158,3 +158,94 @@ def test_rsample_mask_leaves_rows_untouched():
             assert relerr(blk, want) < 1e-4
         else:
             assert torch.all(blk == 7.0)
+
+
+# ---- large inducing sets (M > 128: pre-computed factors + tiled GEMM kernels, gp_big.cu; BASELINE configs[4]) ----------
+@pytest.mark.parametrize("params", ["init", "trained_smooth"])
+@pytest.mark.parametrize("D,M,N", [(6, 129, 70), (4, 200, 33), (3, 512, 130)])
+def test_predict_large_inducing_set(params, D, M, N):
+    """Same bar as test_predict (variance and smooth-set mean <= 1e-4 vs the fp64 oracle) on the large-M path."""
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=D + M, trained_like=params != "init", smooth_mean=True)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    h = torch.tanh(torch.randn(N, D, generator=torch.Generator().manual_seed(N)))
+    ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h), torch.float64, "direct", full_cov=False)
+    hc = h.cuda()
+    with torch.no_grad():
+        pred = lik(gp(hc.transpose(0, 1).view(D, N, 1)))
+        mean, var = pred.mean, pred.variance
+    assert gp._runtime(lik).M == M and M > 128
+    assert relerr(var, ref["variance"]) < 1e-4
+    if params == "init":
+        assert mean.abs().max().item() < 1e-6
+    else:
+        assert relerr(mean, ref["mean"]) < 1e-4
+
+
+def test_large_and_small_paths_agree_at_the_boundary():
+    """M = 128 runs the shared-memory kernels, the same parameters padded to M = 129 (one extra far-away inducing
+    point with zero variational weight) run the tiled path: both must give the same predictive."""
+    D, M, N = 5, 128, 90
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=77, trained_like=True, smooth_mean=True)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    h = torch.tanh(torch.randn(N, D, generator=torch.Generator().manual_seed(4))).cuda()
+    with torch.no_grad():
+        p = lik(gp(h.transpose(0, 1).view(D, N, 1)))
+        m_small, v_small = p.mean.clone(), p.variance.clone()
+    ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h.cpu()), torch.float64, "direct", full_cov=False)
+    # extra inducing point at z = 40 (k(z, x) == 0 for |x| < 1), m_q = c there, unit L_q diagonal
+    sd2 = {k: v.clone() for k, v in gp_sd.items()}
+    sd2[gp_ref.K_INDUCING] = torch.cat([gp_sd[gp_ref.K_INDUCING], torch.full((D, 1, 1), 40.0)], 1)
+    sd2[gp_ref.K_VMEAN] = torch.cat([gp_sd[gp_ref.K_VMEAN], gp_sd["mean_module.constant"].reshape(D, 1)], 1)
+    vc = torch.zeros(D, M + 1, M + 1)
+    vc[:, :M, :M] = gp_sd[gp_ref.K_VCHOL]
+    vc[:, M, M] = 1.0
+    sd2[gp_ref.K_VCHOL] = vc
+    gp2, lik2 = make_gp(sd2, lik_sd)
+    with torch.no_grad():
+        p2 = lik2(gp2(h.transpose(0, 1).view(D, N, 1)))
+        m_big, v_big = p2.mean, p2.variance
+    assert relerr(v_small, ref["variance"]) < 1e-4 and relerr(v_big, ref["variance"]) < 1e-4
+    assert relerr(m_small, ref["mean"]) < 1e-4 and relerr(m_big, ref["mean"]) < 1e-4
+    assert relerr(v_big, v_small) < 2e-5
+
+
+def test_trigger_large_inducing_set():
+    """dvg_gp_trigger on the large-M path: values / thresholds / decisions vs oracle/trigger_ref.py."""
+    from dvg_b200 import _capi
+    D, M, N, S, W, T = 6, 256, 8, 37, 5, 14
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=12, trained_like=True, smooth_mean=True)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    rt = gp._runtime(lik)
+    g = torch.Generator().manual_seed(6)
+    lat = torch.tanh(torch.randn(T, S * N, D, generator=g) * torch.linspace(0.3, 1.5, T).reshape(T, 1, 1))
+    stat_rows = (torch.arange(S) * N + 3).int().cuda()
+    window = torch.zeros(S, W, device="cuda")
+    count = torch.zeros(1, dtype=torch.int32, device="cuda")
+    value, thr = torch.empty(S, device="cuda"), torch.empty(S, device="cuda")
+    mask = torch.empty(S, dtype=torch.uint8, device="cuda")
+    ctx = [[] for _ in range(S)]
+    n_checked = 0
+    for t in range(T):
+        x = lat[t].cuda()
+        warm = 1 if t < W else 0
+        _capi.check(rt.lib.dvg_gp_trigger(rt.handle, S, _capi.ptr(x), D, _capi.ptr(stat_rows), _capi.ptr(window), W,
+                                          _capi.ptr(count), warm, float(np.float32(trigger_ref.FACTOR)),
+                                          _capi.ptr(value), _capi.ptr(thr), _capi.ptr(mask), _capi.stream_ptr()))
+        v_gpu, thr_gpu, m_gpu = value.cpu().numpy(), thr.cpu().numpy(), mask.cpu().numpy()
+        ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(lat[t, 3::N]), torch.float64, "direct",
+                                full_cov=False)["variance"].float().numpy()          # [D, S]
+        for s in range(S):
+            v = trigger_ref.trigger_value(ref[:, s:s + 1], 0)
+            assert abs(v_gpu[s] - v) <= 1e-4 * abs(v)
+            if warm:
+                ctx[s].append(v)
+                assert m_gpu[s] == 0
+            else:
+                c = trigger_ref.slide(np.array(ctx[s], dtype=np.float32), v)
+                ctx[s] = list(c)
+                th = trigger_ref.threshold(c)
+                assert abs(thr_gpu[s] - th) <= 1e-4 * abs(th)
+                if abs(float(v) - float(th)) > 1e-4 * abs(float(th)):
+                    assert bool(m_gpu[s]) == bool(v > th)
+                    n_checked += 1
+    assert n_checked > 200
