@@ -178,12 +178,29 @@ def run_ours(args):
         allsc = shard.gather_scores(sc, world * S)
         return shard.select_best(allsc, higher_is_better=False)
 
+    # N > 1: the score all-gather + arg-best of rollout i run on a side stream, overlapped with rollout i + 1 (the
+    # exchange never stalls the compute stream; only a snapshot of the [S, B] score matrix is taken in stream order)
+    s_sel = torch.cuda.Stream() if world > 1 else None
+    sel = {}
+
     def one_step():
         graph.replay()
-        if world == 1:
-            return held["best"]
-        allsc = shard.gather_scores(held["sc"], world * S)   # the only collective: one all-gather of scores
-        return shard.select_best(allsc, higher_is_better=False)
+        if world == 1 or os.environ.get("DVG_BENCH_NOSEL"):      # (debug switch: skip the cross-rank selection)
+            return held.get("best")
+        main = torch.cuda.current_stream()
+        snap = held["sc"].clone()                            # ordered after the graph on the compute stream
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(s_sel):
+            s_sel.wait_event(ev)
+            allsc = shard.gather_scores(snap, world * S)     # the only collective: one all-gather of scores
+            sel["best"] = shard.select_best(allsc, higher_is_better=False)
+            snap.record_stream(s_sel)
+        return sel
+
+    def finish_selection():
+        if s_sel is not None:
+            torch.cuda.current_stream().wait_stream(s_sel)
 
     def sync_all():
         if world > 1:
@@ -192,6 +209,7 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         one_step()
+    finish_selection()
     sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -201,6 +219,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         best = one_step()
+    finish_selection()              # e1 is ordered after the last selection
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
