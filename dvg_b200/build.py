@@ -18,6 +18,8 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-Xptxas", "-v", "-cudart", "static",
 ]
+if os.environ.get("DVG_STEP_NPOLY"):     # developer build: exponentials on the FMA pipe in the step kernel's epilogue
+    NVCC_FLAGS.append("-DDVG_STEP_NPOLY=" + os.environ["DVG_STEP_NPOLY"])
 if os.environ.get("DVG_TRACE"):          # developer build: per-CTA timestamps in the tensor-core kernel
     NVCC_FLAGS.append("-DDVG_TRACE")
 

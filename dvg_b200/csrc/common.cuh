@@ -101,11 +101,15 @@ __device__ __forceinline__ float ex2_poly(float x) {
 // Exponent arguments are clamped at 40 (E <= 2^40, triple products stay finite; sigmoid/tanh are saturated to
 // fp32 precision well before).  E_i, E_f, E_o use the FMA-pipe polynomial, E_g, E_c the MUFU: 4 MUFU + ~57 FP32
 // ops per hidden unit, balanced between the two pipes.  Abs. error ~3e-7.
+// NPOLY of the three sigmoid exponentials use the FMA-pipe polynomial, the rest the MUFU (the rolled epilogue of
+// lstm_step.cu is issue bound, not MUFU bound: ~80 issue slots per cell at NPOLY = 3 against 5 XU results at 16
+// lanes/clk/SM; all-MUFU, NPOLY = 0, was fastest; the fully unrolled per-GEMM epilogues keep 3).
+template <int NPOLY = 3>
 __device__ __forceinline__ void lstm_cell_fast(float ai, float af, float ag, float ao, float bi, float bf, float bg,
                                                float bo, float c_prev, float& h_new, float& c_new) {
-  const float Ei = ex2_poly(fminf(fmaf(ai, -kLog2e, bi), 40.f));
-  const float Ef = ex2_poly(fminf(fmaf(af, -kLog2e, bf), 40.f));
-  const float Eo = ex2_poly(fminf(fmaf(ao, -kLog2e, bo), 40.f));
+  const float Ei = NPOLY >= 1 ? ex2_poly(fminf(fmaf(ai, -kLog2e, bi), 40.f)) : ex2_ftz(fminf(fmaf(ai, -kLog2e, bi), 40.f));
+  const float Ef = NPOLY >= 2 ? ex2_poly(fminf(fmaf(af, -kLog2e, bf), 40.f)) : ex2_ftz(fminf(fmaf(af, -kLog2e, bf), 40.f));
+  const float Eo = NPOLY >= 3 ? ex2_poly(fminf(fmaf(ao, -kLog2e, bo), 40.f)) : ex2_ftz(fminf(fmaf(ao, -kLog2e, bo), 40.f));
   const float Eg = ex2_ftz(fminf(fmaf(ag, -2.f * kLog2e, bg), 40.f));
   const float pi = 1.f + Ei, pf = 1.f + Ef, pg = 1.f + Eg;
   const float P = pi * pg;

@@ -46,6 +46,10 @@ constexpr int STEP_THREADS = 64 + EPI_WARPS * 32 + 32;
 constexpr int AUX_WARP = 2 + EPI_WARPS;
 constexpr int STEP_MAX_STAGES = 6;
 constexpr int STEP_XMAX = 8;            // layer-0 items per pair (one x-ready mbarrier each)
+#ifndef DVG_STEP_NPOLY
+#define DVG_STEP_NPOLY 0      // measured on kth_s100: 3 -> 52.1 us, 2 -> 50.9, 1 -> 50.7, 0 -> 49.7 us per step
+#endif
+constexpr int STEP_NPOLY = DVG_STEP_NPOLY;   // sigmoid exponentials on the FMA pipe (rest: MUFU), see lstm_cell_fast
 constexpr int STEP_BAR_BYTES = 384;     // mbarriers + tmem slot + misc words
 
 struct StepPhase {
@@ -240,6 +244,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
     if (lane == 0) {
       int s = 0, pm = 0, xj = 0;
       uint32_t phs = 0;
+      // L2 eviction priorities: the packed h images of the previous step and the packed x slab are read exactly once
+      // per consumer and are dead afterwards (the state blocks ping-pong) -> evict first; the weights are re-read by
+      // every row group of every step -> evict last.  (Measured neutral on kth_s100, where both state blocks and the
+      // weights already stay in the 126 MB L2; it matters when the caller's conv nets stream through L2 in between.)
+      const uint64_t pol_stream = ptx::l2_policy_evict_first(), pol_keep = ptx::l2_policy_evict_last();
       for (int k = 0;; ++k) {
         const int item = item_at(k);
         if (item < 0) break;
@@ -258,6 +267,17 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         for (int i = 0; i < KB; ++i) {
           const bool rec = i < f.kb_rec;
           const int kb = rec ? i : i - f.kb_rec;
+          // The weight half of a stage never depends on this launch: request it as soon as the stage is free, THEN
+          // wait for the activation k-block (dependency counter / x-pack) -- half of the stage's bytes are already in
+          // flight while the producing pair is still in its epilogue.
+          ptx::mbar_wait(empty_bar(s), phs ^ 1u);
+          const int wk = rec ? f.kb_in + kb : kb;          // weight K order: [input | recurrent]
+          const uint8_t* bsrc = f.w + (size_t)(nt * KB + wk) * (2u * b_part) + rank * b_half;
+          const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+          ptx::mbar_expect_tx(full_bar(s), a_bytes + nparts * b_half);
+          ptx::bulk_g2s_hint(sb, bsrc, b_half, full_bar(s), pol_keep);
+          if (nparts == 2) ptx::bulk_g2s_hint(sb + b_half, bsrc + b_part, b_half, full_bar(s), pol_keep);
           if (!rec) {
             if (!layer0) {
               poll_ge(f.wait_flags + rg * f.kb_in + kb, 2, item);
@@ -269,17 +289,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
             }
             if (pm < 3 && kb == 0) TRACE(2 + pm * 8 + 1);
           }
-          ptx::mbar_wait(empty_bar(s), phs ^ 1u);
           const uint8_t* asrc = rec ? f.a_rec + (size_t)(rt * f.kb_rec + kb) * (2u * TC_A_IMG)
                                     : a_in + (size_t)(rt * f.kb_in + kb) * (2u * TC_A_IMG);
-          const int wk = rec ? f.kb_in + kb : kb;          // weight K order: [input | recurrent]
-          const uint8_t* bsrc = f.w + (size_t)(nt * KB + wk) * (2u * b_part) + rank * b_half;
-          const uint32_t sa = base + (uint32_t)s * stage_bytes;
-          const uint32_t sb = sa + a_bytes;
-          ptx::mbar_expect_tx(full_bar(s), a_bytes + nparts * b_half);
-          ptx::bulk_g2s(sa, asrc, a_bytes, full_bar(s));
-          ptx::bulk_g2s(sb, bsrc, b_half, full_bar(s));
-          if (nparts == 2) ptx::bulk_g2s(sb + b_half, bsrc + b_part, b_half, full_bar(s));
+          if (rec || layer0) ptx::bulk_g2s_hint(sa, asrc, a_bytes, full_bar(s), pol_stream);
+          else ptx::bulk_g2s(sa, asrc, a_bytes, full_bar(s));        // h' of the layer below: re-read by every N tile
           if (++s == p.stages) { s = 0; phs ^= 1u; }
         }
         if (pm < 3) TRACE(2 + pm * 8 + 7);
@@ -441,7 +454,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           const int rr = i * 4 + er;
           cin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row_w0 + rr < p.rows)
-            cin[i] = __ldg(reinterpret_cast<const float4*>(f.c_in + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32) + ec);
+            cin[i] = __ldcs(reinterpret_cast<const float4*>(f.c_in + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32) + ec);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -484,7 +497,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              lstm_cell_fast(__uint_as_float(rc[i]), __uint_as_float(rc[4 + i]), __uint_as_float(rc[8 + i]),
+              lstm_cell_fast<STEP_NPOLY>(__uint_as_float(rc[i]), __uint_as_float(rc[4 + i]), __uint_as_float(rc[8 + i]),
                              __uint_as_float(rc[12 + i]), sb[cb + i], sb[64 + cb + i], sb[128 + cb + i],
                              sb[192 + cb + i], cp[i], hn[i], cn[i]);
           }
@@ -569,8 +582,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         for (int i = 0; i < 8; ++i) {      // h' tile -> global
           const int rr = i * 4 + er;
           const float4 t = *reinterpret_cast<const float4*>(eb + rr * 128 + ((ec ^ (rr & 7)) << 4));
-          if (row_w0 + rr < p.rows)
-            reinterpret_cast<float4*>(f.h_out + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32)[ec] = t;
+          if (row_w0 + rr < p.rows)     // fp32 h' is only there for the caller's `hidden` views: streaming store
+            __stcs(reinterpret_cast<float4*>(f.h_out + (size_t)(row_w0 + rr) * p.H + nt * 64 + half * 32) + ec, t);
         }
         __syncwarp();
         if (etid == 0 && tm == 0) TRACE(29);
@@ -580,8 +593,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         const int ncol_half = f.n_tile / 2;
         const int c_begin = half * ncol_half;
         const bool vec2 = (f.ldy & 1) == 0 && (f.n_valid & 1) == 0;
+        // (rolled loops: this code runs once per head tile and is cold in the instruction caches -- unrolled it was
+        // ~10 KB of straight-line code and the head epilogue took 4.4 us for 128 x 96 outputs)
+#pragma unroll 1
         for (int g0 = 0; g0 < ncol_half; g0 += 32) {
           const int gw = ncol_half - g0 < 32 ? ncol_half - g0 : 32;   // 32 or 16
+#pragma unroll 1
           for (int c16 = 0; c16 < gw; c16 += 16) {
             float v[16];
             ptx::tmem_ld16_wait(tacc + c_begin + g0 + c16, v);
@@ -593,17 +610,19 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
                   make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
           }
           __syncwarp();
-          const int lpr = gw >> 1;              // lanes per row (one float2 each)
+          const int lpr = gw >> 1;              // lanes per row (one float2 each): 16 or 8
           const int rpi = 32 / lpr;             // rows per instruction
+          const int lr = gw == 32 ? lane >> 4 : lane >> 3;
+          const int cc = (gw == 32 ? lane & 15 : lane & 7) * 2;
+#pragma unroll 1
           for (int i = 0; i < 32 / rpi; ++i) {
-            const int rr = i * rpi + lane / lpr;
-            const int cc = (lane % lpr) * 2;
+            const int rr = i * rpi + lr;
             const float2 t = *reinterpret_cast<const float2*>(eb + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4);
             const int col = c_begin + g0 + cc;
             const int grow = row_w0 + rr;
             if (grow < p.rows && col < f.n_valid) {
               float* dst = f.y + (size_t)grow * f.ldy + col;
-              if (vec2) *reinterpret_cast<float2*>(dst) = t;
+              if (vec2) __stcs(reinterpret_cast<float2*>(dst), t);
               else { dst[0] = t.x; if (col + 1 < f.n_valid) dst[1] = t.y; }
             }
           }
@@ -901,30 +920,65 @@ static double sched_build(int P, int L, int groups, int hk, double x_kb, int d, 
   return mk;
 }
 
+// Two-layer pattern for "a few more tiles per layer than pairs" (n = P + e, 0 < e <= P/4; kth_s100: 80 tiles, 74 pairs).
+// The layer-major order makes e pairs run (L0, L0, L1) and e pairs (L0, L1, L1), and the heads of the last row groups
+// wait for third-slot L1 tiles that themselves follow two full tiles: a three-deep tail ~12 us behind the median
+// pair.  Here no pair gets (L0, L1, L1):
+//   pairs [0, e)        (L1, L1)      layer-1 tiles of the first row groups; their recurrent k-blocks run at once, the
+//                                      input k-blocks as soon as the (first-slot) layer-0 tiles publish
+//   pairs [e, 3e)       (L0, L0, L1)  the second L0 is one of the LAST 2e layer-0 tiles, the L1 one of the last 2e
+//                                      layer-1 tiles (whose inputs are exactly those late L0 tiles)
+//   pairs [3e, P)       (L0, L1)      + one head each for the first `groups` of them
+// Every layer-0 tile is first or second in its list behind another layer-0 tile, so none can block: no deadlock.
+static bool sched_pattern_two_layer(int P, int groups, int hk, std::vector<std::vector<int>>& lists) {
+  const int n = groups * hk, e = n - P;
+  if (e <= 0 || e > P / 4 || P - 3 * e < 1) return false;
+  lists.assign(P, {});
+  const int a = 2 * e;
+  auto L0 = [&](int i) { return i; };
+  auto L1 = [&](int j) { return n + j; };
+  auto HEAD = [&](int g) { return 2 * n + g; };
+  for (int q = 0; q < e; ++q) { lists[q].push_back(L1(q)); lists[q].push_back(L1(e + q)); }
+  for (int i = 0; i < P - e; ++i) lists[e + i].push_back(L0(i));                 // first-slot L0 tiles
+  for (int i = 0; i < a; ++i) lists[e + i].push_back(L0(P - e + i));             // the last 2e L0 tiles, second slot
+  for (int i = 0; i < a; ++i) lists[e + i].push_back(L1(n - a + i));             // their consumers, third slot
+  for (int i = 0; i < P - 3 * e; ++i) lists[3 * e + i].push_back(L1(2 * e + i)); // one L1 per single-L0 pair
+  for (int g = 0; g < groups; ++g) lists[3 * e + g % (P - 3 * e)].push_back(HEAD(g));
+  return true;
+}
+
 int lstm_step_build_schedule(dvg_lstm_s* h, int rows) {
   if (h->sched_dev) { cudaFree(h->sched_dev); h->sched_dev = nullptr; }
   h->sched_len = h->sched_rows = h->sched_pairs = 0;
-  // Experimental: on the kth_s100 workload no list schedule beat the layer-major identity order (2.50 .. 2.73 ms per
-  // rollout against 2.52 ms), so it is opt-in (DVG_STEP_SCHED=1) until the cost model is calibrated better.
+  // DVG_STEP_SCHED: 0 / unset = layer-major identity order, 1 = list scheduler on the cost model, 2 = the two-layer
+  // pattern above.  Both alternatives are experimental: on kth_s100 neither beat the identity order (2.28 ms per rollout
+  // either way) -- the tail only moves from the heads of the last row groups to those of the (L1, L1) pairs, because three
+  // ~6 us tile epilogues per pair plus the ~10 us head chain bound the launch, not the order.
   const char* e = getenv("DVG_STEP_SCHED");
-  if (!(e && e[0] == '1')) return DVG_OK;
+  const int mode = e ? atoi(e) : 0;
+  if (mode == 0) return DVG_OK;
   const int L = h->dims.n_layers, hk = h->dims.hidden_size / 64;
   const int RT = ceil_div(rows, TC_ROWS), groups = ceil_div(RT, 2);
   const int total = L * groups * hk + groups;
   int P = h->sm_count / 2;
   if (P > total) P = total;
-  if (P < 2 || L < 2 || !h->tc_ok) return DVG_OK;   // single layer: layer-major order is already dependency-free
-  SchedCost c;
-  const double x_kb = ceil_div(h->dims.input_size, 16) / 4.0;
-  int best_d = 0;
-  double best = 1e30;
-  for (int d = 0; d <= P / 3; ++d) {
-    const double mk = sched_build(P, L, groups, hk, x_kb, d, c, nullptr);
-    if (mk < best - 1e-9) { best = mk; best_d = d; }
-  }
-  if (const char* fd = getenv("DVG_STEP_SCHED_D")) best_d = std::max(0, std::min(P / 2, atoi(fd)));   // developer override
+  if (P < 2 || L != 2 || !h->tc_ok) return DVG_OK;
   std::vector<std::vector<int>> lists;
-  best = sched_build(P, L, groups, hk, x_kb, best_d, c, &lists);
+  double best = 0.0;
+  int best_d = -1;
+  if (mode == 2) {
+    if (!sched_pattern_two_layer(P, groups, hk, lists)) return DVG_OK;
+  } else {
+    SchedCost c;
+    const double x_kb = ceil_div(h->dims.input_size, 16) / 4.0;
+    best = 1e30;
+    for (int d = 0; d <= P / 3; ++d) {
+      const double mk = sched_build(P, L, groups, hk, x_kb, d, c, nullptr);
+      if (mk < best - 1e-9) { best = mk; best_d = d; }
+    }
+    if (const char* fd = getenv("DVG_STEP_SCHED_D")) best_d = std::max(0, std::min(P / 2, atoi(fd)));   // developer override
+    best = sched_build(P, L, groups, hk, x_kb, best_d, c, &lists);
+  }
   size_t depth = 0;
   int l0_max = 0;
   for (auto& li : lists) {
@@ -935,14 +989,16 @@ int lstm_step_build_schedule(dvg_lstm_s* h, int rows) {
   }
   if (l0_max > STEP_XMAX) return DVG_OK;
   std::vector<int> flat(depth * P, -1);
+  size_t placed = 0;
   for (int q = 0; q < P; ++q)
-    for (size_t k = 0; k < lists[q].size(); ++k) flat[k * P + q] = lists[q][k];
+    for (size_t k = 0; k < lists[q].size(); ++k) { flat[k * P + q] = lists[q][k]; ++placed; }
+  if ((int)placed != total) return DVG_OK;          // defensive: a malformed schedule would hang the kernel
   DVG_CUDA(cudaMalloc(&h->sched_dev, sizeof(int) * flat.size()));
   DVG_CUDA(cudaMemcpy(h->sched_dev, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice));
   h->sched_len = (int)flat.size(); h->sched_rows = rows; h->sched_pairs = P;
   if (getenv("DVG_STEP_SCHED_VERBOSE"))
-    fprintf(stderr, "dvg_b200: step schedule rows=%d pairs=%d d=%d depth=%zu model makespan %.1f us (layer-major %.1f)\n", rows, P,
-            best_d, depth, best, sched_build(P, L, groups, hk, x_kb, 0, c, nullptr));
+    fprintf(stderr, "dvg_b200: step schedule mode=%d rows=%d pairs=%d d=%d depth=%zu model makespan %.1f us\n", mode, rows, P,
+            best_d, depth, best);
   return DVG_OK;
 }
 
