@@ -22,7 +22,7 @@ EXPORTS = [
     "dvg_lstm_state_bytes", "dvg_lstm_state_packed_offset", "dvg_lstm_state_repack",
     "dvg_lstm_step", "dvg_lstm_profile", "dvg_gauss_lstm_step",
     "dvg_gp_prepare", "dvg_gp_refresh", "dvg_gp_prepare_factors", "dvg_gp_refresh_factors", "dvg_gp_destroy", "dvg_gp_predict", "dvg_gp_trigger",
-    "dvg_gp_rsample", "dvg_gp_export", "dvg_rollout_step", "dvg_eval_seq_finn", "dvg_rollout_score",
+    "dvg_gp_rsample", "dvg_gp_export", "dvg_rollout_step", "dvg_eval_seq_finn", "dvg_eval_seq", "dvg_rollout_score",
 ]
 
 
@@ -91,6 +91,7 @@ def load():
     lib.dvg_rollout_step.argtypes = [P, P, c_int, c_int, P, c_int, P, P, P, c_int, c_int, P, P, c_int, P, c_int, c_float,
                                      P, P, P, P, P]
     lib.dvg_eval_seq_finn.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]
+    lib.dvg_eval_seq.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]
     lib.dvg_rollout_score.argtypes = [c_int, c_int, c_int, c_int, P, P, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported

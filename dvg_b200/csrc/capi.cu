@@ -445,6 +445,14 @@ int dvg_eval_seq_finn(int n_frames, int n_samples, int n_seq, int channels, int 
                               (cudaStream_t)stream);
 }
 
+int dvg_eval_seq(int n_frames, int n_samples, int n_seq, int channels, int height, int width, const float* gt,
+                 const float* gen, float* ssim, float* psnr, dvg_stream_t stream) {
+  DVG_REQUIRE(gt && gen && ssim && psnr, "null argument");
+  DVG_REQUIRE(n_frames > 0 && n_samples > 0 && n_seq > 0 && channels > 0, "bad sizes");
+  return eval_seq_skimage_launch(n_frames, n_samples, n_seq, channels, height, width, gt, gen, ssim, psnr,
+                                 (cudaStream_t)stream);
+}
+
 int dvg_rollout_score(int n_steps, int n_rollouts, int n_points, int dim, const float* latents, const float* target,
                       float* scores, dvg_stream_t stream) {
   DVG_REQUIRE(latents && target && scores, "null argument");

@@ -162,6 +162,8 @@ int gp_big_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int
 // rollout.cu
 int eval_seq_finn_launch(int T, int S, int B, int C, int H, int W, const float* gt, const float* gen, float* ssim,
                          float* psnr, cudaStream_t stream);
+int eval_seq_skimage_launch(int T, int S, int B, int C, int H, int W, const float* gt, const float* gen, float* ssim,
+                            float* psnr, cudaStream_t stream);
 int rollout_score_launch(int T, int S, int B, int G, const float* out, const float* target, float* scores,
                          cudaStream_t stream);
 

@@ -43,42 +43,60 @@ __global__ void __launch_bounds__(256) rollout_score_kernel(int T, int S, int B,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// finn_eval_seq on the device (utils.py:237-301): per (frame t, sample s, sequence b) the channel-mean SSIM
-// (11x11 Gaussian window, sigma 1.5, 'valid' region, K1=.01, K2=.03, L=1; NaN -> -1) and PSNR = 10 log10(1/mse).
-// The Gaussian window is separable (fspecial_gauss = g (x) g / (sum g)^2): horizontal pass into shared memory, then
-// vertical pass + SSIM map + mean, in blocks of EV_RB output rows so 128x128 frames fit.  One CTA per (t, s, b).
+// Frame metrics on the device: per (frame t, sample s, sequence b) the channel-mean SSIM and PSNR of a generated frame
+// against the ground truth, without the per-frame D2H copy of generate_frames.py:175-178.  Two variants:
+//   EV_FINN     utils.finn_eval_seq (utils.py:237-301): 11x11 Gaussian window (sigma 1.5), 'valid' region, K1=.01,
+//               K2=.03, L=1, population moments, NaN -> -1; PSNR = 10 log10(1 / mse).
+//   EV_SKIMAGE  utils.eval_seq (utils.py:220-234) = legacy skimage.measure.compare_ssim / compare_psnr defaults, the
+//               metric make_gifs actually selects on (generate_frames.py:178): 7x7 uniform window, sample covariance
+//               (x 49/48), K1=.01, K2=.03, data_range 2 for float images, mean over the interior cropped by 3 pixels;
+//               PSNR = 10 log10(R^2 / mse) with R = 1 when min(ground truth) >= 0 else 2.
+// Both windows are separable: horizontal pass into shared memory, then vertical pass + SSIM map + mean, in blocks of
+// EV_RB output rows so 128x128 frames fit.  One CTA per (t, s, b).
 // ---------------------------------------------------------------------------------------------------
 constexpr int EV_RB = 16;     // output rows per block
-constexpr int EV_WIN = 11;
+enum { EV_FINN = 0, EV_SKIMAGE = 1 };
 
-__global__ void __launch_bounds__(256) eval_seq_finn_kernel(int T, int S, int B, int C, int H, int W,
-                                                            const float* __restrict__ gt,
-                                                            const float* __restrict__ gen, float* __restrict__ ssim,
-                                                            float* __restrict__ psnr) {
+template <int MODE>
+__global__ void __launch_bounds__(256) eval_seq_kernel(int T, int S, int B, int C, int H, int W,
+                                                       const float* __restrict__ gt, const float* __restrict__ gen,
+                                                       float* __restrict__ ssim, float* __restrict__ psnr) {
+  constexpr int WIN = MODE == EV_FINN ? 11 : 7;
   extern __shared__ __align__(16) float sm[];
-  __shared__ float s_win[EV_WIN];
-  __shared__ float s_red[2][8];
+  __shared__ float s_win[WIN];
+  __shared__ float s_red[3][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x % B, s = (blockIdx.x / B) % S, t = blockIdx.x / (B * S);
-  const int Wo = W - (EV_WIN - 1), Ho = H - (EV_WIN - 1);
-  float* s_a = sm;                                   // [EV_RB+10][W]
-  float* s_b = s_a + (EV_RB + EV_WIN - 1) * W;       // [EV_RB+10][W]
-  float* s_h = s_b + (EV_RB + EV_WIN - 1) * W;       // [5][EV_RB+10][Wo]
-  if (tid < EV_WIN) {
-    float g[EV_WIN], tot = 0.f;
-    for (int i = 0; i < EV_WIN; ++i) { const float d = (float)(i - EV_WIN / 2); g[i] = expf(-(d * d) / (2.f * 1.5f * 1.5f)); tot += g[i]; }
-    s_win[tid] = g[tid] / tot;
+  const int Wo = W - (WIN - 1), Ho = H - (WIN - 1);
+  float* s_a = sm;                                   // [EV_RB+WIN-1][W]
+  float* s_b = s_a + (EV_RB + WIN - 1) * W;          // [EV_RB+WIN-1][W]
+  float* s_h = s_b + (EV_RB + WIN - 1) * W;          // [5][EV_RB+WIN-1][Wo]
+  if (tid < WIN) {
+    if (MODE == EV_FINN) {
+      float g[WIN], tot = 0.f;
+      for (int i = 0; i < WIN; ++i) { const float d = (float)(i - WIN / 2); g[i] = expf(-(d * d) / (2.f * 1.5f * 1.5f)); tot += g[i]; }
+      s_win[tid] = g[tid] / tot;
+    } else {
+      s_win[tid] = 1.0f / (float)WIN;
+    }
   }
   __syncthreads();
+  const float c1 = MODE == EV_FINN ? 1e-4f : 4e-4f, c2 = MODE == EV_FINN ? 9e-4f : 3.6e-3f;   // (K1 R)^2, (K2 R)^2
+  const float cov_norm = MODE == EV_FINN ? 1.0f : (float)(WIN * WIN) / (float)(WIN * WIN - 1);
   float ssim_c_sum = 0.f, psnr_c_sum = 0.f;
   for (int c = 0; c < C; ++c) {
     const float* A = gt + (((size_t)t * B + b) * C + c) * H * W;
     const float* G = gen + ((((size_t)t * S + s) * B + b) * C + c) * H * W;
-    float sq = 0.f, acc = 0.f;
-    for (int e = tid; e < H * W; e += 256) { const float d = __ldg(A + e) - __ldg(G + e); sq = fmaf(d, d, sq); }
+    float sq = 0.f, acc = 0.f, amin = 3.0e38f;
+    for (int e = tid; e < H * W; e += 256) {
+      const float av = __ldg(A + e);
+      const float d = av - __ldg(G + e);
+      sq = fmaf(d, d, sq);
+      amin = fminf(amin, av);
+    }
     for (int r0 = 0; r0 < Ho; r0 += EV_RB) {
       const int rows_out = Ho - r0 < EV_RB ? Ho - r0 : EV_RB;
-      const int rows_in = rows_out + EV_WIN - 1;
+      const int rows_in = rows_out + WIN - 1;
       __syncthreads();
       for (int e = tid; e < rows_in * W; e += 256) {
         s_a[e] = __ldg(A + (size_t)r0 * W + e);
@@ -89,44 +107,53 @@ __global__ void __launch_bounds__(256) eval_seq_finn_kernel(int T, int S, int B,
         const int i = e / Wo, j = e - i * Wo;
         float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
-        for (int k = 0; k < EV_WIN; ++k) {
+        for (int k = 0; k < WIN; ++k) {
           const float w = s_win[k], x = s_a[i * W + j + k], y = s_b[i * W + j + k];
           m1 = fmaf(w, x, m1); m2 = fmaf(w, y, m2);
           e11 = fmaf(w * x, x, e11); e22 = fmaf(w * y, y, e22); e12 = fmaf(w * x, y, e12);
         }
-        const int o = i * Wo + j, st = (EV_RB + EV_WIN - 1) * Wo;
+        const int o = i * Wo + j, st = (EV_RB + WIN - 1) * Wo;
         s_h[o] = m1; s_h[st + o] = m2; s_h[2 * st + o] = e11; s_h[3 * st + o] = e22; s_h[4 * st + o] = e12;
       }
       __syncthreads();
       for (int e = tid; e < rows_out * Wo; e += 256) {    // vertical pass + SSIM map
         const int i = e / Wo, j = e - i * Wo;
-        const int st = (EV_RB + EV_WIN - 1) * Wo;
+        const int st = (EV_RB + WIN - 1) * Wo;
         float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
-        for (int k = 0; k < EV_WIN; ++k) {
+        for (int k = 0; k < WIN; ++k) {
           const float w = s_win[k];
           const int o = (i + k) * Wo + j;
           m1 = fmaf(w, s_h[o], m1); m2 = fmaf(w, s_h[st + o], m2);
           e11 = fmaf(w, s_h[2 * st + o], e11); e22 = fmaf(w, s_h[3 * st + o], e22); e12 = fmaf(w, s_h[4 * st + o], e12);
         }
-        const float c1 = 1e-4f, c2 = 9e-4f;
-        const float s11 = e11 - m1 * m1, s22 = e22 - m2 * m2, s12 = e12 - m1 * m2;
+        const float s11 = cov_norm * (e11 - m1 * m1), s22 = cov_norm * (e22 - m2 * m2), s12 = cov_norm * (e12 - m1 * m2);
         acc += ((2.f * m1 * m2 + c1) * (2.f * s12 + c2)) / ((m1 * m1 + m2 * m2 + c1) * (s11 + s22 + c2));
       }
     }
-    // block reduction of (acc, sq)
+    // block reduction of (acc, sq, amin)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    for (int o = 16; o > 0; o >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+    }
     __syncthreads();
-    if (lane == 0) { s_red[0][warp] = acc; s_red[1][warp] = sq; }
+    if (lane == 0) { s_red[0][warp] = acc; s_red[1][warp] = sq; s_red[2][warp] = amin; }
     __syncthreads();
     if (tid == 0) {
-      float a = 0.f, q = 0.f;
-      for (int w8 = 0; w8 < 8; ++w8) { a += s_red[0][w8]; q += s_red[1][w8]; }
+      float a = 0.f, q = 0.f, mn = 3.0e38f;
+      for (int w8 = 0; w8 < 8; ++w8) { a += s_red[0][w8]; q += s_red[1][w8]; mn = fminf(mn, s_red[2][w8]); }
       float sv = a / (float)(Ho * Wo);
-      if (sv != sv) sv = -1.f;                                   // utils.py:247-248
+      const float mse = q / (float)(H * W);
+      if (MODE == EV_FINN) {
+        if (sv != sv) sv = -1.f;                                   // utils.py:247-248
+        psnr_c_sum += 10.f * log10f(1.f / mse);                    // utils.py:259-261
+      } else {
+        const float R = mn >= 0.f ? 1.f : 2.f;                     // skimage compare_psnr, float images
+        psnr_c_sum += 10.f * log10f(R * R / mse);
+      }
       ssim_c_sum += sv;
-      psnr_c_sum += 10.f * log10f(1.f / (q / (float)(H * W)));   // utils.py:259-261
     }
   }
   if (tid == 0) {
@@ -136,18 +163,29 @@ __global__ void __launch_bounds__(256) eval_seq_finn_kernel(int T, int S, int B,
   }
 }
 
-int eval_seq_finn_launch(int T, int S, int B, int C, int H, int W, const float* gt, const float* gen, float* ssim,
-                         float* psnr, cudaStream_t stream) {
-  DVG_REQUIRE(H >= EV_WIN && W >= EV_WIN && W <= 256, "frame size %dx%d unsupported (need 11 <= H, 11 <= W <= 256)", H, W);
-  const size_t smem = sizeof(float) * ((size_t)2 * (EV_RB + EV_WIN - 1) * W + 5 * (size_t)(EV_RB + EV_WIN - 1) * (W - EV_WIN + 1));
+template <int MODE>
+static int eval_seq_launch_t(int T, int S, int B, int C, int H, int W, const float* gt, const float* gen, float* ssim,
+                             float* psnr, cudaStream_t stream) {
+  constexpr int WIN = MODE == EV_FINN ? 11 : 7;
+  DVG_REQUIRE(H >= WIN && W >= WIN && W <= 256, "frame size %dx%d unsupported (need %d <= H, %d <= W <= 256)", H, W, WIN, WIN);
+  const size_t smem = sizeof(float) * ((size_t)2 * (EV_RB + WIN - 1) * W + 5 * (size_t)(EV_RB + WIN - 1) * (W - WIN + 1));
   static bool configured = false;
   if (!configured) {
-    DVG_CUDA(cudaFuncSetAttribute(eval_seq_finn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DVG_CUDA(cudaFuncSetAttribute(eval_seq_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  eval_seq_finn_kernel<<<T * S * B, 256, smem, stream>>>(T, S, B, C, H, W, gt, gen, ssim, psnr);
+  eval_seq_kernel<MODE><<<T * S * B, 256, smem, stream>>>(T, S, B, C, H, W, gt, gen, ssim, psnr);
   DVG_LAUNCH_CHECK();
   return DVG_OK;
+}
+
+int eval_seq_finn_launch(int T, int S, int B, int C, int H, int W, const float* gt, const float* gen, float* ssim,
+                         float* psnr, cudaStream_t stream) {
+  return eval_seq_launch_t<EV_FINN>(T, S, B, C, H, W, gt, gen, ssim, psnr, stream);
+}
+int eval_seq_skimage_launch(int T, int S, int B, int C, int H, int W, const float* gt, const float* gen, float* ssim,
+                            float* psnr, cudaStream_t stream) {
+  return eval_seq_launch_t<EV_SKIMAGE>(T, S, B, C, H, W, gt, gen, ssim, psnr, stream);
 }
 
 int rollout_score_launch(int T, int S, int B, int G, const float* out, const float* target, float* scores,

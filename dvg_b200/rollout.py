@@ -298,6 +298,19 @@ def eval_seq_finn(gt: torch.Tensor, gen: torch.Tensor):
     return out[0], out[1]
 
 
+def eval_seq(gt: torch.Tensor, gen: torch.Tensor):
+    """``utils.eval_seq`` (utils.py:220-234: legacy skimage ``compare_ssim`` / ``compare_psnr`` defaults -- the metric
+    ``make_gifs`` ranks the samples by, generate_frames.py:178,188-189) for all S samples at once, on the device.
+    Same layouts as :func:`eval_seq_finn`."""
+    T, S, B, C, H, W = gen.shape
+    assert gt.shape == (T, B, C, H, W) and gt.is_cuda and gen.is_cuda
+    gt, gen = gt.contiguous().float(), gen.contiguous().float()
+    out = torch.empty(2, S, B, T, device=gen.device, dtype=torch.float32)
+    _capi.check(_capi.load().dvg_eval_seq(T, S, B, C, H, W, _capi.ptr(gt), _capi.ptr(gen), _capi.ptr(out[0]),
+                                          _capi.ptr(out[1]), _capi.stream_ptr()), "dvg_eval_seq")
+    return out[0], out[1]
+
+
 # -------------------------------------------------------------------------------------------------------
 # Pixel-space drivers (encoder / decoder are the reference conv nets on the stock PyTorch path)
 # -------------------------------------------------------------------------------------------------------
@@ -423,14 +436,15 @@ def trigger_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x0,
 @torch.no_grad()
 def make_gifs(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample,
               eps: Optional[Dict] = None, resample_every: Optional[int] = 15, last_frame_skip=False,
-              variant="bf16x3"):
+              variant="bf16x3", metric="skimage"):
     """The computational part of ``make_gifs`` (generate_frames.py:107-217) with everything on the device:
     pass A (approximate posterior, GP mean), pass B (``nsample`` diverse futures, batched), SSIM / PSNR of every
     generated frame against the ground truth and the best-of-N choice per sequence (the gif writing is out of scope).
 
     Returns dict(posterior [n_eval][B,...], samples [n_eval][S,B,...], ssim [B,S,T_f], psnr [B,S,T_f], best [B]).
-    Metrics are the reference's self-contained ``finn_eval_seq`` variant (utils.py:237-301); the skimage-based
-    ``eval_seq`` the script calls is not reproducible here (skimage absent)."""
+    ``metric="skimage"`` (default) is ``utils.eval_seq`` -- what the script calls (generate_frames.py:178) -- restated
+    from the documented legacy skimage defaults (skimage itself is absent here: unpinned); ``metric="finn"`` is the
+    self-contained ``finn_eval_seq`` variant (utils.py:237-301), pinned to the reference's own functions."""
     from . import shard
     posterior = posterior_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval,
                                   last_frame_skip)
@@ -438,7 +452,7 @@ def make_gifs(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past
                               eps=eps, resample_every=resample_every, last_frame_skip=last_frame_skip, variant=variant)
     gt = torch.stack([x[t] for t in range(n_past, n_eval)])                    # [T_f, B, C, H, W]
     gen = torch.stack([samples[t] for t in range(n_past, n_eval)])             # [T_f, S, B, C, H, W]
-    ssim, psnr = eval_seq_finn(gt, gen)                                        # [S, B, T_f]
+    ssim, psnr = (eval_seq if metric == "skimage" else eval_seq_finn)(gt, gen)  # [S, B, T_f]
     best = shard.select_best(ssim.mean(2), higher_is_better=True)              # generate_frames.py:188-189,207
     return {"posterior": posterior, "samples": samples, "ssim": ssim.permute(1, 0, 2), "psnr": psnr.permute(1, 0, 2),
             "best": best}

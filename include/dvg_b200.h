@@ -236,6 +236,13 @@ DVG_API int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows,
 DVG_API int dvg_eval_seq_finn(int n_frames, int n_samples, int n_seq, int channels, int height, int width,
                       const float* gt, const float* gen, float* ssim, float* psnr, dvg_stream_t stream);
 
+/* utils.eval_seq on the device (utils.py:220-234; the metric make_gifs selects on, generate_frames.py:178,188-189):
+ * channel-mean SSIM and PSNR with the legacy skimage.measure.compare_ssim / compare_psnr defaults for float images --
+ * 7x7 uniform window, sample covariance, K1=.01, K2=.03, data_range 2, mean over the interior cropped by 3 pixels;
+ * PSNR = 10 log10(R^2/mse), R = 1 when min(gt) >= 0 else 2.  Same layouts as dvg_eval_seq_finn. */
+DVG_API int dvg_eval_seq(int n_frames, int n_samples, int n_seq, int channels, int height, int width,
+                 const float* gt, const float* gen, float* ssim, float* psnr, dvg_stream_t stream);
+
 /* Device-side scoring pass of the best-of-N selection (the reference scores every sample on the host after a
  * D2H copy per frame, generate_frames.py:175-178,185-190): scores[s, b] = mean over (t, g) of
  * (latents[t, s*B + b, g] - target[t, b, g])^2.  latents [T, S*B, dim] dense, target [T, B, dim], scores [S, B]. */
