@@ -334,5 +334,23 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src
       : "memory");
 }
 
+
+// 16 consecutive columns as raw words + wait.
+__device__ __forceinline__ void tmem_ld16u_wait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+
+// overloads by register-array size
+__device__ __forceinline__ void tmem_ldw_wait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32_wait(taddr, r); }
+__device__ __forceinline__ void tmem_ldw_wait(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16u_wait(taddr, r); }
+
 }  // namespace ptx
 }  // namespace dvg
