@@ -231,27 +231,39 @@ def run_ours(args):
     value = frames_per_step / (ms_per_step * 1e-3)
     n_trig = int(masks.sum().item())
 
-    # ---- e2e: public streaming API (LatentRolloutPipeline) with pinned HOST buffers.  Every step copies its
-    #      inputs H2D and its outputs D2H inside the timed region; copies of neighbouring steps overlap compute.
-    pipe = LatentRolloutPipeline(eng, T)
-    post = (lambda o: select_best_of(o))
-
-    def select_best_of(o):
+    # ---- e2e: public streaming API (LatentRolloutPipeline) with pinned HOST buffers.  Every rollout copies its
+    #      inputs H2D and its results D2H inside the timed region; copies of neighbouring rollouts overlap compute.
+    #      Results that leave the device: the trigger masks, the [S, B] score matrix, the best-of-N choice and the
+    #      WINNING futures' decoder inputs [B, T, G] -- as in the reference's output stage (generate_frames.py:185-217)
+    #      and SURVEY 8e, the non-selected futures never travel.
+    def e2e_post(o):
         sc = score_rollouts(o, target, S, B)
-        return shard.select_best(shard.gather_scores(sc, world * S), higher_is_better=False)
+        allsc = shard.gather_scores(sc, world * S)
+        best = shard.select_best(allsc, higher_is_better=False)
+        winners = shard.gather_winners(o.view(T, S, B, w["G"]).permute(1, 2, 0, 3), best, world * S)   # [B, T, G]
+        return sc, best, winners
 
+    pipe = LatentRolloutPipeline(eng, T, post=e2e_post, full_output=False, capture_post=(world == 1))
     # correctness of the pipelined path first (host-injected noise == the device-resident run), untimed
-    chk, _, _ = pipe.result(pipe.submit(lat_h, eps_h, post=post))
-    assert torch.equal(chk, out.cpu()), "pipelined e2e result differs from the device-resident run"
+    graph.replay()
+    torch.cuda.synchronize()
+    ref_out = out.clone()
+    _, masks_chk, extra_chk = pipe.result(pipe.submit(lat_h, eps_h))
+    if world == 1:
+        b_ref = held["best"].cpu()
+        want = ref_out.view(T, S, B, w["G"])[:, b_ref, torch.arange(B)].permute(1, 0, 2)
+        assert torch.equal(extra_chk[1], b_ref) and torch.equal(extra_chk[2], want.cpu()), \
+            "pipelined e2e result differs from the device-resident run"
+    assert torch.equal(masks_chk, masks.cpu()), "pipelined e2e trigger masks differ from the device-resident run"
     for _ in range(3):
-        pipe.submit(lat_h, None, post=post)
+        pipe.submit(lat_h, None)
     pipe.drain()
     sync_all()
     t0 = time.perf_counter()
     e0.record()
     # timed: latents from pinned host memory every step, rsample noise drawn on the device (as gpytorch does)
-    tickets = [pipe.submit(lat_h, None, post=post) for _ in range(args.steps)]
-    out_last, masks_last, best_last = pipe.result(tickets[-1])
+    tickets = [pipe.submit(lat_h, None) for _ in range(args.steps)]
+    _, masks_last, extra_last = pipe.result(tickets[-1])
     for st in (pipe.s_in, pipe.s_cmp, pipe.s_out):
         torch.cuda.current_stream().wait_stream(st)      # e1 is ordered after all three pipeline streams
     e1.record()
@@ -262,7 +274,7 @@ def run_ours(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = frames_per_step / (ms2.item() / args.steps * 1e-3)
     h2d = lat_h.numel() * 4
-    d2h = out_last.numel() * 4 + masks_last.numel()
+    d2h = pipe.d2h_bytes()
 
     # ---- roofline: time the dominant kernel (LSTM layer GEMM) live, events between launches ----
     roof = None
@@ -289,9 +301,11 @@ def run_ours(args):
                        "triggered_rollout_steps": n_trig, "scope": "hot path only; encoder/decoder convs excluded"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms2.item() / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-                    "how": "LatentRolloutPipeline: pinned host in/out, H2D / compute graph / D2H on three streams, "
-                           "double buffered (copies of neighbouring steps overlap compute); latents H2D every step, rsample noise "
-                           "drawn on the device inside the timed region, decoder inputs + trigger masks D2H every step"},
+                    "how": "LatentRolloutPipeline: pinned host in/out, H2D / compute graph / D2H on three streams, two buffer "
+                           "sets each with its own graph (copies of neighbouring rollouts overlap compute); all latents H2D every "
+                           "rollout, rsample noise drawn on the device inside the timed region; D2H every rollout: trigger masks, "
+                           "score matrix, best-of-N choice and the winning futures' decoder inputs [B,T,G] (non-selected futures "
+                           "stay on the device, as in generate_frames.py:185-217)"},
             "gpu_launches": launches_per_rollout(w, T) * args.steps,
             "clocks": clocks,
             "roofline": roof,

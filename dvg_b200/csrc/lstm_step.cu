@@ -689,9 +689,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       //      dim for every rollout there: two threads per (rollout, dim) task -- |Linv k|^2 and |L_q^T k|^2 -- with the
       //      factors staged in the (now idle) transpose buffers.  Nobody in this launch waits for the result except
       //      the finalisers and the end-of-kernel restore.
-      if (k == 0 && p.trig.enabled && (int)blockIdx.x >= (int)gridDim.x - p.trig.D) {
+      // (small grids -- fewer CTAs than latent dims -- take several dims per CTA)
+      const int trig_ctas = p.trig.D < (int)gridDim.x ? p.trig.D : (int)gridDim.x;
+      if (k == 0 && p.trig.enabled && (int)gridDim.x - 1 - (int)blockIdx.x < trig_ctas)
+      for (int d = (int)gridDim.x - 1 - (int)blockIdx.x; d < p.trig.D; d += trig_ctas) {
         const StepTrig& g = p.trig;
-        const int d = (int)gridDim.x - 1 - (int)blockIdx.x, MP = g.mp;
+        const int MP = g.mp;
         float* s_linv = reinterpret_cast<float*>(s_ebuf);
         float* s_lqt = s_linv + MP * MP;
         float* s_z = s_lqt + MP * MP;

@@ -202,71 +202,86 @@ class RolloutEngine:
 class LatentRolloutPipeline:
     """Host-facing streaming driver for ``RolloutEngine``: ``submit(lat_host, eps_host)`` enqueues one complete
     latent rollout whose inputs live in pinned HOST memory and returns a ticket; ``result(ticket)`` yields the
-    pinned host output (and the trigger masks).  Three CUDA streams and two buffer sets overlap the H2D copy of
-    rollout k+1 and the D2H copy of rollout k-1 with the compute graph of rollout k (the per-step D2H + host numpy
-    of the reference, generate_frames.py:175-176,230, is what this replaces)."""
+    pinned host results.  Three CUDA streams and two complete buffer sets -- each with its own captured CUDA graph, so
+    the H2D copy lands directly in the buffer the graph reads and the D2H copy leaves from the buffer it wrote, no
+    staging copies -- overlap the H2D copy of rollout k+1 and the D2H copy of rollout k-1 with the compute graph of
+    rollout k (the per-step D2H + host numpy of the reference, generate_frames.py:175-176,230, is what this replaces).
 
-    def __init__(self, engine: "RolloutEngine", T: int):
+    ``post(out_dev)`` (optional) is captured at the end of each graph (best-of-N scoring / selection) and returns a
+    tuple of device tensors; they travel to the host with the trigger masks.  ``full_output=False`` skips the D2H
+    copy of the complete [T, S*B, G] decoder-input tensor: as in the reference's own output stage only the selected
+    futures leave the device (generate_frames.py:185-217; SURVEY 8e "only winner frames travel")."""
+
+    def __init__(self, engine: "RolloutEngine", T: int, post=None, full_output: bool = True, capture_post: bool = True):
         self.eng = engine
+        self.post, self.capture_post = post, capture_post
         dev, R, G, S, D, B = engine.dev, engine.R, engine.G, engine.S, engine.D, engine.B
-        self.T = T
-        self.lat = torch.empty(T, R, G, device=dev)
-        self.eps = torch.empty(T, S, D, B, device=dev)
-        self.out = torch.empty(T, R, G, device=dev)
-        self.masks = torch.zeros(T, S, dtype=torch.uint8, device=dev)
-        self.graph = engine.capture_latent_rollout(self.lat, self.eps, self.out, masks=self.masks)
-        self.stage_in = [(torch.empty_like(self.lat), torch.empty_like(self.eps)) for _ in range(2)]
-        self.stage_out = [(torch.empty_like(self.out), torch.empty_like(self.masks)) for _ in range(2)]
-        self.host_out = [(torch.empty(T, R, G).pin_memory(), torch.empty(T, S, dtype=torch.uint8).pin_memory())
-                         for _ in range(2)]
+        self.T, self.full_output = T, full_output
+        self.lat = [torch.empty(T, R, G, device=dev) for _ in range(2)]
+        self.eps = [torch.empty(T, S, D, B, device=dev) for _ in range(2)]
+        self.out = [torch.empty(T, R, G, device=dev) for _ in range(2)]
+        self.masks = [torch.zeros(T, S, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.extra = [None, None]
+        self.graph = []
+        for k in range(2):
+            def hook(k=k):
+                self.extra[k] = tuple(post(self.out[k]))
+            self.graph.append(engine.capture_latent_rollout(self.lat[k], self.eps[k], self.out[k], masks=self.masks[k],
+                                                            post=hook if post is not None and capture_post else None))
+            if post is not None and not capture_post:      # (e.g. post holds NCCL collectives: enqueue it eagerly)
+                hook()
+        self.host_out = [torch.empty(T, R, G).pin_memory() if full_output else None for _ in range(2)]
+        self.host_masks = [torch.empty(T, S, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.host_extra = [tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (self.extra[k] or ()))
+                           for k in range(2)]
         self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
         self.ev_cmp = [torch.cuda.Event() for _ in range(2)]
         self.ev_out = [torch.cuda.Event() for _ in range(2)]
-        self.ev_free_in = [torch.cuda.Event() for _ in range(2)]
         self.n = 0
-        for e in self.ev_out + self.ev_free_in:
+        for e in self.ev_out + self.ev_cmp:
             e.record()
 
-    def submit(self, lat_host: torch.Tensor, eps_host: Optional[torch.Tensor] = None, post=None):
+    def d2h_bytes(self) -> int:
+        n = self.host_masks[0].numel() + sum(t.numel() * t.element_size() for t in self.host_extra[0])
+        return n + (self.host_out[0].numel() * 4 if self.full_output else 0)
+
+    def submit(self, lat_host: torch.Tensor, eps_host: Optional[torch.Tensor] = None):
         """Enqueue one rollout.  ``eps_host`` None: the rsample noise is drawn on the device (torch.randn on the
-        compute stream, like gpytorch's rsample does in the reference) instead of being shipped from the host.
-        ``post(out_dev)`` (optional) runs on the compute stream after the graph (e.g. the best-of-N scoring) and
-        its result is returned by ``result``."""
+        compute stream, like gpytorch's rsample does in the reference) instead of being shipped from the host."""
         k = self.n & 1
         with torch.cuda.stream(self.s_in):
-            self.s_in.wait_event(self.ev_free_in[k])           # staging buffer consumed by an earlier rollout
-            self.stage_in[k][0].copy_(lat_host, non_blocking=True)
+            self.s_in.wait_event(self.ev_cmp[k])               # the graph that read buffer set k two rollouts ago is done
+            self.lat[k].copy_(lat_host, non_blocking=True)
             if eps_host is not None:
-                self.stage_in[k][1].copy_(eps_host, non_blocking=True)
+                self.eps[k].copy_(eps_host, non_blocking=True)
             self.ev_in[k].record()
         with torch.cuda.stream(self.s_cmp):
             self.s_cmp.wait_event(self.ev_in[k])
-            self.lat.copy_(self.stage_in[k][0], non_blocking=True)
-            if eps_host is not None:
-                self.eps.copy_(self.stage_in[k][1], non_blocking=True)
-            else:
-                self.eps.normal_()
-            self.ev_free_in[k].record()
-            self.graph.replay()
-            extra = post(self.out) if post is not None else None
-            self.s_cmp.wait_event(self.ev_out[k])              # host_out/stage_out[k] drained by the D2H stream
-            self.stage_out[k][0].copy_(self.out, non_blocking=True)
-            self.stage_out[k][1].copy_(self.masks, non_blocking=True)
+            self.s_cmp.wait_event(self.ev_out[k])              # out[k] / masks[k] / extra[k] drained by the D2H stream
+            if eps_host is None:
+                self.eps[k].normal_()
+            self.graph[k].replay()
+            if self.post is not None and not self.capture_post:
+                for dst, src in zip(self.extra[k], self.post(self.out[k])):
+                    dst.copy_(src)
             self.ev_cmp[k].record()
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_cmp[k])
-            self.host_out[k][0].copy_(self.stage_out[k][0], non_blocking=True)
-            self.host_out[k][1].copy_(self.stage_out[k][1], non_blocking=True)
+            if self.full_output:
+                self.host_out[k].copy_(self.out[k], non_blocking=True)
+            self.host_masks[k].copy_(self.masks[k], non_blocking=True)
+            for h, d in zip(self.host_extra[k], self.extra[k] or ()):
+                h.copy_(d, non_blocking=True)
             self.ev_out[k].record()
         self.n += 1
-        return (self.n - 1, extra)
+        return self.n - 1
 
     def result(self, ticket):
-        idx, extra = ticket
-        k = idx & 1
+        """(host outputs [T, S*B, G] or None, host masks [T, S], tuple of host copies of ``post``'s tensors)."""
+        k = ticket & 1
         self.ev_out[k].synchronize()
-        return self.host_out[k][0], self.host_out[k][1], extra
+        return self.host_out[k], self.host_masks[k], self.host_extra[k]
 
     def drain(self):
         for s in (self.s_in, self.s_cmp, self.s_out):

@@ -67,11 +67,12 @@ def gather_winners(local_frames: torch.Tensor, best: torch.Tensor, n_rollouts: i
     rank = dist.get_rank(group) if world > 1 else 0
     first, cnt = shard_rollouts(n_rollouts, world, rank)
     B = best.shape[0]
-    out = torch.zeros((B,) + tuple(local_frames.shape[2:]), dtype=local_frames.dtype, device=local_frames.device)
+    # static-shape masked gather (no nonzero / host sync: usable inside CUDA-graph capture)
     mine = (best >= first) & (best < first + cnt)
-    idx = torch.nonzero(mine, as_tuple=False).flatten()
-    if idx.numel():
-        out[idx] = local_frames[(best[idx] - first), idx]
+    local = (best - first).clamp(0, max(cnt - 1, 0))
+    cols = torch.arange(B, device=best.device)
+    out = local_frames[local, cols]
+    out = torch.where(mine.reshape((B,) + (1,) * (out.dim() - 1)), out, torch.zeros((), dtype=out.dtype, device=out.device))
     if world > 1:
         dist.all_reduce(out, group=group)
     return out

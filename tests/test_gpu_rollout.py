@@ -148,6 +148,91 @@ def test_cuda_graph_latent_rollout_equals_eager():
     assert 0 < int(m_e.sum()) < m_e.numel()
 
 
+def test_streaming_pipeline_matches_direct_rollout():
+    """LatentRolloutPipeline (pinned host in, two graph-backed buffer sets, results D2H) against the direct engine call,
+    with full outputs and with winners-only results (post hook captured in the graphs)."""
+    from dvg_b200 import shard
+    from dvg_b200.rollout import LatentRolloutPipeline, RolloutConfig, RolloutEngine, score_rollouts
+    from util import crafted_trigger_case
+    B, S, T, W = 10, 12, 16, 6
+    sd = lstm_ref.random_lstm_state_dict(G, G, H, L, seed=5)
+    gp_sd, lik_sd, lat, eps, jumps = crafted_trigger_case(G, M, B, S, T, W, seed=2)
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=W))
+    out_d = torch.empty(T, S * B, G, device="cuda")
+    m_d = torch.zeros(T, S, dtype=torch.uint8, device="cuda")
+    with torch.no_grad():
+        eng.reset()
+        eng.latent_rollout(lat.cuda(), eps.cuda(), out_d, masks=m_d)
+    target = lat[:, :B].cuda().contiguous()
+
+    def post(o):
+        sc = score_rollouts(o, target, S, B)
+        best = shard.select_best(sc, higher_is_better=False)
+        return sc, best, shard.gather_winners(o.view(T, S, B, G).permute(1, 2, 0, 3), best, S)
+
+    sc_d, best_d, win_d = post(out_d)
+    lat_h, eps_h = lat.pin_memory(), eps.pin_memory()
+    with torch.no_grad():
+        full = LatentRolloutPipeline(eng, T)
+        tickets = [full.submit(lat_h, eps_h) for _ in range(3)]          # exercises both buffer sets
+        for tk in tickets:
+            o, m, extra = full.result(tk)
+            assert extra == () and torch.equal(o, out_d.cpu()) and torch.equal(m, m_d.cpu())
+        win = LatentRolloutPipeline(eng, T, post=post, full_output=False)
+        tickets = [win.submit(lat_h, eps_h) for _ in range(3)]
+        for tk in tickets:
+            o, m, extra = win.result(tk)
+            assert o is None and torch.equal(m, m_d.cpu())
+            assert torch.equal(extra[0], sc_d.cpu()) and torch.equal(extra[1], best_d.cpu())
+            assert torch.equal(extra[2], win_d.cpu())
+        assert win.d2h_bytes() == m_d.numel() + sc_d.numel() * 4 + best_d.numel() * 8 + win_d.numel() * 4
+    assert 0 < int(m_d.sum())
+
+
+def test_many_rollouts_fire_in_the_same_step():
+    """Stress of the end-of-kernel restore + resample: most rollouts jump (and fire) at the same time step, more
+    (rollout, dim) problems than CTAs; checked against the sequential oracle like the crafted case."""
+    from dvg_b200.rollout import RolloutConfig, RolloutEngine
+    from util import check_latent_rollout, crafted_trigger_case
+    B, S, T, W = 10, 40, 12, 6
+    sd = lstm_ref.random_lstm_state_dict(G, G, H, L, seed=9)
+    gp_sd, lik_sd, lat, eps, _ = crafted_trigger_case(G, M, B, S, T, W, seed=3, n_jumps=1)
+    g = torch.Generator().manual_seed(11)
+    lat = -0.8 + 0.1 * torch.tanh(torch.randn(T, S * B, G, generator=g))
+    for s in range(S):
+        if s % 4 != 3:                                    # 30 of the 40 rollouts jump together at t = 8
+            lat[8, s * B:(s + 1) * B] = 0.75 + 0.2 * torch.tanh(torch.randn(B, G, generator=g))
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=W, variant="bf16x3"))
+    out = torch.empty(T, S * B, G, device="cuda")
+    masks = torch.zeros(T, S, dtype=torch.uint8, device="cuda")
+    values = torch.zeros(T, S, device="cuda")
+    with torch.no_grad():
+        eng.latent_rollout(lat.cuda(), eps.cuda(), out, masks=masks, values=values)
+    torch.cuda.synchronize()
+    checked, fired = check_latent_rollout(sd, gp_sd, lik_sd, lat, eps, out.cpu(), masks.cpu(), values.cpu(), B, W)
+    assert int(masks[8].sum()) >= 25, masks[8].tolist()
+    assert fired >= 25 and checked > 100
+
+
+@pytest.mark.parametrize("env", [{"DVG_STEP_SCHED": "2"}, {"DVG_STEP_SCHED": "1"}, {"DVG_STEP_PDL": "0"}])
+def test_step_kernel_developer_switches(env):
+    """The opt-in item schedules and the PDL switch of the step kernel must not change results: re-run the
+    config-shape LSTM parity tests (R = 5000 is the shape the two-layer pattern applies to) in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_lstm.py", "-q", "-x", "-k", "config_shapes or full_size"],
+                       cwd=root, env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_score_rollouts_matches_torch():
     from dvg_b200.rollout import score_rollouts
     T, S, B = 7, 5, 6
