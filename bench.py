@@ -43,7 +43,7 @@ WORKLOADS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
 # capture (profiles/r01_lstm_step.md); keyed by (workload, variant).
-NCU_TRAFFIC_BYTES = {("kth_s100", "bf16x3"): 34.9e6}
+NCU_TRAFFIC_BYTES = {("kth_s100", "bf16x3"): 34.6e6}
 
 
 def peaks():

@@ -449,6 +449,24 @@ def trigger_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x0,
 
 
 @torch.no_grad()
+def plot_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample=5,
+                 eps: Optional[Dict] = None, resample_at: Sequence[int] = (10,), last_frame_skip=False, variant="bf16x3"):
+    """The computational part of ``plot`` (train.py:256-335), the sampling pass run during training: ``nsample`` futures
+    with ONE GP resample (at step 10, train.py:283-285), and per sequence the sample with the smallest summed squared
+    pixel error over all ``n_eval`` frames (strict ``<`` scan of train.py:303-310 == first minimum).
+
+    Returns dict(samples [n_eval][S,B,...], sse [S,B], best [B])."""
+    samples = diverse_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample, eps=eps,
+                              resample_every=None, resample_at=list(resample_at), last_frame_skip=last_frame_skip,
+                              variant=variant)
+    S, B = nsample, x[0].shape[0]
+    sse = torch.zeros(S, B, device=x[0].device)
+    for t in range(n_eval):
+        d = samples[t].float() - x[t].float().unsqueeze(0)
+        sse += d.reshape(S, B, -1).pow(2).sum(2)
+    return {"samples": samples, "sse": sse, "best": sse.argmin(0)}
+
+
 def make_gifs(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample,
               eps: Optional[Dict] = None, resample_every: Optional[int] = 15, last_frame_skip=False,
               variant="bf16x3", metric="skimage"):

@@ -233,6 +233,34 @@ def test_step_kernel_developer_switches(env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_plot_rollout_matches_sequential_oracle():
+    """train.py:256-310 plot(): 5 futures, one resample at step 10, best-of-5 by summed squared error."""
+    from dvg_b200.rollout import plot_rollout
+    sd, gp_sd, lik_sd = _models(seed=7)
+    B, S, n_past, n_eval = 6, 5, 3, 14
+    g = torch.Generator().manual_seed(2)
+    x = [torch.rand(B, G, generator=g) for _ in range(n_eval)]
+    eps = {(s, 10): torch.randn(G, B, generator=g) for s in range(S)}
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    gpu = ToyCodec("cuda", torch.float32)
+    got = plot_rollout(fp, gp, lik, gpu.encoder, gpu.decoder, [t.cuda() for t in x], n_past, n_eval, S, eps=eps)
+    cpu = ToyCodec("cpu", torch.float64)
+    om = rollout_ref.OracleModels(lstm_ref.to_dtype(sd, torch.float64), gp_sd, lik_sd, cpu.encoder, cpu.decoder,
+                                  dtype=torch.float64, gp_mode="direct")
+    ref = rollout_ref.diverse_rollout(om, [t.double() for t in x], n_past, n_eval, S, eps, resample_every=None,
+                                      resample_at=[10])
+    sse = torch.zeros(S, B, dtype=torch.float64)
+    for s in range(S):
+        for t in range(n_eval):
+            assert relerr(got["samples"][t][s], ref[s][t]) < 5e-4, (s, t)
+            sse[s] += (x[t].double() - ref[s][t]).pow(2).reshape(B, -1).sum(1)
+    assert relerr(got["sse"], sse) < 1e-3
+    assert got["best"].cpu().tolist() == sse.argmin(0).tolist()
+    # the samples differ only from the resample step on
+    assert torch.equal(got["samples"][9][0], got["samples"][9][1]) and not torch.equal(got["samples"][10][0], got["samples"][10][1])
+
+
 def test_score_rollouts_matches_torch():
     from dvg_b200.rollout import score_rollouts
     T, S, B = 7, 5, 6
@@ -291,3 +319,15 @@ def test_make_gifs_pixel_space_with_reference_convnets():
             want[:, s] = a
         assert np.abs(out["ssim"].cpu().numpy() - want).max() < 2e-3, metric
     enc.cpu(); dec.cpu()
+
+
+@pytest.mark.parametrize("T,S,B,Gd", [(39, 100, 50, 90), (5, 3, 7, 90), (4, 9, 5, 10), (3, 2, 3, 128), (6, 5, 5, 66)])
+def test_score_rollouts_shapes(T, S, B, Gd):
+    """Streaming scoring kernel: row counts that are not multiples of 8, latent sizes not multiples of 4."""
+    from dvg_b200.rollout import score_rollouts
+    g = torch.Generator().manual_seed(T * 100 + S)
+    out = torch.randn(T, S * B, Gd, generator=g).cuda()
+    target = torch.randn(T, B, Gd, generator=g).cuda()
+    got = score_rollouts(out, target, S, B)
+    want = (out.view(T, S, B, Gd) - target.view(T, 1, B, Gd)).double().pow(2).mean(dim=(0, 3))
+    assert relerr(got, want) < 1e-5
