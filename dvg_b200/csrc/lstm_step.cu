@@ -269,20 +269,26 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         const int rg = j / f.n_tiles, nt = j % f.n_tiles;
         int rt = rg * CM + (int)rank;
         if (rt >= p.row_tiles) rt = p.row_tiles - 1;      // padding CTA of an odd last group: loads stay in bounds
-        const int KB = f.kb_rec + f.kb_in;
+        // (phase fields are copied to registers once per item: the phase index is dynamic, and register-indexed
+        //  constant-bank loads inside the k-block loops were ~100 cycles each on the issue path)
+        const int kb_rec = f.kb_rec, kb_in = f.kb_in;
+        const int KB = kb_rec + kb_in;
         const uint32_t b_half = (uint32_t)f.n_tile * 64u, b_part = (uint32_t)f.n_tile * 128u;
-        const bool layer0 = f.wait_flags == nullptr;
+        const int* wait_flags = f.wait_flags;
+        const bool layer0 = wait_flags == nullptr;
+        const uint8_t* a_rec = f.a_rec;
+        const uint8_t* wbase = f.w;
         const uint8_t* a_in = f.a_in;
-        if (layer0) a_in += (size_t)nt * p.row_tiles * f.kb_in * (2u * TC_A_IMG);
+        if (layer0) a_in += (size_t)nt * p.row_tiles * kb_in * (2u * TC_A_IMG);
         for (int i = 0; i < KB; ++i) {
-          const bool rec = i < f.kb_rec;
-          const int kb = rec ? i : i - f.kb_rec;
+          const bool rec = i < kb_rec;
+          const int kb = rec ? i : i - kb_rec;
           // The weight half of a stage never depends on this launch: request it as soon as the stage is free, THEN
           // wait for the activation k-block (dependency counter / x-pack) -- half of the stage's bytes are already in
           // flight while the producing pair is still in its epilogue.
           ptx::mbar_wait(empty_bar(s), phs ^ 1u);
-          const int wk = rec ? f.kb_in + kb : kb;          // weight K order: [input | recurrent]
-          const uint8_t* bsrc = f.w + (size_t)(nt * KB + wk) * (2u * b_part) + rank * b_half;
+          const int wk = rec ? kb_in + kb : kb;            // weight K order: [input | recurrent]
+          const uint8_t* bsrc = wbase + (size_t)(nt * KB + wk) * (2u * b_part) + rank * b_half;
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint32_t sb = sa + a_bytes;
           ptx::mbar_expect_tx(full_bar(s), a_bytes + nparts * b_half);
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           if (nparts == 2) ptx::bulk_g2s_hint(sb + b_half, bsrc + b_part, b_half, full_bar(s), pol_keep);
           if (!rec) {
             if (!layer0) {
-              poll_ge(f.wait_flags + rg * f.kb_in + kb, 2, item);
+              poll_ge(wait_flags + rg * kb_in + kb, 2, item);
               ptx::fence_proxy_async_all();       // generic-proxy writes of the producing pair -> visible to our TMA
             } else if (kb == 0) {
               ptx::mbar_wait(xready_bar(xj), 0);   // our own epilogue warps packed this item's x rows
@@ -299,8 +305,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
             }
             if (pm < 3 && kb == 0) TRACE(2 + pm * 8 + 1);
           }
-          const uint8_t* asrc = rec ? f.a_rec + (size_t)(rt * f.kb_rec + kb) * (2u * TC_A_IMG)
-                                    : a_in + (size_t)(rt * f.kb_in + kb) * (2u * TC_A_IMG);
+          const uint8_t* asrc = rec ? a_rec + (size_t)(rt * kb_rec + kb) * (2u * TC_A_IMG)
+                                    : a_in + (size_t)(rt * kb_in + kb) * (2u * TC_A_IMG);
           if (rec || layer0) ptx::bulk_g2s_hint(sa, asrc, a_bytes, full_bar(s), pol_stream);
           else ptx::bulk_g2s(sa, asrc, a_bytes, full_bar(s));        // h' of the layer below: re-read by every N tile
           if (++s == p.stages) { s = 0; phs ^= 1u; }
@@ -317,7 +323,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         const int item = item_at(k);
         if (item < 0) break;
         const StepPhase& f = p.ph[phase_of(item)];
-        const int KB = f.kb_rec + f.kb_in;
+        const int kb_rec = f.kb_rec, in_ksteps = f.in_ksteps;
+        const int KB = kb_rec + f.kb_in;
         if (rank == 0) {
           // ===================== MMA issuer (leader CTA) =====================
           const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, f.n_tile);
@@ -330,8 +337,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           uint32_t accum = 0;
           for (int i = 0; i < KB; ++i) {
             int ks = TC_KBLK / 16;
-            if (i >= f.kb_rec) {
-              const int left = f.in_ksteps - (i - f.kb_rec) * (TC_KBLK / 16);
+            if (i >= kb_rec) {
+              const int left = in_ksteps - (i - kb_rec) * (TC_KBLK / 16);
               ks = left < ks ? left : ks;
             }
             ptx::mbar_wait(full_bar(s), phs);
@@ -609,7 +616,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         // through the transpose buffer so the [rows, G] output is written in full row segments.
         const int ncol_half = f.n_tile / 2;
         const int c_begin = half * ncol_half;
-        const bool vec2 = (f.ldy & 1) == 0 && (f.n_valid & 1) == 0;
+        float* const yout = f.y;
+        const int ldy = f.ldy, n_valid = f.n_valid, n_rows = p.rows;
+        const bool vec2 = (ldy & 1) == 0 && (n_valid & 1) == 0;
         // (rolled loops: this code runs once per head tile and is cold in the instruction caches -- unrolled it was
         // ~10 KB of straight-line code and the head epilogue took 4.4 us for 128 x 96 outputs)
 #pragma unroll 1
@@ -627,6 +636,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
                   make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
           }
           __syncwarp();
+          if (etid == 0 && tm == 2) TRACE(g0 == 0 ? 35 : 37);
           const int lpr = gw >> 1;              // lanes per row (one float2 each): 16 or 8
           const int rpi = 32 / lpr;             // rows per instruction
           const int lr = gw == 32 ? lane >> 4 : lane >> 3;
@@ -637,13 +647,14 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
             const float2 t = *reinterpret_cast<const float2*>(eb + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4);
             const int col = c_begin + g0 + cc;
             const int grow = row_w0 + rr;
-            if (grow < p.rows && col < f.n_valid) {
-              float* dst = f.y + (size_t)grow * f.ldy + col;
+            if (grow < n_rows && col < n_valid) {
+              float* dst = yout + (size_t)grow * ldy + col;
               if (vec2) __stcs(reinterpret_cast<float2*>(dst), t);
-              else { dst[0] = t.x; if (col + 1 < f.n_valid) dst[1] = t.y; }
+              else { dst[0] = t.x; if (col + 1 < n_valid) dst[1] = t.y; }
             }
           }
           __syncwarp();
+          if (etid == 0 && tm == 2) TRACE(g0 == 0 ? 36 : 38);
         }
       } else if (f.type == PH_GAUSS && sub < 2) {
         const int nchunks = f.n_tile / 16;
