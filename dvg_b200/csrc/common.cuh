@@ -124,6 +124,13 @@ __device__ __forceinline__ float tanh_fast_prescaled(float a, float b) {
   return (1.f - E) * rcp_ftz(1.f + E);
 }
 
+// Same with the exponential on the FMA pipe (ex2_poly): 1 MUFU.  The head epilogue of lstm_step.cu is XU bound (only
+// transcendentals, no other math), so it alternates the two forms.
+__device__ __forceinline__ float tanh_fast_prescaled_poly(float a, float b) {
+  const float E = ex2_poly(fminf(fmaf(a, -2.f * kLog2e, b), 40.f));
+  return (1.f - E) * rcp_ftz(1.f + E);
+}
+
 // a ~= hi + lo with both bf16 (round-to-nearest): relative residual <= 2^-17.
 __device__ __forceinline__ void split_bf16(float a, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(a);

@@ -629,7 +629,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
             float v[16];
             ptx::tmem_ld16_wait(tacc + c_begin + g0 + c16, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = tanh_fast_prescaled(v[i], sb[c_begin + g0 + c16 + i]);
+            for (int i = 0; i < 16; ++i)      // XU bound: every other exponential goes to the FMA pipe
+              v[i] = (i & 1) ? tanh_fast_prescaled_poly(v[i], sb[c_begin + g0 + c16 + i])
+                             : tanh_fast_prescaled(v[i], sb[c_begin + g0 + c16 + i]);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4)
               *reinterpret_cast<float4*>(eb + lane * 128 + ((((c16 >> 2) + c4) ^ (lane & 7)) << 4)) =
@@ -641,7 +643,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           const int rpi = 32 / lpr;             // rows per instruction
           const int lr = gw == 32 ? lane >> 4 : lane >> 3;
           const int cc = (gw == 32 ? lane & 15 : lane & 7) * 2;
-#pragma unroll 1
+#pragma unroll 4
           for (int i = 0; i < 32 / rpi; ++i) {
             const int rr = i * rpi + lr;
             const float2 t = *reinterpret_cast<const float2*>(eb + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4);
