@@ -47,7 +47,7 @@ static void lstm_free_all(dvg_lstm_s* h) {
   auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
   fr(h->f_embed_wt); fr(h->f_embed_b); fr(h->f_head_wt); fr(h->f_head_b);
   for (int l = 0; l < MAX_LAYERS; ++l) { fr(h->f_layer_wt[l]); fr(h->f_layer_b[l]); }
-  fr(h->scratch_e); fr(h->tc_xp); fr(h->tc_ep);
+  fr(h->scratch_e); fr(h->tc_xp); fr(h->tc_ep); fr(h->rs_buf);
   for (int i = 0; i < 16; ++i)
     if (h->prof_ev[i]) { cudaEventDestroy(h->prof_ev[i]); h->prof_ev[i] = nullptr; }
   lstm_tc_free(h);
@@ -115,7 +115,7 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
   if (rows <= h->reserved_rows) return DVG_OK;
   DVG_CUDA(cudaDeviceSynchronize());
   auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
-  fr(h->scratch_e); fr(h->tc_xp); fr(h->tc_ep);
+  fr(h->scratch_e); fr(h->tc_xp); fr(h->tc_ep); fr(h->rs_buf);
   h->reserved_rows = 0;
   DVG_CUDA(cudaMalloc(&h->scratch_e, sizeof(float) * (size_t)rows * h->dims.hidden_size));
   if (h->tc_ok) {
@@ -123,6 +123,7 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
                                                                                         : lstm_tc_scratch_bytes_xp(h, rows);
     DVG_CUDA(cudaMalloc(&h->tc_xp, xpb));
     DVG_CUDA(cudaMemset(h->tc_xp, 0, xpb));
+    DVG_CUDA(cudaMalloc(&h->rs_buf, sizeof(float) * (size_t)rows * h->dims.output_size));
     DVG_CUDA(cudaMalloc(&h->tc_ep, lstm_tc_scratch_bytes_ep(h, rows)));
     DVG_CUDA(cudaMemset(h->tc_ep, 0, lstm_tc_scratch_bytes_ep(h, rows)));
     if (h->fused_flags) cudaFree(h->fused_flags);

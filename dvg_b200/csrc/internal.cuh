@@ -52,6 +52,7 @@ struct dvg_lstm_s {
   float* scratch_e = nullptr;    // fp32 [rows][H]: embed output (FFMA variant)
   uint8_t* tc_xp = nullptr;      // packed x            [RT][kbx][2][16 KB]
   uint8_t* tc_ep = nullptr;      // packed embed output [RT][H/64][2][16 KB]
+  float* rs_buf = nullptr;       // [rows][G_out] side buffer of the step kernel's in-launch GP resample
 
   // --- optional per-kernel timing (dvg_lstm_profile): events recorded between launches ------------
   bool prof_on = false;

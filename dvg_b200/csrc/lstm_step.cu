@@ -89,7 +89,8 @@ struct StepArgs {
   const uint8_t* hold;            // mask known BEFORE the launch (plain dvg_lstm_step); nullptr in trigger-fused steps
   const int* sched; int sched_len;   // optional host-built item order: pair p runs sched[p], sched[p + pairs], ...
   int* flag_words; int n_flag_words;     // dependency counters, then [mask_ready][done_ctr]; exit counter follows
-  int* mask_ready; int* done_ctr;
+  int* mask_ready; int* done_ctr; int* rs_next; int* rs_done;
+  float* rs_buf;                  // [rows, G] side buffer of the in-kernel resample
   unsigned long long* trace;
   StepTrig trig;
   StepPhase ph[STEP_MAX_PHASES];
@@ -784,20 +785,63 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
     }
     __syncthreads();
     const int n_fired = s_misc[0];
+    if (threadIdx.x == 0) TRACE(39);
     if (n_fired > 0) {
+      // Phase A -- their decoder input becomes a GP posterior sample of the encoder latent instead of the LSTM
+      // prediction (generate_frames.py:291-292).  The (fired rollout, latent dim) problems only need the step's INPUT,
+      // so they start as soon as the mask is known, taken from a dynamic queue by whichever CTAs have finished their
+      // tiles (most pairs are done ~15 us before the last heads): 256 threads per problem in the now idle operand
+      // stages, results into a side buffer because the head tiles of other pairs may still be writing y.
+      // (Two problems at a time per CTA -- the two halves of the 16 epilogue warps -- measured slower.)
+      const bool rs = p.trig.rs_eps != nullptr;
+      const int n_tasks = rs ? n_fired * p.trig.D : 0;
+      if (rs) {
+        const StepTrig& g = p.trig;
+        float* smf = reinterpret_cast<float*>(smem_raw);
+        for (;;) {
+          if (threadIdx.x == 0) s_misc[1] = atomicAdd(p.rs_next, 1);
+          __syncthreads();
+          const int task = s_misc[1];
+          if (task >= n_tasks) break;
+          if (warp >= 2 && warp < 2 + 8) {          // 256 threads (RS_THREADS)
+            const int sr = g.trig_list[task / g.D], d = task % g.D;
+            gp_rsample_body(smf, (int)threadIdx.x - 64, [] { ptx::named_bar_sync(2, 256); }, sr, d, g.n_points, g.D,
+                            g.mp, p.x, p.ldx, g.rs_eps, g.z, g.linv, g.lqt, g.alpha, g.hyp, p.rs_buf, p.G);
+          }
+          __syncthreads();                          // shared memory and s_misc[1] are reused by the next problem
+          if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(p.rs_done, 1);
+          }
+        }
+      }
+      if (threadIdx.x == 0) TRACE(40);
+      // Phase B -- once every CTA has finished its tiles (and every problem is solved): copy the fired rollouts' state
+      // rows (fp32 h, c and the packed h images) back from the input block, and their samples into y.
       if (threadIdx.x == 0) {
         poll_ge(p.done_ctr, (int)gridDim.x, -2);
+        if (rs) poll_ge(p.rs_done, n_tasks, -3);
         __threadfence();
+        TRACE(41);
       }
       __syncthreads();
-      const int chunks = 3 * p.L;
+      const int chunks = 3 * p.L + (rs ? 1 : 0);
       const int hk = p.H / 64;
       for (int wi = blockIdx.x; wi < n_fired * chunks; wi += gridDim.x) {
         const int s = p.trig.trig_list[wi / chunks];
-        const int c = wi % chunks, l = c / 3, kind = c % 3;
-        const StepPhase& f = p.ph[l];
+        const int c = wi % chunks;
         const int r0 = s * p.rows_per_flag;
         const int r1 = r0 + p.rows_per_flag < p.rows ? r0 + p.rows_per_flag : p.rows;
+        if (c == 3 * p.L) {                          // samples -> y rows of the rollout
+          const int n = (r1 - r0) * p.G;
+          for (int i = threadIdx.x; i < n; i += STEP_THREADS) {
+            const int r = r0 + i / p.G, gcol = i % p.G;
+            p.trig.rs_out[(size_t)r * p.trig.rs_ldo + gcol] = __ldcg(p.rs_buf + (size_t)r * p.G + gcol);
+          }
+          continue;
+        }
+        const int l = c / 3, kind = c % 3;
+        const StepPhase& f = p.ph[l];
         if (kind < 2) {
           const float4* src = reinterpret_cast<const float4*>((kind == 0 ? f.h_in : f.c_in) + (size_t)r0 * p.H);
           float4* dst = reinterpret_cast<float4*>((kind == 0 ? f.h_out : f.c_out) + (size_t)r0 * p.H);
@@ -813,26 +857,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           }
         }
       }
-      // ... and their decoder input becomes a GP posterior sample of the encoder latent instead of the LSTM
-      // prediction (generate_frames.py:291-292): one (fired rollout, latent dim) problem per CTA trip, solved by the
-      // epilogue warps in the now idle stage buffers.  Every head tile has been written (done_ctr), so the rows are
-      // simply overwritten.
-      if (p.trig.rs_eps != nullptr && warp >= 2 && warp < 2 + 8) {          // 256 threads (RS_THREADS)
-        const StepTrig& g = p.trig;
-        float* smf = reinterpret_cast<float*>(smem_raw);
-        for (int wi = blockIdx.x; wi < n_fired * g.D; wi += gridDim.x) {
-          const int s = g.trig_list[wi / g.D], d = wi % g.D;
-          gp_rsample_body(smf, (int)threadIdx.x - 64, [] { ptx::named_bar_sync(2, 256); }, s, d, g.n_points, g.D,
-                          g.mp, p.x, p.ldx, g.rs_eps, g.z, g.linv, g.lqt, g.alpha, g.hyp, g.rs_out, g.rs_ldo);
-          ptx::named_bar_sync(2, 256);   // shared memory is reused by the next problem
-        }
-      }
     }
   }
   // Self-resetting dependency counters: the last CTA to get here (every CTA has finished reading them) zeroes
   // them for the next launch -- no cudaMemset node per step.
   __syncthreads();
   if (threadIdx.x == 0) {
+    TRACE(42);
     int* exit_ctr = p.flag_words + p.n_flag_words;
     __threadfence();
     if (atomicAdd(exit_ctr, 1) == (int)gridDim.x - 1) {
@@ -1062,9 +1093,12 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   const int fstride = (int)align_up((size_t)groups * hk, 32);
   int* flags = h->fused_flags;
   a.flag_words = flags;
-  a.n_flag_words = L * fstride + 2;
+  a.n_flag_words = L * fstride + 4;
   a.mask_ready = flags + (size_t)L * fstride;
   a.done_ctr = a.mask_ready + 1;
+  a.rs_next = a.mask_ready + 2;
+  a.rs_done = a.mask_ready + 3;
+  a.rs_buf = h->rs_buf;
   if (trig != nullptr) {
     StepTrig& t = a.trig;
     t.enabled = 1; t.S = trig->S; t.D = g->dims.num_dims; t.mp = g->mp; t.W = trig->W; t.warmup = trig->warmup;
@@ -1169,7 +1203,7 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
               (int)cfg.gridDim.x, a.total_items, stages, a.restore);
       for (int b = 0; b < (int)cfg.gridDim.x; ++b) {
         fprintf(stderr, "cta %3d:", b);
-        for (int i = 0; i < 40; ++i) {
+        for (int i = 0; i < 44; ++i) {
           unsigned long long v = hbuf[b * TRACE_SLOTS + i];
           if (i == 2 || i == 10 || i == 18 || i == 26) fprintf(stderr, " |");
           if (v >= 1000000ull && v < 2000000ull) fprintf(stderr, " #%lld", (long long)(v - 1000000ull));

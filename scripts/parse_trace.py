@@ -9,7 +9,7 @@ for line in open(sys.argv[1]):
     toks = line.split(":", 1)[1].replace("|", " ").replace("#", "").split()
     rows.append([int(t) for t in toks])
 a = np.array(rows)
-names = {0: "start", 1: "setup", 26: "trigdone", 27: "xpack", 28: "it0 published", 29: "it0 stored", 30: "end", 31: "finalizer", 32: "it0 loopdone", 33: "it0 hpstored", 34: "it0 fenced", 35: "head tanh g0", 36: "head store g0", 37: "head tanh g1", 38: "head store g1"}
+names = {0: "start", 1: "setup", 26: "trigdone", 27: "xpack", 28: "it0 published", 29: "it0 stored", 30: "end", 31: "finalizer", 32: "it0 loopdone", 33: "it0 hpstored", 34: "it0 fenced", 35: "head tanh g0", 36: "head store g0", 37: "head tanh g1", 38: "head store g1", 39: "tail mask known", 40: "tail rsample done", 41: "tail all done", 42: "exit"}
 for m in range(3):
     for k, n in enumerate(["pstart", "depok", "stage0", "mmaissued", "accready", "epidone", "item", "requested"]):
         names[2 + m * 8 + k] = f"it{m} {n}"
