@@ -8,7 +8,7 @@
 namespace dvg {
 
 __host__ __device__ inline size_t gp_rsample_smem_floats(int N, int mp) {
-  return (size_t)2 * mp * mp + 3 * (size_t)N * (mp + 1) + (size_t)N * (N + 1) + 4 * (size_t)N + 2 * (size_t)mp;
+  return (size_t)2 * mp * mp + 3 * (size_t)N * (mp + 4) + (size_t)N * (N + 1) + 4 * (size_t)N + 2 * (size_t)mp;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -31,18 +31,20 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
                                                 float* __restrict__ out, int ldo) {
 #ifdef DVG_TRACE
   long long tq[8]; int nq = 0;
-#define RSQ() do { sync(); tq[nq++] = clock64(); } while (0)
+#define RSQ() do { sync(); if (nq < 8) tq[nq++] = clock64(); } while (0)
 #else
 #define RSQ() do {} while (0)
 #endif
   RSQ();
   const int MP = mp;
-  const int ldk = MP + 1, lds = N + 1;
+  // rows of K / U / R are read as float4: stride MP + 4 floats keeps them 16-byte aligned (MP % 4 == 0) and, for
+  // MP / 4 even (MP = 40), makes the per-thread-row float4 reads bank-conflict free
+  const int ldk = MP + 4, lds = N + 1;
   float* s_linv = smf;                 // [MP][MP]
   float* s_lqt = s_linv + MP * MP;     // [MP][MP]
-  float* s_k = s_lqt + MP * MP;        // [N][MP+1]  K_xz
-  float* s_u = s_k + N * ldk;          // [N][MP+1]  (Linv k_n)
-  float* s_r = s_u + N * ldk;          // [N][MP+1]  (L_q^T k_n)
+  float* s_k = s_lqt + MP * MP;        // [N][MP+4]  K_xz
+  float* s_u = s_k + N * ldk;          // [N][MP+4]  (Linv k_n)
+  float* s_r = s_u + N * ldk;          // [N][MP+4]  (L_q^T k_n)
   float* s_sig = s_r + N * ldk;        // [N][N+1]   Sigma_y -> L
   float* s_x = s_sig + N * lds;        // [N]
   float* s_mean = s_x + N;             // [N]
@@ -90,30 +92,28 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
   }
   sync();
   RSQ();
-  // Thread mapping for the O(N M^2) / O(N^2 M) / O(N^3) phases: the point index (n or b) is the FAST thread index
-  // (row stride ldk / lds is odd -> conflict-free), the matrix row (j or a) is shared by a whole warp (broadcast
-  // reads), and there are no runtime integer divisions.  (First version: 4-way bank conflicts + unpipelined LDS
-  // chains + idiv -> 140 k cycles per problem.)
+  // Thread mapping for the O(N M^2) / O(N^3) phases: the point index (n or a) is the FAST thread index (row strides
+  // ldk / lds -> conflict-free), the matrix row (j or b) is shared by a whole warp (broadcast reads), and there are
+  // no runtime integer divisions.  All dot products read float4.  (History, cycles per problem on B200: first
+  // version 140 k; scalar LDS + triangle skipping by `continue` 87 k; float4 dots + flat pair list 70 k.)
   const int lg = N <= 32 ? 5 : (N <= 64 ? 6 : 7);       // N <= 128 (shared-memory bound)
   const int fi = tid & ((1 << lg) - 1);                 // point index
   const int grp = tid >> lg, ngrp = RS_THREADS >> lg;   // which matrix rows this thread visits
+  const int MB = MP >> 2;
   if (fi < N) {
-    const float* kr = s_k + fi * ldk;
+    const float4* kr4 = reinterpret_cast<const float4*>(s_k + fi * ldk);
     for (int j = grp; j < MP; j += ngrp) {
-      const float* lr = s_linv + j * MP;
-      const float* qr = s_lqt + j * MP;
+      const float4* lr4 = reinterpret_cast<const float4*>(s_linv + j * MP);
+      const float4* qr4 = reinterpret_cast<const float4*>(s_lqt + j * MP);
       float v0 = 0.f, v1 = 0.f, w0 = 0.f, w1 = 0.f;
-      const int jm = j & ~1;
-#pragma unroll 4
-      for (int m = 0; m < jm; m += 2) {                 // Linv row j: m <= j
-        v0 = fmaf(lr[m], kr[m], v0);
-        v1 = fmaf(lr[m + 1], kr[m + 1], v1);
+      const int jb = j >> 2;
+      for (int mb = 0; mb <= jb; ++mb) {                // Linv row j: entries m <= j (exact zeros beyond j)
+        const float4 l = lr4[mb], k = kr4[mb];
+        v0 = fmaf(l.x, k.x, v0); v1 = fmaf(l.y, k.y, v1); v0 = fmaf(l.z, k.z, v0); v1 = fmaf(l.w, k.w, v1);
       }
-      for (int m = jm; m <= j; ++m) v0 = fmaf(lr[m], kr[m], v0);
-#pragma unroll 4
-      for (int m = jm; m + 1 < MP; m += 2) {            // L_q^T row j: m >= j (entries below j are zero)
-        w0 = fmaf(qr[m], kr[m], w0);
-        w1 = fmaf(qr[m + 1], kr[m + 1], w1);
+      for (int mb = jb; mb < MB; ++mb) {                // L_q^T row j: entries m >= j (exact zeros below j)
+        const float4 q = qr4[mb], k = kr4[mb];
+        w0 = fmaf(q.x, k.x, w0); w1 = fmaf(q.y, k.y, w1); w0 = fmaf(q.z, k.z, w0); w1 = fmaf(q.w, k.w, w1);
       }
       s_u[fi * ldk + j] = v0 + v1;
       s_r[fi * ldk + j] = w0 + w1;
@@ -129,31 +129,39 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
     }
     s_mean[n] = c + (mu0 + mu1);       // MP is a multiple of 4
   }
-  if (fi < N) {
-    const float* rb = s_r + fi * ldk;
-    const float* ub = s_u + fi * ldk;
-    for (int a = grp; a < N; a += ngrp) {
-      if (fi > a) continue;                             // lower triangle: b = fi <= a
-      const float* ra = s_r + a * ldk;
-      const float* ua = s_u + a * ldk;
-      float rr0 = 0.f, rr1 = 0.f, uu0 = 0.f, uu1 = 0.f;
-#pragma unroll 4
-      for (int m = 0; m < MP; m += 2) {
-        rr0 = fmaf(ra[m], rb[m], rr0);
-        uu0 = fmaf(ua[m], ub[m], uu0);
-        rr1 = fmaf(ra[m + 1], rb[m + 1], rr1);
-        uu1 = fmaf(ua[m + 1], ub[m + 1], uu1);
-      }
-      const float t = (s_x[a] - s_x[fi]) * inv_ell;
-      const float kxx = a == fi ? sc : sc * expf(-0.5f * t * t);
-      s_sig[a * lds + fi] = (rr0 + rr1) + (kxx - (uu0 + uu1)) + (a == fi ? noise : 0.f);
+  // Sigma_y, lower triangle: the N (N + 1) / 2 pairs (a, b <= a) are dealt out flat (b fastest: one row a is a
+  // broadcast, consecutive rows b are conflict free), so every thread gets the same number of pairs.
+  for (int pidx = tid; pidx < N * (N + 1) / 2; pidx += RS_THREADS) {
+    int a = (int)((sqrtf(8.f * (float)pidx + 1.f) - 1.f) * 0.5f);
+    while (a * (a + 1) / 2 > pidx) --a;
+    while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
+    const int b = pidx - a * (a + 1) / 2;
+    const float4* ra4 = reinterpret_cast<const float4*>(s_r + a * ldk);
+    const float4* rb4 = reinterpret_cast<const float4*>(s_r + b * ldk);
+    const float4* ua4 = reinterpret_cast<const float4*>(s_u + a * ldk);
+    const float4* ub4 = reinterpret_cast<const float4*>(s_u + b * ldk);
+    float rr0 = 0.f, rr1 = 0.f, uu0 = 0.f, uu1 = 0.f;
+#pragma unroll 2
+    for (int mb = 0; mb < MB; ++mb) {
+      const float4 r1 = ra4[mb], r2 = rb4[mb], u1 = ua4[mb], u2 = ub4[mb];
+      rr0 = fmaf(r1.x, r2.x, rr0); uu0 = fmaf(u1.x, u2.x, uu0);
+      rr1 = fmaf(r1.y, r2.y, rr1); uu1 = fmaf(u1.y, u2.y, uu1);
+      rr0 = fmaf(r1.z, r2.z, rr0); uu0 = fmaf(u1.z, u2.z, uu0);
+      rr1 = fmaf(r1.w, r2.w, rr1); uu1 = fmaf(u1.w, u2.w, uu1);
     }
+    const float t = (s_x[a] - s_x[b]) * inv_ell;
+    const float kxx = a == b ? sc : sc * expf(-0.5f * t * t);
+    s_sig[a * lds + b] = (rr0 + rr1) + (kxx - (uu0 + uu1)) + (a == b ? noise : 0.f);
   }
   sync();
   RSQ();
   // Cholesky as LDL^T, right-looking with UNSCALED columns (one barrier per column): after step j the trailing
   // block holds S - sum_{k<=j} c_k c_k^T / d_k with c_k the unscaled column k and d_k its diagonal;
-  // L[i][j] = c_j[i] / sqrt(d_j) is applied in one pass at the end.
+  // L[i][j] = c_j[i] / sqrt(d_j) is applied in one pass at the end.  ~41 k cycles for N = 50 and the largest phase
+  // left: two alternatives were measured and were no faster -- panels of 4 columns (two barriers per panel, 44.6 k:
+  // the read-modify-write of the trailing block through shared memory serialises on LDS -> FMA -> STS latency either
+  // way) and a left-looking one-thread-per-row variant (loads only, 64-thread barrier, 47.5 k: two lone warps issue at
+  // ~0.25 IPC).  Next: several problems per CTA (one per warp pair) instead of 256 threads on one.
   for (int j = 0; j + 1 < N; ++j) {
     const float inv_d = __fdividef(1.0f, s_sig[j * lds + j]);
     const int a = j + 1 + fi;                             // this thread's ROW (consecutive threads -> stride lds, odd:
