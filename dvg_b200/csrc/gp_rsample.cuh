@@ -102,21 +102,40 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
   const int MB = MP >> 2;
   if (fi < N) {
     const float4* kr4 = reinterpret_cast<const float4*>(s_k + fi * ldk);
-    for (int j = grp; j < MP; j += ngrp) {
+    // two matrix rows (j, j + ngrp) at a time: twice the independent FMA chains per thread
+    for (int j = grp; j < MP; j += 2 * ngrp) {
+      const int j2 = j + ngrp < MP ? j + ngrp : j;      // (last odd row: computed twice, stored once)
       const float4* lr4 = reinterpret_cast<const float4*>(s_linv + j * MP);
       const float4* qr4 = reinterpret_cast<const float4*>(s_lqt + j * MP);
-      float v0 = 0.f, v1 = 0.f, w0 = 0.f, w1 = 0.f;
-      const int jb = j >> 2;
-      for (int mb = 0; mb <= jb; ++mb) {                // Linv row j: entries m <= j (exact zeros beyond j)
-        const float4 l = lr4[mb], k = kr4[mb];
-        v0 = fmaf(l.x, k.x, v0); v1 = fmaf(l.y, k.y, v1); v0 = fmaf(l.z, k.z, v0); v1 = fmaf(l.w, k.w, v1);
-      }
-      for (int mb = jb; mb < MB; ++mb) {                // L_q^T row j: entries m >= j (exact zeros below j)
-        const float4 q = qr4[mb], k = kr4[mb];
-        w0 = fmaf(q.x, k.x, w0); w1 = fmaf(q.y, k.y, w1); w0 = fmaf(q.z, k.z, w0); w1 = fmaf(q.w, k.w, w1);
+      const float4* lr4b = reinterpret_cast<const float4*>(s_linv + j2 * MP);
+      const float4* qr4b = reinterpret_cast<const float4*>(s_lqt + j2 * MP);
+      float v0 = 0.f, v1 = 0.f, w0 = 0.f, w1 = 0.f, x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
+      const int jb = j >> 2, jb2 = j2 >> 2;
+      for (int mb = 0; mb < MB; ++mb) {
+        const float4 k = kr4[mb];
+        if (mb <= jb) {                                 // Linv row j: entries m <= j (exact zeros beyond j)
+          const float4 l = lr4[mb];
+          v0 = fmaf(l.x, k.x, v0); v1 = fmaf(l.y, k.y, v1); v0 = fmaf(l.z, k.z, v0); v1 = fmaf(l.w, k.w, v1);
+        }
+        if (mb >= jb) {                                 // L_q^T row j: entries m >= j (exact zeros below j)
+          const float4 q = qr4[mb];
+          w0 = fmaf(q.x, k.x, w0); w1 = fmaf(q.y, k.y, w1); w0 = fmaf(q.z, k.z, w0); w1 = fmaf(q.w, k.w, w1);
+        }
+        if (mb <= jb2) {
+          const float4 l = lr4b[mb];
+          x0 = fmaf(l.x, k.x, x0); x1 = fmaf(l.y, k.y, x1); x0 = fmaf(l.z, k.z, x0); x1 = fmaf(l.w, k.w, x1);
+        }
+        if (mb >= jb2) {
+          const float4 q = qr4b[mb];
+          y0 = fmaf(q.x, k.x, y0); y1 = fmaf(q.y, k.y, y1); y0 = fmaf(q.z, k.z, y0); y1 = fmaf(q.w, k.w, y1);
+        }
       }
       s_u[fi * ldk + j] = v0 + v1;
       s_r[fi * ldk + j] = w0 + w1;
+      if (j2 != j) {
+        s_u[fi * ldk + j2] = x0 + x1;
+        s_r[fi * ldk + j2] = y0 + y1;
+      }
     }
   }
   sync();
@@ -167,9 +186,22 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
     const int a = j + 1 + fi;                             // this thread's ROW (consecutive threads -> stride lds, odd:
     if (a < N) {                                          // conflict-free; columns b are warp-uniform -> broadcast)
       const float ca = s_sig[a * lds + j] * inv_d;
-#pragma unroll 4
-      for (int b = j + 1 + grp; b <= a; b += ngrp)
-        s_sig[a * lds + b] = fmaf(-ca, s_sig[b * lds + j], s_sig[a * lds + b]);
+      // batches of 4 with all loads issued before the first store: a plain read-modify-write loop serialises on
+      // LDS -> FMA -> STS because the compiler must assume the store aliases the next loads
+      for (int b0 = j + 1 + grp; b0 <= a; b0 += 4 * ngrp) {
+        float xv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = b0 + u * ngrp;
+          xv[u] = b <= a ? s_sig[a * lds + b] : 0.f;
+          yv[u] = b <= a ? s_sig[b * lds + j] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = b0 + u * ngrp;
+          if (b <= a) s_sig[a * lds + b] = fmaf(-ca, yv[u], xv[u]);
+        }
+      }
     }
     sync();
   }
