@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(RS_THREADS) gp_rsample_kernel(int S, int N, in
                                                          const float* __restrict__ hyp, float* __restrict__ out, int ldo) {
   if (mask != nullptr && mask[blockIdx.x] == 0) return;
   extern __shared__ __align__(16) float smf[];
-  gp_rsample_body(smf, (int)threadIdx.x, [] { __syncthreads(); }, blockIdx.x, blockIdx.y, N, D, mp, x, ldx, eps, zall, linv_all,
+  gp_rsample_body<RS_THREADS>(smf, (int)threadIdx.x, [] { __syncthreads(); }, blockIdx.x, blockIdx.y, N, D, mp, x, ldx, eps, zall, linv_all,
                   lqt_all, alpha_all, hyp, out, ldo);
 }
 
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(RS_THREADS) gp_rsample_list_kernel(int N, int 
   extern __shared__ __align__(16) float smf[];
   const int n = *trig_count;
   for (int i = blockIdx.y; i < n; i += gridDim.y) {
-    gp_rsample_body(smf, (int)threadIdx.x, [] { __syncthreads(); }, trig_list[i], blockIdx.x, N, D, mp, x, ldx, eps, zall,
+    gp_rsample_body<RS_THREADS>(smf, (int)threadIdx.x, [] { __syncthreads(); }, trig_list[i], blockIdx.x, N, D, mp, x, ldx, eps, zall,
                     linv_all, lqt_all, alpha_all, hyp, out, ldo);
     __syncthreads();   // shared memory is reused by the next rollout
   }

@@ -17,11 +17,11 @@ __host__ __device__ inline size_t gp_rsample_smem_floats(int N, int mp) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 
-// One (rollout, dim) problem per call, all RS_THREADS threads of the CTA: full [N,N] predictive covariance in
+// One (rollout, dim) problem per call, NTHR cooperating threads (256 in the stand-alone kernels, 512 in the step kernel): full [N,N] predictive covariance in
 // shared memory, Cholesky, y = mean + L eps.  Every global operand (factors, z, beta, eps, x) is staged into
 // shared memory first with batched coalesced loads: the first version read beta / eps / z from global inside
 // dependent inner loops and spent ~45 of its 70 us waiting on L2.
-template <class Sync>
+template <int NTHR, class Sync>
 __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync sync, int s_idx, int d, int N, int D,
                                                 int mp, const float* __restrict__ x, int ldx,
                                                 const float* __restrict__ eps,
@@ -56,27 +56,27 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
     const float4* g1 = reinterpret_cast<const float4*>(linv_all + (size_t)d * MP * MP);
     const float4* g2 = reinterpret_cast<const float4*>(lqt_all + (size_t)d * MP * MP);
     const int n4 = MP * MP / 4;
-    for (int e0 = 0; e0 < n4; e0 += RS_THREADS * 2) {       // 4 independent 16-byte loads in flight per thread
+    for (int e0 = 0; e0 < n4; e0 += NTHR * 2) {       // 4 independent 16-byte loads in flight per thread
       float4 t[2][2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int e = e0 + u * RS_THREADS + tid;
+        const int e = e0 + u * NTHR + tid;
         if (e < n4) { t[u][0] = __ldg(g1 + e); t[u][1] = __ldg(g2 + e); }
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int e = e0 + u * RS_THREADS + tid;
+        const int e = e0 + u * NTHR + tid;
         if (e < n4) {
           reinterpret_cast<float4*>(s_linv)[e] = t[u][0];
           reinterpret_cast<float4*>(s_lqt)[e] = t[u][1];
         }
       }
     }
-    for (int e = tid; e < MP; e += RS_THREADS) {
+    for (int e = tid; e < MP; e += NTHR) {
       s_z[e] = __ldg(zall + (size_t)d * MP + e);
       s_beta[e] = __ldg(alpha_all + (size_t)d * MP + e);
     }
-    for (int n = tid; n < N; n += RS_THREADS) {
+    for (int n = tid; n < N; n += NTHR) {
       s_x[n] = __ldg(x + (size_t)(s_idx * N + n) * ldx + d);
       s_eps[n] = __ldg(eps + ((size_t)s_idx * D + d) * N + n);
     }
@@ -85,7 +85,7 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
   const float inv_ell = 1.0f / ell;
   sync();
   RSQ();
-  for (int e = tid; e < N * MP; e += RS_THREADS) {
+  for (int e = tid; e < N * MP; e += NTHR) {
     const int n = e / MP, m = e % MP;
     const float t = (s_x[n] - s_z[m]) * inv_ell;
     s_k[n * ldk + m] = sc * expf(-0.5f * t * t);
@@ -98,7 +98,7 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
   // version 140 k; scalar LDS + triangle skipping by `continue` 87 k; float4 dots + flat pair list 70 k.)
   const int lg = N <= 32 ? 5 : (N <= 64 ? 6 : 7);       // N <= 128 (shared-memory bound)
   const int fi = tid & ((1 << lg) - 1);                 // point index
-  const int grp = tid >> lg, ngrp = RS_THREADS >> lg;   // which matrix rows this thread visits
+  const int grp = tid >> lg, ngrp = NTHR >> lg;   // which matrix rows this thread visits
   const int MB = MP >> 2;
   if (fi < N) {
     const float4* kr4 = reinterpret_cast<const float4*>(s_k + fi * ldk);
@@ -140,7 +140,7 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
   }
   sync();
   RSQ();
-  for (int n = tid; n < N; n += RS_THREADS) {
+  for (int n = tid; n < N; n += NTHR) {
     float mu0 = 0.f, mu1 = 0.f;
     for (int j = 0; j + 1 < MP; j += 2) {
       mu0 = fmaf(s_beta[j], s_u[n * ldk + j], mu0);
@@ -150,7 +150,7 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
   }
   // Sigma_y, lower triangle: the N (N + 1) / 2 pairs (a, b <= a) are dealt out flat (b fastest: one row a is a
   // broadcast, consecutive rows b are conflict free), so every thread gets the same number of pairs.
-  for (int pidx = tid; pidx < N * (N + 1) / 2; pidx += RS_THREADS) {
+  for (int pidx = tid; pidx < N * (N + 1) / 2; pidx += NTHR) {
     int a = (int)((sqrtf(8.f * (float)pidx + 1.f) - 1.f) * 0.5f);
     while (a * (a + 1) / 2 > pidx) --a;
     while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
@@ -210,10 +210,10 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
     if (fi > j && fi < N) s_sig[fi * lds + j] *= rs;
   }
   sync();
-  for (int j = tid; j < N; j += RS_THREADS) s_sig[j * lds + j] = sqrtf(s_sig[j * lds + j]);
+  for (int j = tid; j < N; j += NTHR) s_sig[j * lds + j] = sqrtf(s_sig[j * lds + j]);
   sync();
   RSQ();
-  for (int n = tid; n < N; n += RS_THREADS) {
+  for (int n = tid; n < N; n += NTHR) {
     float a0 = 0.f, a1 = 0.f;
     int k = 0;
     for (; k + 1 <= n; k += 2) {

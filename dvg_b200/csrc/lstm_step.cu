@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       // Phase A -- their decoder input becomes a GP posterior sample of the encoder latent instead of the LSTM
       // prediction (generate_frames.py:291-292).  The (fired rollout, latent dim) problems only need the step's INPUT,
       // so they start as soon as the mask is known, taken from a dynamic queue by whichever CTAs have finished their
-      // tiles (most pairs are done ~15 us before the last heads): 256 threads per problem in the now idle operand
+      // tiles (most pairs are done ~15 us before the last heads): all 16 epilogue warps on one problem in the now idle operand
       // stages, results into a side buffer because the head tiles of other pairs may still be writing y.
       // (Two problems at a time per CTA -- the two halves of the 16 epilogue warps -- measured slower.)
       const bool rs = p.trig.rs_eps != nullptr;
@@ -803,10 +803,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           __syncthreads();
           const int task = s_misc[1];
           if (task >= n_tasks) break;
-          if (warp >= 2 && warp < 2 + 8) {          // 256 threads (RS_THREADS)
+          if (warp >= 2 && warp < 2 + STEP_EW) {    // all epilogue warps on one problem
             const int sr = g.trig_list[task / g.D], d = task % g.D;
-            gp_rsample_body(smf, (int)threadIdx.x - 64, [] { ptx::named_bar_sync(2, 256); }, sr, d, g.n_points, g.D,
-                            g.mp, p.x, p.ldx, g.rs_eps, g.z, g.linv, g.lqt, g.alpha, g.hyp, p.rs_buf, p.G);
+            gp_rsample_body<STEP_EW * 32>(smf, (int)threadIdx.x - 64, [] { ptx::named_bar_sync(2, STEP_EW * 32); }, sr, d,
+                                          g.n_points, g.D, g.mp, p.x, p.ldx, g.rs_eps, g.z, g.linv, g.lqt, g.alpha, g.hyp,
+                                          p.rs_buf, p.G);
           }
           __syncthreads();                          // shared memory and s_misc[1] are reused by the next problem
           if (threadIdx.x == 0) {
