@@ -20,6 +20,8 @@ NVCC_FLAGS = [
 ]
 if os.environ.get("DVG_STEP_NPOLY"):     # developer build: exponentials on the FMA pipe in the step kernel's epilogue
     NVCC_FLAGS.append("-DDVG_STEP_NPOLY=" + os.environ["DVG_STEP_NPOLY"])
+if os.environ.get("DVG_STEP_TRIG_EARLY"):   # developer build: 0 = trigger partial sums after the first tile
+    NVCC_FLAGS.append("-DDVG_STEP_TRIG_EARLY=" + os.environ["DVG_STEP_TRIG_EARLY"])
 if os.environ.get("DVG_STEP_EW"):        # developer build: 8 or 16 epilogue warps in the step kernel
     NVCC_FLAGS.append("-DDVG_STEP_EW=" + os.environ["DVG_STEP_EW"])
 if os.environ.get("DVG_TRACE"):          # developer build: per-CTA timestamps in the tensor-core kernel

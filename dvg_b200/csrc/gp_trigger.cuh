@@ -110,6 +110,20 @@ __device__ __forceinline__ float gp_trig_rows(const float* __restrict__ mat, con
   }
   return part;
 }
+// k_m = s exp(-0.5 ((x - z_m) / ell)^2) for all M inducing points, in registers.
+template <int M>
+__device__ __forceinline__ void gp_trig_kvec(float xv, float sc, float inv_ell, const float* __restrict__ z, float (&k)[M]) {
+#pragma unroll
+  for (int m = 0; m < M; m += 4) {
+    const float4 z4 = *reinterpret_cast<const float4*>(z + m);
+    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float t = (xv - zz[e]) * inv_ell;
+      k[m + e] = sc * ex2_ftz(t * t * (-0.5f * kLog2e));
+    }
+  }
+}
 template <int M>
 __device__ __forceinline__ void gp_trig_partial_rolled(float xv, float sc, float inv_ell, const float* __restrict__ linv,
                                                        const float* __restrict__ lqt, const float* __restrict__ z,

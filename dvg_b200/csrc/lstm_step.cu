@@ -60,6 +60,10 @@ constexpr int STEP_XMAX = 8;            // layer-0 items per pair (one x-ready m
 #define DVG_STEP_NPOLY 0      // measured on kth_s100: 3 -> 52.1 us, 2 -> 50.9, 1 -> 50.7, 0 -> 49.7 us per step
 #endif
 constexpr int STEP_NPOLY = DVG_STEP_NPOLY;   // sigmoid exponentials on the FMA pipe (rest: MUFU), see lstm_cell_fast
+#ifndef DVG_STEP_TRIG_EARLY
+#define DVG_STEP_TRIG_EARLY 1
+#endif
+constexpr bool STEP_TRIG_EARLY = DVG_STEP_TRIG_EARLY != 0;   // trigger partial sums before the first tile epilogue
 constexpr int STEP_BAR_BYTES = 384;     // mbarriers + tmem slot + misc words
 
 struct StepPhase {
@@ -440,6 +444,78 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       }
       if (etid == 0) TRACE(27);
     }
+    // ---- GP variance trigger (generate_frames.py:227-232,275): the last D CTAs evaluate one latent dim for every
+    //      rollout: FOUR threads per (rollout, dim) task -- |Linv k|^2 and |L_q^T k|^2, each split into two row halves
+    //      -- with the factors staged in the idle transpose buffers.  Nobody in this launch waits for the result
+    //      except the finalisers and the end-of-kernel restore / resample; running it in the idle window before the
+    //      first accumulator (STEP_TRIG_EARLY) makes the mask known ~15 us earlier, so a fired step's resample
+    //      problems start as soon as the first pairs finish.
+    //      (small grids -- fewer CTAs than latent dims -- take several dims per CTA)
+    auto trigger_partials = [&]() {
+      const int trig_ctas = p.trig.D < (int)gridDim.x ? p.trig.D : (int)gridDim.x;
+      if (!p.trig.enabled || (int)gridDim.x - 1 - (int)blockIdx.x >= trig_ctas) return;
+      const StepTrig& g = p.trig;
+      const int MP = g.mp;
+      constexpr int TPQ = STEP_EW * 8;              // threads per quarter
+      float* s_linv = reinterpret_cast<float*>(s_ebuf);
+      float* s_lqt = s_linv + MP * MP;
+      float* s_z = s_lqt + MP * MP;
+      float* s_part = s_z + MP;                     // [3][TPQ]
+      const int qt = etid / TPQ, li = etid % TPQ;
+      for (int d = (int)gridDim.x - 1 - (int)blockIdx.x; d < g.D; d += trig_ctas) {
+        ptx::named_bar_sync(1, STEP_EW * 32);       // every warp is done with its transpose buffer / the last dim
+        {
+          const float4* g1 = reinterpret_cast<const float4*>(g.linv + (size_t)d * MP * MP);
+          const float4* g2 = reinterpret_cast<const float4*>(g.lqt + (size_t)d * MP * MP);
+          for (int e = etid; e < MP * MP / 4; e += STEP_EW * 32) {
+            reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
+            reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
+          }
+          for (int e = etid; e < MP; e += STEP_EW * 32) s_z[e] = g.z[(size_t)d * MP + e];
+        }
+        const float ell = g.hyp[d * 4 + 0], sc = g.hyp[d * 4 + 1], noise = g.hyp[d * 4 + 3];
+        float xv[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {               // latents come from HBM: issue the loads of up to 4 rounds first
+          const int i = b * TPQ + li;
+          xv[b] = i < g.S ? __ldg(p.x + (size_t)g.stat_rows[i] * p.ldx + d) : 0.f;
+        }
+        ptx::named_bar_sync(1, STEP_EW * 32);
+        for (int base_s = 0; base_s < g.S; base_s += TPQ) {
+          const int i = base_s + li;
+          const int b = base_s / TPQ;
+          const float xi = b < 4 ? (b == 0 ? xv[0] : b == 1 ? xv[1] : b == 2 ? xv[2] : xv[3])
+                                 : (i < g.S ? __ldg(p.x + (size_t)g.stat_rows[i] * p.ldx + d) : 0.f);
+          float part = 0.f;
+          if (i < g.S) {
+            if (MP == 40) {
+              float kk[40];
+              gp_trig_kvec<40>(xi, sc, 1.0f / ell, s_z, kk);
+              part = qt == 0 ? gp_trig_rows<40, 0, 20>(s_linv, kk, 0, 20, 0.f)
+                   : qt == 1 ? gp_trig_rows<40, 0, 40>(s_linv, kk, 20, 40, 0.f)
+                   : qt == 2 ? gp_trig_rows<40, 0, 40>(s_lqt, kk, 0, 20, 0.f)
+                             : gp_trig_rows<40, 20, 40>(s_lqt, kk, 20, 40, 0.f);
+            } else if ((qt & 1) == 0) {
+              part = gp_trig_partial<0>(xi, sc, 1.0f / ell, MP, qt == 0 ? s_linv : s_lqt, s_z, qt != 0);
+            }
+          }
+          if (qt > 0) s_part[(qt - 1) * TPQ + li] = part;
+          ptx::named_bar_sync(1, STEP_EW * 32);
+          if (qt == 0 && i < g.S)
+            g.var_rows[(size_t)d * g.S + i] = (sc - (part + s_part[li])) + (s_part[TPQ + li] + s_part[2 * TPQ + li]) + noise;
+          ptx::named_bar_sync(1, STEP_EW * 32);
+        }
+        if (d == 0 && etid == 0) *g.trig_count = 0;   // ordered before the finalisers by the ticket below
+        __threadfence();
+        ptx::named_bar_sync(1, STEP_EW * 32);      // also: the transpose buffers go back to the tile epilogues
+        if (etid == 0) {
+          atomicAdd(g.ticket, 1u);
+          TRACE(26);
+        }
+      }
+    };
+    if (STEP_TRIG_EARLY) trigger_partials();
+
     int mit = 0;
     for (int k = 0;; ++k, ++mit) {
       const int item = item_at(k);
@@ -698,69 +774,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         if (p.trace) p.trace[(size_t)blockIdx.x * TRACE_SLOTS + 2 + tm * 8 + 6] = 1000000ull + item;
 #endif
       }
-      // ---- GP variance trigger (generate_frames.py:227-232,275): after their first tile the epilogue warps wait
-      //      for the next layer's accumulator anyway, so the last D CTAs (two items or fewer each) evaluate one latent
-      //      dim for every rollout there: two threads per (rollout, dim) task -- |Linv k|^2 and |L_q^T k|^2 -- with the
-      //      factors staged in the (now idle) transpose buffers.  Nobody in this launch waits for the result except
-      //      the finalisers and the end-of-kernel restore.
-      // (small grids -- fewer CTAs than latent dims -- take several dims per CTA)
-      const int trig_ctas = p.trig.D < (int)gridDim.x ? p.trig.D : (int)gridDim.x;
-      if (k == 0 && p.trig.enabled && (int)gridDim.x - 1 - (int)blockIdx.x < trig_ctas)
-      for (int d = (int)gridDim.x - 1 - (int)blockIdx.x; d < p.trig.D; d += trig_ctas) {
-        const StepTrig& g = p.trig;
-        const int MP = g.mp;
-        float* s_linv = reinterpret_cast<float*>(s_ebuf);
-        float* s_lqt = s_linv + MP * MP;
-        float* s_z = s_lqt + MP * MP;
-        float* s_part = s_z + MP;
-        ptx::named_bar_sync(1, STEP_EW * 32);     // every warp is done with its transpose buffer
-        {
-          const float4* g1 = reinterpret_cast<const float4*>(g.linv + (size_t)d * MP * MP);
-          const float4* g2 = reinterpret_cast<const float4*>(g.lqt + (size_t)d * MP * MP);
-          for (int e = etid; e < MP * MP / 4; e += STEP_EW * 32) {
-            reinterpret_cast<float4*>(s_linv)[e] = __ldg(g1 + e);
-            reinterpret_cast<float4*>(s_lqt)[e] = __ldg(g2 + e);
-          }
-          for (int e = etid; e < MP; e += STEP_EW * 32) s_z[e] = g.z[(size_t)d * MP + e];
-        }
-        const float ell = g.hyp[d * 4 + 0], sc = g.hyp[d * 4 + 1], noise = g.hyp[d * 4 + 3];
-        constexpr int TPH = STEP_EW * 16;            // threads per half: one (rollout, dim) task per thread pair
-        const int hf = etid / TPH, li = etid % TPH;
-        float xv[4];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {               // latents come from HBM: issue the loads of up to 4 rounds first
-          const int i = b * TPH + li;
-          xv[b] = i < g.S ? __ldg(p.x + (size_t)g.stat_rows[i] * p.ldx + d) : 0.f;
-        }
-        ptx::named_bar_sync(1, STEP_EW * 32);
-        for (int base_s = 0; base_s < g.S; base_s += TPH) {
-          const int i = base_s + li;
-          const int b = base_s / TPH;
-          float xi = b < 4 ? (b == 0 ? xv[0] : b == 1 ? xv[1] : b == 2 ? xv[2] : xv[3])
-                           : (i < g.S ? __ldg(p.x + (size_t)g.stat_rows[i] * p.ldx + d) : 0.f);
-          float pv = 0.f, pw = 0.f;
-          if (i < g.S) {
-            if (MP == 40) {
-              gp_trig_partial_rolled<40>(xi, sc, 1.0f / ell, hf == 0 ? s_linv : nullptr, hf == 0 ? nullptr : s_lqt, s_z,
-                                         pv, pw);
-            } else {
-              const float part = gp_trig_partial<0>(xi, sc, 1.0f / ell, MP, hf == 0 ? s_linv : s_lqt, s_z, hf != 0);
-              pv = part; pw = part;
-            }
-          }
-          if (hf == 1) s_part[li] = pw;
-          ptx::named_bar_sync(1, STEP_EW * 32);
-          if (hf == 0 && i < g.S) g.var_rows[(size_t)d * g.S + i] = (sc - pv) + s_part[li] + noise;
-          ptx::named_bar_sync(1, STEP_EW * 32);
-        }
-        if (d == 0 && etid == 0) *g.trig_count = 0;   // ordered before the finalisers by the ticket below
-        __threadfence();
-        ptx::named_bar_sync(1, STEP_EW * 32);      // also: the transpose buffers go back to the tile epilogues
-        if (etid == 0) {
-          atomicAdd(g.ticket, 1u);
-          TRACE(26);
-        }
-      }
+      if (!STEP_TRIG_EARLY && k == 0) trigger_partials();
     }
   }
 
@@ -1219,7 +1233,7 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
 }
 
 bool lstm_tc_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows) {
-  const size_t need = sizeof(float) * ((size_t)2 * g->mp * g->mp + g->mp + STEP_EW * 16);
+  const size_t need = sizeof(float) * ((size_t)2 * g->mp * g->mp + g->mp + 3 * STEP_EW * 8);
   const int pairs = h->sm_count / 2;
   return lstm_step_usable(h, rows) && !g->big && need <= (size_t)STEP_EBUF_BYTES && g->dims.num_dims <= pairs * 2;
 }
