@@ -38,12 +38,13 @@ WORKLOADS = {
     "kth_s100": dict(G=90, H=256, L=2, M=40, B=50, S=100, n_past=10, n_future=30, window=12),
     "smmnist_b16": dict(G=90, H=256, L=2, M=40, B=16, S=1, n_past=5, n_future=10, window=5),
     "bair_s32": dict(G=90, H=256, L=2, M=40, B=50, S=32, n_past=2, n_future=28, window=12),
+    "ucf_s100": dict(G=90, H=256, L=2, M=40, B=64, S=100, n_past=5, n_future=25, window=12),
 }
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
 # capture (profiles/r01_lstm_step.md); keyed by (workload, variant).
-NCU_TRAFFIC_BYTES = {("kth_s100", "bf16x3"): 34.6e6}
+NCU_TRAFFIC_BYTES = {("kth_s100", "bf16x3"): 33.2e6}
 
 
 def peaks():
@@ -292,8 +293,10 @@ def run_ours(args):
             "dtype": {"bf16x3": "fp32-grade (bf16x3 split products, fp32 accumulate)", "bf16": "bf16",
                       "fp32": "fp32"}[args.variant],
             "data": "synthetic",
-            "config": {"workload": args.workload + " (BASELINE configs[1]: KTH-shaped, B=50 x S=100 futures per GPU, "
-                       "10 past + 30 future, g_dim 90, rnn 256x2, GP M=40, trigger window 12)",
+            "config": {"workload": args.workload + (" (BASELINE configs[1]: KTH-shaped, B=50 x S=100 futures per GPU, "
+                       "10 past + 30 future, g_dim 90, rnn 256x2, GP M=40, trigger window 12)" if args.workload == "kth_s100"
+                                                    else " (B=%d x S=%d futures per GPU, %d past + %d future, g_dim %d, rnn %dx%d, GP M=%d, "
+                                                    "trigger window %d)" % (B, S, w["n_past"], w["n_future"], w["G"], w["H"], w["L"], w["M"], w["window"])),
                        "rows_per_gpu": R, "time_steps": T, "frames_per_step": frames_per_step,
                        "row_steps_per_s": world * R * T / (ms_per_step * 1e-3),
                        "variant": args.variant, "cuda_graph": True,

@@ -59,15 +59,28 @@ __global__ void __launch_bounds__(256) rollout_score_kernel(int T, int S, int B,
   if (live) {
     const size_t blk = (size_t)row0 * G + 4 * (size_t)j;
     const int ga = (4 * j) % G;             // column of element 0 within row ra
+    // per-element target offsets are the same for every time slice: computed once (the first version re-derived
+    // row % B and the column for every element of every slice and was instruction bound)
+    int toff[4];
+    bool ok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool first = e < split;
+      const int row = row0 + (first ? ra : rb);
+      ok[e] = row < R;
+      toff[e] = ok[e] ? (row % B) * G + (first ? ga + e : e - split) : 0;
+    }
+    const bool whole = row0 + rb < R;       // the float4 stays inside the valid rows of the tensor
+    const size_t slice_o = (size_t)R * G, slice_t = (size_t)B * G;
     for (int t0 = 0; t0 < T; t0 += TB) {
       float4 v[TB];
 #pragma unroll
       for (int u = 0; u < TB; ++u)
         if (t0 + u < T) {
-          const float* src = out + (size_t)(t0 + u) * R * G + blk;
-          if (row0 + rb < R) {
+          const float* src = out + (size_t)(t0 + u) * slice_o + blk;
+          if (whole) {
             v[u] = __ldcs(reinterpret_cast<const float4*>(src));
-          } else {            // the float4 would run past the last valid row of the tensor: element-wise
+          } else {            // would run past the last valid row: element-wise
             float x[4] = {0.f, 0.f, 0.f, 0.f};
             for (int e = 0; e < split; ++e) x[e] = __ldg(src + e);
             v[u] = make_float4(x[0], x[1], x[2], x[3]);
@@ -77,15 +90,12 @@ __global__ void __launch_bounds__(256) rollout_score_kernel(int T, int S, int B,
       for (int u = 0; u < TB; ++u) {
         if (t0 + u >= T) continue;
         const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        const float* tg = target + (size_t)(t0 + u) * B * G;
+        const float* tg = target + (size_t)(t0 + u) * slice_t;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const bool first = e < split;
-          const int row = row0 + (first ? ra : rb);
-          if (row < R) {
-            const int g = first ? ga + e : e - split;
-            const float dlt = x[e] - __ldg(tg + (size_t)(row % B) * G + g);
-            if (first) acc0 = fmaf(dlt, dlt, acc0);
+          if (ok[e]) {
+            const float dlt = x[e] - __ldg(tg + toff[e]);
+            if (e < split) acc0 = fmaf(dlt, dlt, acc0);
             else acc1 = fmaf(dlt, dlt, acc1);
           }
         }
