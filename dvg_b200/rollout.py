@@ -361,49 +361,145 @@ def posterior_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x
 def diverse_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample,
                     eps: Optional[Dict] = None, resample_every: Optional[int] = 15,
                     resample_at: Optional[Sequence[int]] = None, last_frame_skip=False, variant="bf16x3",
-                    record_latents=False):
+                    record_latents=False, codec=None, engine: Optional["RolloutEngine"] = None,
+                    eps_dev: Optional[torch.Tensor] = None, frames_out: Optional[torch.Tensor] = None):
     """generate_frames.py:138-178 / train.py:262-289 with the S samples batched.
 
     The context phase (i < n_past) is identical for every sample (teacher forcing, no randomness), so it
     is computed once with B rows; its LSTM state is then broadcast to the S*B rows of the engine.
     ``eps[(s, i)]`` ([D,B]) injects the rsample noise; missing entries are drawn with torch.randn.
-    Returns frames ``gen[t]`` of shape [S, B, C, H, W] (t < n_past: ground truth broadcast)."""
+    Returns frames ``gen[t]`` of shape [S, B, C, H, W] (t < n_past: ground truth broadcast).
+
+    ``codec`` (a ``dvg_b200.codec.BatchedCodec`` of the same encoder / decoder) switches the conv stacks to the
+    sample-batched execution of SURVEY §8f rank 2 (folded BatchNorm, channels-last, row chunks, skip half of the
+    decoder convs computed once per sequence).  ``engine`` reuses a prebuilt ``RolloutEngine``; ``eps_dev``
+    [n_hits, S, D, B] is the device-resident noise of the resample steps in order; ``frames_out``
+    [n_eval - n_ctx, S*B, C, H, W] receives the generated frames -- with all three the call is a fixed launch
+    sequence without host transfers (``PixelRollout`` captures it into one CUDA graph)."""
     B = x[0].shape[0]
     S = nsample
     D = gp_layer.num_dims
     dev = x[0].device
+    enc = encoder if codec is None else codec.encode
     frame_predictor.hidden = frame_predictor.init_hidden()
     skip = None
     x_in = x[0]
     i = 1
     while i < min(n_past, n_eval):
-        h, skip = encoder(x_in)
+        h, skip = enc(x_in)
         frame_predictor(h)
         x_in = x[i]
         i += 1
-    eng = RolloutEngine(frame_predictor, gp_layer, likelihood,
-                        RolloutConfig(n_points=B, n_rollouts=S, variant=variant))
+    eng = engine if engine is not None else RolloutEngine(
+        frame_predictor, gp_layer, likelihood, RolloutConfig(n_points=B, n_rollouts=S, variant=variant))
+    eng.cur = 0
     eng.load_broadcast_state(frame_predictor.hidden)
-    gens = [_rep(x[t], S).view(S, B, *x[t].shape[1:]) for t in range(i)]
-    lats = [None] * i
+    n_ctx = i
+    gens = [_rep(x[t], S).view(S, B, *x[t].shape[1:]) for t in range(n_ctx)] if frames_out is None else []
+    lats = [None] * n_ctx
     xs = _rep(x_in, S)
-    skip_s = [_rep(sk, S) for sk in skip] if skip is not None else None
+    shared = codec is not None and not last_frame_skip and skip is not None
+    if shared:
+        codec.set_shared_skips(skip)
+        skip_s = None
+    else:
+        skip_s = [_rep(sk, S) for sk in skip] if skip is not None else None
     out = torch.empty(S * B, D, device=dev)
-    for i in range(i, n_eval):
-        h, sk = encoder(xs)
-        if last_frame_skip or skip_s is None:
-            skip_s = sk
+    n_hit = 0
+    for i in range(n_ctx, n_eval):
+        if shared:
+            h, sk = codec.encode(xs, want_skips=False)
+        else:
+            h, sk = enc(xs)
+            if last_frame_skip or skip_s is None:
+                skip_s = sk
         hit = (resample_every is not None and i % resample_every == 0) or (resample_at is not None and i in resample_at)
         e = None
-        if hit:
+        if hit and eps_dev is not None:
+            e = eps_dev[n_hit]
+            n_hit += 1
+        elif hit:
             e = torch.stack([(eps[(s, i)] if eps is not None and (s, i) in eps else torch.randn(D, B)).to(dev)
                              for s in range(S)]).float().contiguous()
         eng.step_manual_mode(h.contiguous(), e, out, resample=hit)
-        xs = decoder([out, skip_s])
-        gens.append(xs.view(S, B, *xs.shape[1:]))
+        dst = frames_out[i - n_ctx] if frames_out is not None else None
+        if shared:
+            xs = codec.decode_shared(out, out=dst)
+        else:
+            xs = decoder([out, skip_s]) if codec is None else codec.decode(out, skip_s)
+            if dst is not None:
+                dst.copy_(xs)
+                xs = dst
+        if frames_out is None:
+            gens.append(xs.view(S, B, *xs.shape[1:]))
         if record_latents:
             lats.append(out.clone().view(S, B, D))
+    if frames_out is not None:
+        return (frames_out, lats) if record_latents else frames_out
     return (gens, lats) if record_latents else gens
+
+
+def resample_steps(n_past, n_eval, resample_every: Optional[int] = 15, resample_at: Optional[Sequence[int]] = None):
+    """The steps of the sampling phase at which ``diverse_rollout`` draws a GP sample (generate_frames.py:167)."""
+    return [i for i in range(min(n_past, n_eval), n_eval)
+            if (resample_every is not None and i % resample_every == 0) or (resample_at is not None and i in resample_at)]
+
+
+class PixelRollout:
+    """Pass B of ``make_gifs`` (generate_frames.py:138-178) in pixel space as ONE fixed launch sequence: context
+    phase on B rows, S*B-row sampling phase through ``BatchedCodec`` + ``RolloutEngine``; with ``graph=True`` the
+    whole thing (all conv launches included) is captured into a CUDA graph and ``run`` is a replay -- what makes the
+    small configurations (SM-MNIST, B=16: ~25 launches of a few microseconds per time step) launch-latency free.
+
+    ``x`` static [n_ctx, B, C, W, W] (context frames), ``eps`` static [n_hits, S, D, B]; ``frames``
+    [n_eval - n_ctx, S*B, C, W, W] is the result buffer."""
+
+    def __init__(self, frame_predictor, gp_layer, likelihood, encoder, decoder, frame_shape, n_points, nsample, n_past,
+                 n_eval, resample_every: Optional[int] = 15, resample_at: Optional[Sequence[int]] = None,
+                 variant="bf16x3", codec_dtype=torch.float32, chunk_rows: Optional[int] = None, graph: bool = True):
+        from .codec import BatchedCodec
+        self.args = (frame_predictor, gp_layer, likelihood, encoder, decoder)
+        self.B, self.S, self.n_past, self.n_eval = n_points, nsample, n_past, n_eval
+        self.kw = dict(resample_every=resample_every, resample_at=resample_at, variant=variant)
+        dev = next(frame_predictor.parameters()).device
+        D = gp_layer.num_dims
+        self.n_ctx = min(n_past, n_eval)
+        self.hits = resample_steps(n_past, n_eval, resample_every, resample_at)
+        self.codec = BatchedCodec(encoder, decoder, n_points, dtype=codec_dtype, chunk_rows=chunk_rows)
+        self.engine = RolloutEngine(frame_predictor, gp_layer, likelihood,
+                                    RolloutConfig(n_points=n_points, n_rollouts=nsample, variant=variant))
+        self.x = torch.zeros(self.n_ctx, n_points, *frame_shape, device=dev)
+        self.eps = torch.zeros(max(1, len(self.hits)), nsample, D, n_points, device=dev)
+        self.frames = torch.empty(n_eval - self.n_ctx, nsample * n_points, *frame_shape, device=dev)
+        self.graph = None
+        if graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._launch()                                  # cuDNN autotune / lazy allocations outside capture
+                self._launch()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+
+    def _launch(self):
+        fp, gp, lik, enc, dec = self.args
+        diverse_rollout(fp, gp, lik, enc, dec, list(self.x.unbind(0)), self.n_past, self.n_eval, self.S,
+                        codec=self.codec, engine=self.engine, eps_dev=self.eps, frames_out=self.frames, **self.kw)
+
+    def run(self, x=None, eps=None):
+        """Copy the inputs into the static buffers (when given) and launch; returns ``frames`` (async)."""
+        if x is not None:
+            self.x.copy_(torch.stack(list(x[:self.n_ctx])) if not torch.is_tensor(x) else x[:self.n_ctx])
+        if eps is not None:
+            self.eps.copy_(eps)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+        return self.frames
 
 
 @torch.no_grad()
@@ -469,7 +565,7 @@ def plot_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_p
 
 def make_gifs(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample,
               eps: Optional[Dict] = None, resample_every: Optional[int] = 15, last_frame_skip=False,
-              variant="bf16x3", metric="skimage"):
+              variant="bf16x3", metric="skimage", codec=None):
     """The computational part of ``make_gifs`` (generate_frames.py:107-217) with everything on the device:
     pass A (approximate posterior, GP mean), pass B (``nsample`` diverse futures, batched), SSIM / PSNR of every
     generated frame against the ground truth and the best-of-N choice per sequence (the gif writing is out of scope).
@@ -477,12 +573,14 @@ def make_gifs(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past
     Returns dict(posterior [n_eval][B,...], samples [n_eval][S,B,...], ssim [B,S,T_f], psnr [B,S,T_f], best [B]).
     ``metric="skimage"`` (default) is ``utils.eval_seq`` -- what the script calls (generate_frames.py:178) -- restated
     from the documented legacy skimage defaults (skimage itself is absent here: unpinned); ``metric="finn"`` is the
-    self-contained ``finn_eval_seq`` variant (utils.py:237-301), pinned to the reference's own functions."""
+    self-contained ``finn_eval_seq`` variant (utils.py:237-301), pinned to the reference's own functions.
+    ``codec``: optional ``BatchedCodec`` for the S*B-row sampling pass (see ``diverse_rollout``)."""
     from . import shard
     posterior = posterior_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval,
                                   last_frame_skip)
     samples = diverse_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval, nsample,
-                              eps=eps, resample_every=resample_every, last_frame_skip=last_frame_skip, variant=variant)
+                              eps=eps, resample_every=resample_every, last_frame_skip=last_frame_skip, variant=variant,
+                              codec=codec)
     gt = torch.stack([x[t] for t in range(n_past, n_eval)])                    # [T_f, B, C, H, W]
     gen = torch.stack([samples[t] for t in range(n_past, n_eval)])             # [T_f, S, B, C, H, W]
     ssim, psnr = (eval_seq if metric == "skimage" else eval_seq_finn)(gt, gen)  # [S, B, T_f]

@@ -321,6 +321,57 @@ def test_make_gifs_pixel_space_with_reference_convnets():
     enc.cpu(); dec.cpu()
 
 
+@pytest.mark.parametrize("model,nc", [("dcgan_64", 1), ("vgg_64", 3)])
+def test_batched_codec_pixel_rollout_matches_oracle(model, nc):
+    """Sample-batched conv execution (folded BN, channels-last, shared-skip decoder, row chunks)
+    and the CUDA-graphed ``PixelRollout`` against the sequential CPU oracle on the plain nets."""
+    from dvg_b200.codec import BatchedCodec
+    from dvg_b200.convnets import make_codec
+    from dvg_b200.rollout import PixelRollout, diverse_rollout, resample_steps
+    torch.manual_seed(0)
+    g_dim, B, S, n_past, n_eval = 90, 3, 4, 3, 8
+    enc, dec = make_codec(model, g_dim, nc)
+    for m in (enc, dec):
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.data.normal_(1.0, 0.02); mod.bias.data.zero_()
+                mod.running_mean.normal_(0, 0.05); mod.running_var.uniform_(0.5, 1.5)
+        m.eval()
+    sd = lstm_ref.random_lstm_state_dict(g_dim, g_dim, H, L, seed=14)
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(g_dim, M, seed=14, trained_like=True, smooth_mean=True)
+    g = torch.Generator().manual_seed(6)
+    x = [torch.rand(B, nc, 64, 64, generator=g) for _ in range(n_eval)]
+    eps = {(s, i): torch.randn(g_dim, B, generator=g) for s in range(S) for i in range(n_eval)}
+    with torch.no_grad():
+        om = rollout_ref.OracleModels(sd, gp_sd, lik_sd, enc, dec, gp_mode="direct")
+        ref = rollout_ref.diverse_rollout(om, x, n_past, n_eval, S, eps, resample_every=3)
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    enc_g, dec_g = enc.cuda(), dec.cuda()
+    xg = [t.cuda() for t in x]
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        codec = BatchedCodec(enc_g, dec_g, n_points=B, chunk_rows=2 * B)      # 2 chunks of the 12 rows
+        got = diverse_rollout(fp, gp, lik, enc_g, dec_g, xg, n_past, n_eval, S, eps=eps, resample_every=3, codec=codec)
+        for t in range(n_eval):
+            for s in range(S):
+                assert relerr(got[t][s], ref[s][t]) < 2e-3, (t, s)
+        hits = resample_steps(n_past, n_eval, 3)
+        assert hits == [3, 6]
+        eps_dev = torch.stack([torch.stack([eps[(s, i)] for s in range(S)]) for i in hits]).cuda()
+        for graph in (False, True):
+            pr = PixelRollout(fp, gp, lik, enc_g, dec_g, (nc, 64, 64), B, S, n_past, n_eval, resample_every=3, graph=graph)
+            for rep in range(2):                                 # a replay must not depend on leftover state
+                frames = pr.run(xg, eps_dev).clone()
+                for t in range(n_past, n_eval):
+                    for s in range(S):
+                        assert relerr(frames[t - n_past].view(S, B, nc, 64, 64)[s], ref[s][t]) < 2e-3, (graph, rep, t, s)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+        enc.cpu(); dec.cpu()
+
+
 @pytest.mark.parametrize("T,S,B,Gd", [(39, 100, 50, 90), (5, 3, 7, 90), (4, 9, 5, 10), (3, 2, 3, 128), (6, 5, 5, 66)])
 def test_score_rollouts_shapes(T, S, B, Gd):
     """Streaming scoring kernel: row counts that are not multiples of 8, latent sizes not multiples of 4."""
