@@ -23,6 +23,7 @@ EXPORTS = [
     "dvg_lstm_step", "dvg_lstm_profile", "dvg_gauss_lstm_step",
     "dvg_gp_prepare", "dvg_gp_refresh", "dvg_gp_prepare_factors", "dvg_gp_refresh_factors", "dvg_gp_destroy", "dvg_gp_predict", "dvg_gp_trigger",
     "dvg_gp_rsample", "dvg_gp_export", "dvg_rollout_step", "dvg_eval_seq_finn", "dvg_eval_seq", "dvg_rollout_score",
+    "dvg_moving_mnist_draws", "dvg_moving_mnist",
 ]
 
 
@@ -93,6 +94,8 @@ def load():
     lib.dvg_eval_seq_finn.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]
     lib.dvg_eval_seq.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]
     lib.dvg_rollout_score.argtypes = [c_int, c_int, c_int, c_int, P, P, P, P]
+    lib.dvg_moving_mnist_draws.argtypes = [c_int, c_int]
+    lib.dvg_moving_mnist.argtypes = [c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
         if name not in ("dvg_last_error", "dvg_lstm_state_bytes", "dvg_lstm_state_packed_offset"):

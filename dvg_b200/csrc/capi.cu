@@ -461,4 +461,18 @@ int dvg_rollout_score(int n_steps, int n_rollouts, int n_points, int dim, const 
   return rollout_score_launch(n_steps, n_rollouts, n_points, dim, latents, target, scores, (cudaStream_t)stream);
 }
 
+int dvg_moving_mnist_draws(int n_frames, int n_digits) { return n_digits * (5 + 4 * n_frames); }
+
+int dvg_moving_mnist(int n_seq, int n_frames, int image_size, int n_digits, int deterministic, const float* digit_bank,
+                     int n_bank, const uint32_t* draws, int draws_per_seq, int32_t* traj, float* frames,
+                     dvg_stream_t stream) {
+  DVG_REQUIRE(digit_bank && draws && traj && frames, "null argument");
+  DVG_REQUIRE(n_seq > 0 && n_frames > 0 && n_digits > 0 && n_bank > 0, "bad sizes");
+  DVG_REQUIRE(image_size > 33 && image_size % 4 == 0, "image_size must be a multiple of 4 and > 33 (got %d)", image_size);
+  DVG_REQUIRE(draws_per_seq >= dvg_moving_mnist_draws(n_frames, n_digits),
+              "draw stream too short: %d < %d words per sequence", draws_per_seq, dvg_moving_mnist_draws(n_frames, n_digits));
+  return moving_mnist_launch(n_seq, n_frames, image_size, n_digits, deterministic, digit_bank, n_bank, draws,
+                             draws_per_seq, traj, frames, (cudaStream_t)stream);
+}
+
 }  // extern "C"

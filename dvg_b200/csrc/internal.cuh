@@ -168,4 +168,8 @@ int eval_seq_skimage_launch(int T, int S, int B, int C, int H, int W, const floa
 int rollout_score_launch(int T, int S, int B, int G, const float* out, const float* target, float* scores,
                          cudaStream_t stream);
 
+// moving_mnist.cu
+int moving_mnist_launch(int B, int T, int W, int n_digits, int deterministic, const float* bank, int n_bank,
+                        const uint32_t* draws, int draws_per_seq, int32_t* traj, float* frames, cudaStream_t stream);
+
 }  // namespace dvg

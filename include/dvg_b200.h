@@ -249,6 +249,19 @@ DVG_API int dvg_eval_seq(int n_frames, int n_samples, int n_seq, int channels, i
 DVG_API int dvg_rollout_score(int n_steps, int n_rollouts, int n_points, int dim, const float* latents,
                       const float* target, float* scores, dvg_stream_t stream);
 
+/* Bouncing-digit batches on the device (data/moving_mnist.py:38-91, MovingMNIST.__getitem__, for n_seq samples at
+ * once).  digit_bank [n_bank, 32, 32] fp32 in [0,1] (the 32x32-scaled MNIST digits, :22-25).
+ * draws [n_seq, draws_per_seq] raw 32-bit integers: the k-th np.random.randint(lo, hi) call the reference makes for a
+ * sample (digit index, sx, sy, dx, dy, then the velocity redraws at bounces, digit after digit) is
+ * lo + draws[seq][k] % (hi - lo); draws_per_seq >= dvg_moving_mnist_draws(n_frames, n_digits) (the worst case).
+ * deterministic != 0 mirrors velocities at the walls instead (:58,65,72,79).  traj is workspace and by-product:
+ * int32 [n_seq, n_digits, 1 + 2*n_frames] = {digit index, (sx, sy) per frame}.  frames [n_frames, n_seq, 1, W, W] fp32
+ * -- the list-of-frames layout utils.normalize_data produces (utils.py:86-95) -- = min(1, sum of the digits). */
+DVG_API int dvg_moving_mnist_draws(int n_frames, int n_digits);
+DVG_API int dvg_moving_mnist(int n_seq, int n_frames, int image_size, int n_digits, int deterministic,
+                     const float* digit_bank, int n_bank, const uint32_t* draws, int draws_per_seq, int32_t* traj,
+                     float* frames, dvg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
