@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(128) mnist_traj_kernel(int B, int T, int W, in
 
 // One warp per frame, warp-stride loop over the T*B frames (grid sized to the SM count): no CTA barriers, every lane
 // streams 128-bit stores; the n_digits (index, sx, sy) triples are broadcast loads hoisted out of the pixel loop.
+template <int ND>
 __global__ void __launch_bounds__(256) mnist_render_kernel(int B, int T, int W, int n_digits,
                                                            const float* __restrict__ bank,
                                                            const int32_t* __restrict__ traj, float* __restrict__ frames) {
@@ -84,9 +85,9 @@ __global__ void __launch_bounds__(256) mnist_render_kernel(int B, int T, int W, 
   const int rec = 1 + 2 * T;
   for (long long f = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); f < n_frames; f += (long long)gridDim.x * wpb) {
     const int t = (int)(f / B), b = (int)(f - (long long)t * B);
-    int pi[MAX_DIGITS], px[MAX_DIGITS], py[MAX_DIGITS];
+    int pi[ND], px[ND], py[ND];
 #pragma unroll
-    for (int n = 0; n < MAX_DIGITS; ++n) {
+    for (int n = 0; n < ND; ++n) {
       pi[n] = 0; px[n] = 0; py[n] = -2 * DIGIT;          // unused slots never cover a pixel
       if (n < n_digits) {
         const int32_t* tr = traj + ((size_t)b * n_digits + n) * rec;
@@ -100,14 +101,14 @@ __global__ void __launch_bounds__(256) mnist_render_kernel(int B, int T, int W, 
       const int y = (q * 4) / W, x0 = (q * 4) - y * W;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int n = 0; n < MAX_DIGITS; ++n) {             // accumulation order of the reference's `+=` over digits (:85)
-        const int dyy = y - py[n];
-        if (dyy < 0 || dyy >= DIGIT) continue;
+      for (int n = 0; n < ND; ++n) {                     // accumulation order of the reference's `+=` over digits (:85)
+        const int dyy = y - py[n], dx0 = x0 - px[n];
+        if ((unsigned)dyy >= (unsigned)DIGIT || dx0 <= -4 || dx0 >= DIGIT) continue;   // quad outside this digit
         const float* d = bank + ((size_t)pi[n] * DIGIT + dyy) * DIGIT;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int dxx = x0 + j - px[n];
-          if (dxx >= 0 && dxx < DIGIT) v[j] += __ldg(d + dxx);
+          const int dxx = dx0 + j;
+          if ((unsigned)dxx < (unsigned)DIGIT) v[j] += __ldg(d + dxx);
         }
       }
       float4 o;                                          // x[x > 1] = 1 (:89)
@@ -134,7 +135,9 @@ int moving_mnist_launch(int B, int T, int W, int n_digits, int deterministic, co
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long want = ((long long)B * T + 7) / 8;
   const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
-  mnist_render_kernel<<<grid, 256, 0, stream>>>(B, T, W, n_digits, bank, traj, frames);
+  if (n_digits <= 2) mnist_render_kernel<2><<<grid, 256, 0, stream>>>(B, T, W, n_digits, bank, traj, frames);
+  else if (n_digits <= 4) mnist_render_kernel<4><<<grid, 256, 0, stream>>>(B, T, W, n_digits, bank, traj, frames);
+  else mnist_render_kernel<MAX_DIGITS><<<grid, 256, 0, stream>>>(B, T, W, n_digits, bank, traj, frames);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("moving_mnist launch: %s", cudaGetErrorString(e)); return DVG_ERR_CUDA; }
   return DVG_OK;

@@ -55,14 +55,20 @@ def test_full_size_properties_and_device_draws():
     pos = traj[:, :, 1:]
     assert pos.min().item() >= 0 and pos.max().item() < W - 32
     assert traj[:, :, 0].min().item() >= 0 and traj[:, :, 0].max().item() < 32
-    # per-frame mass never exceeds the mass of its digits, and equals it where the two digits do not overlap
+    # per-frame mass never exceeds the mass of its digits
     mass = bank.sum(dim=(1, 2))[traj[:, :, 0].long()].sum(1)            # [B]
     fm = frames.sum(dim=(2, 3, 4))                                      # [T, B]
     assert (fm <= mass[None] * (1 + 1e-5) + 1e-3).all()
-    sx, sy = pos[:, :, 0::2], pos[:, :, 1::2]                           # [B, n, T]
+    # ... and equals it where the digits do not overlap (needs an arena wider than two digits)
+    W2, B2 = 128, 200
+    f2, tr2 = moving_mnist_batch(bank, B2, T, W2, generator=g, return_traj=True)
+    pos2 = tr2[:, :, 1:]
+    sx, sy = pos2[:, :, 0::2], pos2[:, :, 1::2]                         # [B, n, T]
     apart = ((sx[:, 0] - sx[:, 1]).abs() >= 32) | ((sy[:, 0] - sy[:, 1]).abs() >= 32)    # [B, T]
-    assert apart.any()
-    assert torch.allclose(fm.t()[apart], mass[:, None].expand(B, T)[apart], rtol=1e-4, atol=1e-3)
+    assert apart.float().mean().item() > 0.3
+    mass2 = bank.sum(dim=(1, 2))[tr2[:, :, 0].long()].sum(1)
+    fm2 = f2.sum(dim=(2, 3, 4)).t()                                     # [B, T]
+    assert torch.allclose(fm2[apart], mass2[:, None].expand(B2, T)[apart], rtol=1e-4, atol=1e-3)
     # digits move: consecutive frames differ for (almost) every sequence
     assert ((frames[1:] - frames[:-1]).abs().sum(dim=(2, 3, 4)) > 0).float().mean().item() > 0.9
 
