@@ -11,24 +11,29 @@
 // producing pair).  Items are processed in a global order in which every dependency precedes its consumer and all pairs
 // are co-resident, so the schedule cannot deadlock.
 //
-// Warp roles (352 threads):
-//   warp 0      TMA producer (one lane): dependency polls, cp.async.bulk of the k-block stages
-//   warp 1      leader CTA: tcgen05.mma issuer;  peer CTA: relays "my stage landed" to the leader
-//   warps 2-9   x-pack prologue, GP trigger partial sums (CTAs < D), tile epilogues
-//   warp 10     auxiliary: in the last CTA it finalises the GP trigger (window / threshold / decision) once the D
-//               trigger CTAs have delivered their variances
+// Warp roles (608 threads with the default 16 epilogue warps):
+//   warp 0       TMA producer (one lane): dependency polls, cp.async.bulk of the k-block stages (the weight half of a
+//                stage is requested before the poll, L2 eviction hints: weights evict_last, activations evict_first)
+//   warp 1       leader CTA: tcgen05.mma issuer;  peer CTA: relays "my stage landed" to the leader
+//   warps 2-17   x-pack prologue of the pair's own layer-0 items, GP trigger partial sums (4 threads per
+//                (rollout, dim) task, in the idle window before the first accumulator is ready), tile epilogues;
+//                after the CTA's last tile: GP resample problems of the fired rollouts from a dynamic queue
+//   warp 18      auxiliary: in the last ceil(S/32) CTAs it finalises the GP trigger (window / threshold / decision)
+//                once the partial variances have been delivered, and publishes the mask
 //
-// What changed against the first fused kernel (profiles/r01_lstm_fused.md, ncu + timestamp traces):
+// Design decisions that came out of the ncu / %globaltimer traces (profiles/r01_lstm_step.md):
 //   * the x operand is packed by the consuming pair itself into a private scratch slab (no all-CTA pre-pass, no
 //     cross-CTA flag on the way to the first MMA);
 //   * k-block granular dependencies instead of "all N tiles of the row group";
-//   * the LSTM epilogue is a compact loop over 8 hidden units (the fully unrolled version was 36 KB of straight-line
+//   * the LSTM epilogue is a compact loop over 4 hidden units (a fully unrolled version was 36 KB of straight-line
 //     code and ~70 % of its issue slots were instruction-fetch stalls); results are parked in already consumed TMEM
 //     columns (tcgen05.st) so no register array needs dynamic indexing;
 //   * nobody waits for the trigger mask: the LSTM always advances and, in the rare step where rollouts fired, their
 //     state rows are restored from the input block at the end of the launch (generate_frames.py:289-295: a triggered
-//     rollout does not advance its LSTM);
-//   * the trigger is finalised by a dedicated warp instead of stalling one CTA's epilogue warps.
+//     rollout does not advance its LSTM) and their GP samples (generate_frames.py:291-292) are computed by the CTAs
+//     that run out of tiles first;
+//   * the trigger is finalised by a dedicated warp instead of stalling one CTA's epilogue warps;
+//   * consecutive launches overlap their prologue / teardown through programmatic dependent launch.
 #include <stdlib.h>
 
 #include <algorithm>

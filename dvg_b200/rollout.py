@@ -173,9 +173,8 @@ class RolloutEngine:
 
     def capture_latent_rollout(self, lat, eps, out, masks=None, values=None, post=None):
         """CUDA-graph the whole T-step latent rollout (static launch sequence, zero host work per replay).
-        T must be even so the ping-pong state returns to block 0; call ``reset()`` semantics are captured
-        too (the graph zeroes state and window first)."""
-        assert lat.shape[0] % 2 == 0 or True
+        ``reset()`` is captured too (the graph zeroes state and window first), so every replay starts from block 0
+        whatever the parity of T."""
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

@@ -1,4 +1,4 @@
-"""Summarise a DVG_TRACE dump of lstm_fused_kernel (stderr of a DVG_TC_TRACE=1 run)."""
+"""Summarise a DVG_TRACE dump of lstm_step_kernel (stderr of a DVG_TC_TRACE=1 run)."""
 import sys
 import numpy as np
 
