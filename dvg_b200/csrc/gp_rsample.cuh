@@ -150,11 +150,14 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
   }
   // Sigma_y, lower triangle: the N (N + 1) / 2 pairs (a, b <= a) are dealt out flat (b fastest: one row a is a
   // broadcast, consecutive rows b are conflict free), so every thread gets the same number of pairs.
-  for (int pidx = tid; pidx < N * (N + 1) / 2; pidx += NTHR) {
-    int a = (int)((sqrtf(8.f * (float)pidx + 1.f) - 1.f) * 0.5f);
+  const int npairs = N * (N + 1) / 2;
+  auto pair_of = [](int pidx, int& a, int& b) {
+    a = (int)((sqrtf(8.f * (float)pidx + 1.f) - 1.f) * 0.5f);
     while (a * (a + 1) / 2 > pidx) --a;
     while ((a + 1) * (a + 2) / 2 <= pidx) ++a;
-    const int b = pidx - a * (a + 1) / 2;
+    b = pidx - a * (a + 1) / 2;
+  };
+  auto sigma_y = [&](int a, int b) -> float {
     const float4* ra4 = reinterpret_cast<const float4*>(s_r + a * ldk);
     const float4* rb4 = reinterpret_cast<const float4*>(s_r + b * ldk);
     const float4* ua4 = reinterpret_cast<const float4*>(s_u + a * ldk);
@@ -170,48 +173,101 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
     }
     const float t = (s_x[a] - s_x[b]) * inv_ell;
     const float kxx = a == b ? sc : sc * expf(-0.5f * t * t);
-    s_sig[a * lds + b] = (rr0 + rr1) + (kxx - (uu0 + uu1)) + (a == b ? noise : 0.f);
-  }
-  sync();
-  RSQ();
-  // Cholesky as LDL^T, right-looking with UNSCALED columns (one barrier per column): after step j the trailing
-  // block holds S - sum_{k<=j} c_k c_k^T / d_k with c_k the unscaled column k and d_k its diagonal;
-  // L[i][j] = c_j[i] / sqrt(d_j) is applied in one pass at the end.  ~41 k cycles for N = 50 and the largest phase
-  // left: two alternatives were measured and were no faster -- panels of 4 columns (two barriers per panel, 44.6 k:
-  // the read-modify-write of the trailing block through shared memory serialises on LDS -> FMA -> STS latency either
-  // way) and a left-looking one-thread-per-row variant (loads only, 64-thread barrier, 47.5 k: two lone warps issue at
-  // ~0.25 IPC).  Next: several problems per CTA (one per warp pair) instead of 256 threads on one.
-  for (int j = 0; j + 1 < N; ++j) {
-    const float inv_d = __fdividef(1.0f, s_sig[j * lds + j]);
-    const int a = j + 1 + fi;                             // this thread's ROW (consecutive threads -> stride lds, odd:
-    if (a < N) {                                          // conflict-free; columns b are warp-uniform -> broadcast)
-      const float ca = s_sig[a * lds + j] * inv_d;
-      // batches of 4 with all loads issued before the first store: a plain read-modify-write loop serialises on
-      // LDS -> FMA -> STS because the compiler must assume the store aliases the next loads
-      for (int b0 = j + 1 + grp; b0 <= a; b0 += 4 * ngrp) {
-        float xv[4], yv[4];
+    return (rr0 + rr1) + (kxx - (uu0 + uu1)) + (a == b ? noise : 0.f);
+  };
+  // Cholesky as LDL^T, right-looking with UNSCALED columns: after step j the trailing block holds
+  // S - sum_{k<=j} c_k c_k^T / d_k with c_k the unscaled column k and d_k its diagonal; L[i][j] = c_j[i] / sqrt(d_j)
+  // is applied in one pass at the end.
+  constexpr int SLOTS = 2048 / NTHR;                     // matrix elements a thread can own in registers
+  if (npairs <= SLOTS * NTHR) {
+    // Register-resident variant (N <= 63): every thread OWNS its <= SLOTS elements of the triangle for the whole
+    // factorisation; per column the owners of column j publish it to a double-buffered N-float vector, one barrier,
+    // and every owner of a trailing element applies x -= (c[a] / d) c[b] in registers: no read-modify-write of the
+    // trailing block through shared memory.  Same operations in the same order per element, so the result is
+    // bit-identical to the shared-memory variant below.
+    float xv[SLOTS];
+    int ar[SLOTS], br[SLOTS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int b = b0 + u * ngrp;
-          xv[u] = b <= a ? s_sig[a * lds + b] : 0.f;
-          yv[u] = b <= a ? s_sig[b * lds + j] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int b = b0 + u * ngrp;
-          if (b <= a) s_sig[a * lds + b] = fmaf(-ca, yv[u], xv[u]);
-        }
+    for (int k = 0; k < SLOTS; ++k) {
+      const int pidx = tid + k * NTHR;
+      xv[k] = 0.f; ar[k] = 0; br[k] = -1;                // empty slot: never a column owner, never trailing
+      if (pidx < npairs) {
+        pair_of(pidx, ar[k], br[k]);
+        xv[k] = sigma_y(ar[k], br[k]);
       }
     }
+    RSQ();
+    // (Measured, cycles for N = 50 on 16 warps: shared-memory variant ~18 k, this one 14.5 k = ~300 per column, the
+    // barrier round trip dominating; a two-columns-per-barrier version that re-derives the second column locally
+    // was slower, 24 k: two dependent reciprocals and seven LDS per element on the chain.)
+    float* colbuf = s_k;                                 // K_xz is dead after the U / R phase: 2 x N floats of it
+    for (int j = 0; j + 1 < N; ++j) {
+      float* col = colbuf + (j & 1) * N;
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k)
+        if (br[k] == j) col[ar[k]] = xv[k];
+      sync();
+      const float inv_d = __fdividef(1.0f, col[j]);
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k)
+        if (br[k] > j) {
+          const float ca = col[ar[k]] * inv_d;
+          xv[k] = fmaf(-ca, col[br[k]], xv[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k)
+      if (ar[k] == br[k]) s_t[ar[k]] = xv[k];            // d_j
+    sync();
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k)
+      if (br[k] >= 0) s_sig[ar[k] * lds + br[k]] = ar[k] == br[k] ? sqrtf(xv[k]) : xv[k] * rsqrtf(s_t[br[k]]);
+    sync();
+  } else {
+    for (int pidx = tid; pidx < npairs; pidx += NTHR) {
+      int a, b;
+      pair_of(pidx, a, b);
+      s_sig[a * lds + b] = sigma_y(a, b);
+    }
+    sync();
+    RSQ();
+    // Shared-memory variant (one barrier per column).  ~41 k cycles for N = 50 with 256 threads; two alternatives
+    // were measured and were no faster -- panels of 4 columns (two barriers per panel, 44.6 k: the read-modify-write
+    // of the trailing block through shared memory serialises on LDS -> FMA -> STS latency either way) and a
+    // left-looking one-thread-per-row variant (loads only, 64-thread barrier, 47.5 k: two lone warps issue at
+    // ~0.25 IPC).
+    for (int j = 0; j + 1 < N; ++j) {
+      const float inv_d = __fdividef(1.0f, s_sig[j * lds + j]);
+      const int a = j + 1 + fi;                           // this thread's ROW (consecutive threads -> stride lds, odd:
+      if (a < N) {                                        // conflict-free; columns b are warp-uniform -> broadcast)
+        const float ca = s_sig[a * lds + j] * inv_d;
+        // batches of 4 with all loads issued before the first store: a plain read-modify-write loop serialises on
+        // LDS -> FMA -> STS because the compiler must assume the store aliases the next loads
+        for (int b0 = j + 1 + grp; b0 <= a; b0 += 4 * ngrp) {
+          float xv[4], yv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int b = b0 + u * ngrp;
+            xv[u] = b <= a ? s_sig[a * lds + b] : 0.f;
+            yv[u] = b <= a ? s_sig[b * lds + j] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int b = b0 + u * ngrp;
+            if (b <= a) s_sig[a * lds + b] = fmaf(-ca, yv[u], xv[u]);
+          }
+        }
+      }
+      sync();
+    }
+    for (int j = grp; j < N; j += ngrp) {
+      const float rs = rsqrtf(s_sig[j * lds + j]);
+      if (fi > j && fi < N) s_sig[fi * lds + j] *= rs;
+    }
+    sync();
+    for (int j = tid; j < N; j += NTHR) s_sig[j * lds + j] = sqrtf(s_sig[j * lds + j]);
     sync();
   }
-  for (int j = grp; j < N; j += ngrp) {
-    const float rs = rsqrtf(s_sig[j * lds + j]);
-    if (fi > j && fi < N) s_sig[fi * lds + j] *= rs;
-  }
-  sync();
-  for (int j = tid; j < N; j += NTHR) s_sig[j * lds + j] = sqrtf(s_sig[j * lds + j]);
-  sync();
   RSQ();
   for (int n = tid; n < N; n += NTHR) {
     float a0 = 0.f, a1 = 0.f;

@@ -53,12 +53,14 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--arms", nargs="+", default=["plain", "codec", "codec_bf16", "graph", "graph_bf16"])
     ap.add_argument("--out", default="gpurun_out/pixel_bench.json")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="torch.backends.cudnn.benchmark = True (autotuned convs)")
     args = ap.parse_args()
     from dvg_b200.codec import BatchedCodec
     from dvg_b200.convnets import make_codec
     from dvg_b200.rollout import PixelRollout, RolloutConfig, RolloutEngine, diverse_rollout, resample_steps
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = args.cudnn_benchmark
     results = []
     for name in args.workloads:
         model, nc, width, n_past, n_eval, s_over = PIXEL[name]
@@ -75,7 +77,7 @@ def main():
         eps_dev = torch.randn(max(1, len(hits)), S, w["G"], B, generator=g).to(dev)
         frames = S * B * (n_eval - n_past)
         row = {"workload": name, "codec": model, "B": B, "S": S, "rows": S * B, "n_past": n_past, "n_eval": n_eval,
-               "frames_per_rollout": frames, "arms": {}}
+               "frames_per_rollout": frames, "cudnn_benchmark": args.cudnn_benchmark, "arms": {}}
         eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S))
         fbuf = torch.empty(n_eval - min(n_past, n_eval), S * B, nc, width, width, device=dev)
 
