@@ -384,6 +384,8 @@ int dvg_gp_rsample(dvg_gp_t h, int n_rollouts, int n_points, const float* x, int
                    const uint8_t* mask, float* out, int ldo, dvg_stream_t stream) {
   DVG_REQUIRE(h && x && eps && out, "null argument");
   DVG_REQUIRE(n_rollouts > 0 && n_points > 0, "bad sizes");
+  DVG_REQUIRE(n_points <= 128, "rsample correlates at most 128 points per call (got %d): the [N,N] covariance is factorised "
+              "in shared memory", n_points);
   DVG_REQUIRE(ldx >= h->dims.num_dims && ldo >= h->dims.num_dims, "bad leading dimension");
   DVG_REQUIRE(!h->big, "rsample with a large inducing set (pre-computed factors, M=%d) is not implemented yet",
               h->dims.num_inducing);

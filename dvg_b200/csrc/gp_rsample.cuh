@@ -52,7 +52,21 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
   float* s_eps = s_t + N;              // [N]
   float* s_z = s_eps + N;              // [MP]
   float* s_beta = s_z + MP;            // [MP]
+  // All global operands are requested before the first shared-memory store, so the problem pays ONE L2 round trip
+  // (~1 k cycles) instead of three dependent ones (factors, then z / beta / x / eps, then the hyper-parameters).
+  const float ell = __ldg(hyp + d * 4 + 0), sc = __ldg(hyp + d * 4 + 1), c = __ldg(hyp + d * 4 + 2),
+              noise = __ldg(hyp + d * 4 + 3);
   {
+    // N, MP <= 128 <= NTHR: one element per thread
+    float zr = 0.f, betar = 0.f, xr = 0.f, er = 0.f;
+    if (tid < MP) {
+      zr = __ldg(zall + (size_t)d * MP + tid);
+      betar = __ldg(alpha_all + (size_t)d * MP + tid);
+    }
+    if (tid < N) {
+      xr = __ldg(x + (size_t)(s_idx * N + tid) * ldx + d);
+      er = __ldg(eps + ((size_t)s_idx * D + d) * N + tid);
+    }
     const float4* g1 = reinterpret_cast<const float4*>(linv_all + (size_t)d * MP * MP);
     const float4* g2 = reinterpret_cast<const float4*>(lqt_all + (size_t)d * MP * MP);
     const int n4 = MP * MP / 4;
@@ -72,16 +86,9 @@ __device__ __forceinline__ void gp_rsample_body(float* smf, const int tid, Sync 
         }
       }
     }
-    for (int e = tid; e < MP; e += NTHR) {
-      s_z[e] = __ldg(zall + (size_t)d * MP + e);
-      s_beta[e] = __ldg(alpha_all + (size_t)d * MP + e);
-    }
-    for (int n = tid; n < N; n += NTHR) {
-      s_x[n] = __ldg(x + (size_t)(s_idx * N + n) * ldx + d);
-      s_eps[n] = __ldg(eps + ((size_t)s_idx * D + d) * N + n);
-    }
+    if (tid < MP) { s_z[tid] = zr; s_beta[tid] = betar; }
+    if (tid < N) { s_x[tid] = xr; s_eps[tid] = er; }
   }
-  const float ell = hyp[d * 4 + 0], sc = hyp[d * 4 + 1], c = hyp[d * 4 + 2], noise = hyp[d * 4 + 3];
   const float inv_ell = 1.0f / ell;
   sync();
   RSQ();

@@ -200,7 +200,8 @@ DVG_API int dvg_gp_trigger(dvg_gp_t h, int n_rollouts, const float* x, int ldx, 
  * mask is set (mask NULL = all):  latent[s*N + n, d] = mean + (chol(Sigma_y) eps)[n] with
  * Sigma_y the full [N,N] predictive covariance of rollout s in dimension d.
  *   x [S*N, D] (ldx), eps [S, D, N] standard normal, out [S*N, D] (ldo) -- rows of unmasked rollouts are
- *   left untouched, so `out` can be the LSTM output buffer (on-device select).
+ *   left untouched, so `out` can be the LSTM output buffer (on-device select).  N <= 128 (the batch size of one
+ *   rollout; the reference correlates exactly the N points of one call).
  *   When `mask` is the very buffer the last dvg_gp_trigger call on this handle wrote (same pointer, same
  *   n_rollouts), the compacted list of fired rollouts produced by that call is used instead of re-reading it. */
 DVG_API int dvg_gp_rsample(dvg_gp_t h, int n_rollouts, int n_points, const float* x, int ldx,

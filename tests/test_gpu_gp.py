@@ -86,6 +86,32 @@ def test_rsample(trained):
     assert relerr(got, want) < 1e-4
 
 
+@pytest.mark.parametrize("D,M,N", [(5, 40, 1), (7, 24, 2), (3, 40, 63), (3, 40, 64), (2, 64, 100), (2, 40, 128)])
+def test_rsample_sizes(D, M, N):
+    """Point counts around the register-resident Cholesky's limit (N <= 63 with 256 threads in the stand-alone kernel)
+    and up to the documented maximum of 128."""
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=5 + N, trained_like=True, smooth_mean=True)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    g = torch.Generator().manual_seed(N)
+    h = torch.tanh(torch.randn(N, D, generator=g))
+    eps = torch.randn(D, N, generator=g)
+    ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h), torch.float64, "direct")
+    want = gp_ref.rsample(ref["mean"], ref["covar"], eps.double())
+    with torch.no_grad():
+        got = lik(gp(h.cuda().transpose(0, 1).view(D, N, 1))).rsample(eps=eps.cuda())
+    assert relerr(got, want) < 1e-4
+
+
+def test_rsample_rejects_more_than_128_points():
+    from dvg_b200 import _capi
+    D, M, N = 2, 40, 129
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=1)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    h = torch.tanh(torch.randn(N, D))
+    with torch.no_grad(), pytest.raises(_capi.DvgError):
+        lik(gp(h.cuda().transpose(0, 1).view(D, N, 1))).rsample(eps=torch.randn(D, N).cuda())
+
+
 def test_trigger_sequence_matches_numpy_oracle():
     """Device window / threshold / decision vs oracle/trigger_ref.py over a 60-step sequence for S=7
     independent rollouts (decisions bit-exact outside a 1e-5 band around the threshold)."""
