@@ -333,6 +333,28 @@ def _rep(t, S):
 
 
 @torch.no_grad()
+def generation(frame_predictor, encoder, decoder, x_in, skip):
+    """``generation`` of generate_frames.py:220-224: one autoregressive pixel step, ``decoder([frame_predictor(
+    encoder(x_in)[0]), skip])``; advances ``frame_predictor.hidden``."""
+    h = encoder(x_in)[0]
+    return decoder([frame_predictor(h), skip])
+
+
+@torch.no_grad()
+def var_value(gp_layer, likelihood, encoder, x_in, context_array, stat_col: int = 3):
+    """``var_value`` of generate_frames.py:227-232 without the host round trip: the trigger statistic
+    ``||variance[:, stat_col]||_2`` over the latent dims of the encoder latent of ``x_in`` and the window slid by
+    one.  ``context_array`` is a 1-D float tensor (any device); both results stay on the GPU.  The batched,
+    fused form of the same arithmetic is ``RolloutEngine.step_trigger_mode``."""
+    h = encoder(x_in)[0]
+    D = gp_layer.num_dims
+    var = likelihood(gp_layer(h.transpose(0, 1).view(D, h.shape[0], 1))).variance          # [D, N]
+    value = var[:, stat_col].float().norm()
+    ctx = torch.as_tensor(context_array, dtype=torch.float32, device=value.device)
+    return value, torch.cat([ctx[1:], value.reshape(1)])
+
+
+@torch.no_grad()
 def posterior_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, n_past, n_eval,
                       last_frame_skip=False):
     """generate_frames.py:111-134 (B rows).  Returns the list of n_eval frames."""

@@ -321,6 +321,41 @@ def test_make_gifs_pixel_space_with_reference_convnets():
     enc.cpu(); dec.cpu()
 
 
+def test_generation_and_var_value_helpers():
+    """The script-level helpers of generate_frames.py:220-232 (``generation``, ``var_value``) against the oracle."""
+    from dvg_b200.convnets import make_codec
+    from dvg_b200.rollout import generation, var_value
+    from oracle import trigger_ref
+    torch.manual_seed(0)
+    g_dim, B = 90, 6
+    enc, dec = make_codec("dcgan_64", g_dim, 1)
+    enc.eval(); dec.eval()
+    sd = lstm_ref.random_lstm_state_dict(g_dim, g_dim, H, L, seed=15)
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(g_dim, M, seed=15, trained_like=True, smooth_mean=True)
+    g = torch.Generator().manual_seed(8)
+    x0, x1 = torch.rand(B, 1, 64, 64, generator=g), torch.rand(B, 1, 64, 64, generator=g)
+    ctx = torch.rand(12, generator=g)
+    with torch.no_grad():
+        h0, skip = enc(x0)
+        pred, _ = lstm_ref.lstm_forward(sd, h0, lstm_ref.init_hidden(L, B, H))
+        want_frame = dec([pred, skip])
+        h1 = enc(x1)[0]
+        ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h1), torch.float64, "direct", full_cov=False)
+        want_value = trigger_ref.trigger_value(ref["variance"].float().numpy(), 3)
+        want_ctx = trigger_ref.slide(ctx.numpy(), want_value)
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    enc_g, dec_g = enc.cuda(), dec.cuda()
+    fp.hidden = fp.init_hidden()
+    got = generation(fp, enc_g, dec_g, x0.cuda(), [s.cuda() for s in skip])
+    assert relerr(got, want_frame) < 2e-3
+    value, new_ctx = var_value(gp, lik, enc_g, x1.cuda(), ctx)
+    assert value.is_cuda and new_ctx.is_cuda and new_ctx.shape == (12,)
+    assert abs(value.item() - float(want_value)) < 1e-4 * float(want_value)
+    assert np.allclose(new_ctx.cpu().numpy(), want_ctx, rtol=1e-4)
+    enc.cpu(); dec.cpu()
+
+
 @pytest.mark.parametrize("model,nc", [("dcgan_64", 1), ("vgg_64", 3)])
 def test_batched_codec_pixel_rollout_matches_oracle(model, nc):
     """Sample-batched conv execution (folded BN, channels-last, shared-skip decoder, row chunks)
