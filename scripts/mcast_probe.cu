@@ -1,19 +1,22 @@
-// L2 -> shared-memory operand streaming with and without cluster multicast: the measurement behind DESIGN.md §7
-// item 1 (the step kernel's MMA phases run at the ~9.5 TB/s L2 -> SM rate: 64 KB per k-block and CTA, of which the
-// 32 KB activation half is the same for the CTAs that work on the N tiles of one row group).
+// Operand-ring probes for lstm_step_kernel (results: profiles/r01_mcast_probe.md).
 //
-// Every CTA streams ITERS stages of 64 KB through a 3-stage ring, like lstm_step_kernel's producer:
+// Part 1 -- L2 -> shared-memory streaming with and without cluster multicast.  Every CTA streams ITERS stages of
+// 64 KB through a 3-stage ring, like the step kernel's producer:
 //   private half (32 KB)   cp.async.bulk by the CTA itself                      (the weight images)
 //   shared half  (32 KB)   CLUSTER == 1: cp.async.bulk by the CTA itself
 //                          CLUSTER  > 1: each CTA of the cluster multicasts its 1/CLUSTER slice to all of them
 // A stage is "consumed" by one warp reading a few words of it; with multicast a stage may only be refilled once every
 // CTA of the cluster has released it (remote arrives on each CTA's empty barrier).  Sources stay L2 resident
-// (footprint well below 126 MB), so the result is the L2 -> SM path, not HBM.
+// (footprint well below 126 MB), so the result is the L2 -> SM path, not HBM.  Measured (round 1): 0.48 us per stage
+// = 20 TB/s without multicast, 1.07 / 1.42 / 2.09 us with clusters of 2 / 4 / 8.
+//
+// Part 2 -- the cta_group::2 pair protocol in isolation (pair_kernel below; not yet run): relay hop vs completing the
+// peer's copies on the leader's barrier, with and without emulated tensor work.
 //
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I dvg_b200/csrc -o /tmp/mcast_probe \
-//        scripts/mcast_probe.cu && /tmp/mcast_probe
-// Output: one JSON line per cluster size with the smem fill rate and the L2 read rate.  mbarrier waits trap after ~2 s
-// instead of hanging (ptx.cuh), so a protocol bug shows up as a CUDA error.
+//        scripts/mcast_probe.cu && /tmp/mcast_probe [iters]
+// Output: one JSON line per configuration.  mbarrier waits trap after ~2 s instead of hanging (ptx.cuh), so a protocol
+// bug shows up as a CUDA error.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -81,6 +84,112 @@ __global__ void __launch_bounds__(THREADS, 1) probe_kernel(const uint8_t* __rest
   }
   __syncthreads();
   if (CLUSTER > 1) ptx::cluster_sync_all();          // nobody exits while peers may still arrive on its barriers
+}
+
+// The step kernel's pair protocol in isolation: both CTAs of a cta_group::2 pair fill their own 64 KB stage, ONE
+// consumer (the leader's MMA issuer) needs both halves, "computes" for `busy` cycles (0.78 us of tensor work per k-block
+// in the real kernel) and releases the stage to both producers (tcgen05.commit multicast in the real kernel, two
+// arrives here).
+//   DIRECT == 0   as lstm_step_kernel does it today: the peer's relay warp waits for its own full barrier and then
+//                 arrives on the leader's `pfull` barrier
+//   DIRECT == 1   the peer's bulk copies complete on the LEADER's pfull barrier (remote expect_tx + remote mbarrier
+//                 operand), no relay hop -- if the hardware rejects a completion barrier outside the destination CTA
+//                 this variant traps / reports a CUDA error, which is the answer too
+template <int DIRECT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+    pair_kernel(const uint8_t* __restrict__ src, int n_chunks, int iters, int busy, unsigned* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) unsigned long long bars[3 * STAGES];
+  const uint32_t full0 = ptx::smem_u32(&bars[0]), empty0 = ptx::smem_u32(&bars[STAGES]),
+                 pfull0 = ptx::smem_u32(&bars[2 * STAGES]);
+  const uint32_t rank = ptx::cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full0 + 8 * s, 1);
+      ptx::mbar_init(empty0 + 8 * s, 1);             // released by the leader's consumer
+      ptx::mbar_init(pfull0 + 8 * s, 1);             // relay arrive, or the peer's remote expect_tx
+    }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  ptx::cluster_sync_all();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    uint32_t leader_pfull0;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_pfull0) : "r"(pfull0), "r"(0));
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      if (it >= STAGES) ptx::mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+      const uint32_t dst = ptx::smem_u32(smem + (size_t)s * STAGE_BYTES);
+      const uint8_t* g = src + (size_t)((blockIdx.x * 7 + it) % n_chunks) * STAGE_BYTES;
+      if (DIRECT && rank == 1) {
+        const uint32_t bar = leader_pfull0 + 8 * s;
+        asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"((uint32_t)STAGE_BYTES)
+                     : "memory");
+        ptx::bulk_g2s(dst, g, HALF, bar);
+        ptx::bulk_g2s(dst + HALF, g + HALF, HALF, bar);
+      } else {
+        ptx::mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+        ptx::bulk_g2s(dst, g, HALF, full0 + 8 * s);
+        ptx::bulk_g2s(dst + HALF, g + HALF, HALF, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    if (rank == 0) {
+      unsigned acc = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        ptx::mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+        ptx::mbar_wait(pfull0 + 8 * s, (it / STAGES) & 1);
+        acc += reinterpret_cast<const unsigned*>(smem + (size_t)s * STAGE_BYTES)[it & 1023];
+        const long long t0 = clock64();
+        while (clock64() - t0 < busy) {}
+        ptx::mbar_arrive_remote(empty0 + 8 * s, 0);
+        ptx::mbar_arrive_remote(empty0 + 8 * s, 1);
+      }
+      if (acc == 0x12345678u) sink[0] = acc;
+    } else if (!DIRECT) {
+      for (int it = 0; it < iters; ++it) {           // relay: "my stage landed" -> leader's pfull
+        const int s = it % STAGES;
+        ptx::mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+        ptx::mbar_arrive_remote(pfull0 + 8 * s, 0);
+      }
+    }
+  }
+  __syncthreads();
+  ptx::cluster_sync_all();
+}
+
+template <int DIRECT>
+static int run_pair(const uint8_t* src, int n_chunks, int sms, int iters, int busy, unsigned* sink) {
+  const int grid = sms / 2 * 2;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES;
+  cudaFuncSetAttribute(pair_kernel<DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    pair_kernel<DIRECT><<<grid, THREADS, smem>>>(src, n_chunks, iters, busy, sink);
+    cudaEventRecord(e1);
+    cudaError_t se = cudaEventSynchronize(e1);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess || se != cudaSuccess) {
+      printf("{\"pair\": \"%s\", \"busy_cycles\": %d, \"error\": \"%s / %s\"}\n", DIRECT ? "direct" : "relay", busy,
+             cudaGetErrorString(le), cudaGetErrorString(se));
+      return 1;
+    }
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  printf("{\"pair\": \"%s\", \"busy_cycles\": %d, \"ctas\": %d, \"iters\": %d, \"ms\": %.4f, \"us_per_stage\": %.3f, "
+         "\"smem_fill_TBps\": %.2f}\n",
+         DIRECT ? "direct" : "relay", busy, grid, iters, best, best * 1e3 / iters,
+         (double)grid * iters * STAGE_BYTES / (best * 1e-3) / 1e12);
+  return 0;
 }
 
 template <int CLUSTER>
@@ -151,5 +260,12 @@ int main(int argc, char** argv) {
   rc |= run<2>(sh, pr, n_sh, n_pr, sms, iters, sink);
   rc |= run<4>(sh, pr, n_sh, n_pr, sms, iters, sink);
   rc |= run<8>(sh, pr, n_sh, n_pr, sms, iters, sink);
+  // the pair protocol, without and with 0.78 us (1530 cycles at 1.965 GHz) of emulated tensor work per stage; the
+  // direct variant last: if it faults, the context is gone
+  const int n_st = n_sh / 2;                          // 64 KB chunks in the `sh` buffer
+  rc |= run_pair<0>(sh, n_st, sms, iters, 0, sink);
+  rc |= run_pair<0>(sh, n_st, sms, iters, 1530, sink);
+  rc |= run_pair<1>(sh, n_st, sms, iters, 0, sink);
+  rc |= run_pair<1>(sh, n_st, sms, iters, 1530, sink);
   return rc;
 }
