@@ -35,3 +35,21 @@ def test_deterministic_mode_mirrors_velocity():
     _, traj = ref.sample(bank, words, 6, 64, 1, deterministic=True)
     xs = traj[0, 1::2]
     assert list(xs) == [30, 31, 27, 23, 19, 15]                         # 34 -> clamped to 31, velocity mirrored
+
+
+def test_host_helpers_without_gpu():
+    """draws_per_seq agrees with the oracle's worst case and the C ABI; the synthetic digit bank looks like digits
+    (values in [0, 1], mostly background); the generator itself refuses CPU tensors (no CPU fallback)."""
+    import torch
+    from dvg_b200 import _capi
+    from dvg_b200.data import draws_per_seq, moving_mnist_batch, synthetic_digit_bank
+    lib = _capi.load()
+    for T, n in [(1, 1), (15, 2), (105, 2), (20, 8)]:
+        assert draws_per_seq(T, n) == ref.draws_per_seq(T, n) == lib.dvg_moving_mnist_draws(T, n)
+    bank = synthetic_digit_bank(5, seed=3)
+    assert bank.shape == (5, 32, 32) and bank.dtype == torch.float32
+    assert bank.min().item() >= 0.0 and bank.max().item() <= 1.0
+    assert (bank == 0).float().mean().item() > 0.5 and bank.sum(dim=(1, 2)).min().item() > 10.0
+    assert torch.equal(bank, synthetic_digit_bank(5, seed=3))
+    with pytest.raises(_capi.DvgError):
+        moving_mnist_batch(bank, 2, 5)
