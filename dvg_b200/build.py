@@ -9,7 +9,9 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB_DIR = os.path.join(PKG, "_lib")
+# DVG_LIB_TAG=<tag>: developer builds (DVG_TRACE=1, DVG_STEP_*=...) go to _lib_<tag>/ and are loaded from there, so a
+# trace build and the product build can travel to the GPU box side by side.
+LIB_DIR = os.path.join(PKG, "_lib" + ("_" + os.environ["DVG_LIB_TAG"] if os.environ.get("DVG_LIB_TAG") else ""))
 LIB = os.path.join(LIB_DIR, "libdvg_b200.so")
 SOURCES = ["capi.cu", "lstm_fp32.cu", "lstm_tc.cu", "lstm_step.cu", "gp.cu", "gp_big.cu", "rollout.cu", "moving_mnist.cu"]
 HEADERS = ["common.cuh", "internal.cuh", "ptx.cuh", "gp_trigger.cuh", "gp_rsample.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "dvg_b200.h")]

@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
                                     : a_in + (size_t)(rt * kb_in + kb) * (2u * TC_A_IMG);
           if (rec || layer0) ptx::bulk_g2s_hint(sa, asrc, a_bytes, full_bar(s), pol_stream);
           else ptx::bulk_g2s(sa, asrc, a_bytes, full_bar(s));        // h' of the layer below: re-read by every N tile
+          if (pm < 3 && i < 8) TRACE(88 + pm * 8 + i);
           if (++s == p.stages) { s = 0; phs ^= 1u; }
         }
         if (pm < 3) TRACE(2 + pm * 8 + 7);
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
             ptx::mbar_wait(full_bar(s), phs);
             ptx::mbar_wait(pfull_bar(s), phs);
             if (mit < 3 && i == 0) TRACE(2 + mit * 8 + 2);
+            if (mit < 3 && i < 8) TRACE(64 + mit * 8 + i);
             ptx::tc_fence_after();
             const uint32_t sa = base + (uint32_t)s * stage_bytes;
             const uint64_t a_hi = ptx::make_sw128_desc(sa);
@@ -1223,7 +1225,7 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
               (int)cfg.gridDim.x, a.total_items, stages, a.restore);
       for (int b = 0; b < (int)cfg.gridDim.x; ++b) {
         fprintf(stderr, "cta %3d:", b);
-        for (int i = 0; i < 44; ++i) {
+        for (int i = 0; i < 112; ++i) {
           unsigned long long v = hbuf[b * TRACE_SLOTS + i];
           if (i == 2 || i == 10 || i == 18 || i == 26) fprintf(stderr, " |");
           if (v >= 1000000ull && v < 2000000ull) fprintf(stderr, " #%lld", (long long)(v - 1000000ull));

@@ -6,7 +6,7 @@
 
 namespace dvg {
 
-constexpr int TRACE_SLOTS = 64;
+constexpr int TRACE_SLOTS = 128;
 #ifdef DVG_TRACE
 #define TRACE(slot)                                                                   \
   do {                                                                                \

@@ -13,6 +13,10 @@ names = {0: "start", 1: "setup", 26: "trigdone", 27: "xpack", 28: "it0 published
 for m in range(3):
     for k, n in enumerate(["pstart", "depok", "stage0", "mmaissued", "accready", "epidone", "item", "requested"]):
         names[2 + m * 8 + k] = f"it{m} {n}"
+for m in range(3):
+    for i in range(8):
+        names[64 + m * 8 + i] = f"it{m} kb{i} full@mma"
+        names[88 + m * 8 + i] = f"it{m} kb{i} issued"
 for s in range(a.shape[1]):
     col = a[:, s]
     v = col[col >= 0]
