@@ -69,6 +69,9 @@ constexpr int STEP_NPOLY = DVG_STEP_NPOLY;   // sigmoid exponentials on the FMA 
 #define DVG_STEP_TRIG_EARLY 1
 #endif
 constexpr bool STEP_TRIG_EARLY = DVG_STEP_TRIG_EARLY != 0;   // trigger partial sums before the first tile epilogue
+#ifndef DVG_STEP_POLL_BATCH
+#define DVG_STEP_POLL_BATCH 0     // measured slower (fence.acq_rel.gpu + 16-wide sampling): kth_s100 +1.2 us per step
+#endif
 constexpr int STEP_BAR_BYTES = 384;     // mbarriers + tmem slot + misc words
 
 struct StepPhase {
@@ -93,6 +96,7 @@ struct StepTrig {
 };
 struct StepArgs {
   int rows, row_tiles, groups, nsplit, stages, n_phases, total_items, H, L, G, ldx, kbx, rows_per_flag, restore;
+  int head_mega;                  // head items load ALL their k-blocks into the (drained) ring at once, see the producer
   uint32_t stage_bytes;
   const float* x; uint8_t* xp;
   const uint8_t* hold;            // mask known BEFORE the launch (plain dvg_lstm_step); nullptr in trigger-fused steps
@@ -118,6 +122,40 @@ __device__ __forceinline__ void poll_ge(const int* flag, int target, int item) {
     }
   }
   (void)ptx::ld_acquire_gpu(flag);
+}
+
+// Dependency wait of a consumer item: k-block `j` of flags[0..n) must have reached `target`.  Every not yet
+// acknowledged flag is sampled in the same poll iteration (independent relaxed loads: one L2 round trip for all of
+// them), one acquire fence + one generic->async proxy fence follow, and every flag seen at target BEFORE the fences is
+// recorded in `ready` so the k-blocks it covers skip both the poll and the fences.  (One poll + ld.acquire +
+// fence.proxy.async per k-block cost the producer lane ~1.1 us each -- three dependent L2 round trips -- although the
+// four producing tiles of a row group publish within ~1 us of each other: traces of round 2, profiles/r02_*.)
+__device__ __forceinline__ void poll_deps(const int* flags, int n, int j, int target, uint32_t& ready, int item) {
+  if ((ready >> j) & 1u) return;
+#if !DVG_STEP_POLL_BATCH
+  poll_ge(flags + j, target, item);
+  ptx::fence_proxy_async_all();
+  return;
+#endif
+  const long long t0 = clock64();
+  for (;;) {
+    int v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = (q < n && !((ready >> q) & 1u)) ? ptx::ld_relaxed_gpu(flags + q) : 0;
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) m |= (v[q] >= target ? 1u : 0u) << q;
+    if ((m >> j) & 1u) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      ptx::fence_proxy_async_all();       // generic-proxy writes of the producing pairs -> visible to our TMA
+      ready |= m;
+      return;
+    }
+    if (clock64() - t0 > 4000000000LL) {
+      printf("dvg_b200: dependency wait timed out (block %d item %d k-block %d)\n", (int)blockIdx.x, item, j);
+      __trap();
+    }
+  }
 }
 
 __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid_constant__ StepArgs p) {
@@ -263,6 +301,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
     // ===================== TMA producer (both CTAs of the pair) =====================
     if (lane == 0) {
       int s = 0, pm = 0, xj = 0;
+#ifdef DVG_TRACE
+      int dep_item = -1;
+#endif
       uint32_t phs = 0;
       // L2 eviction priorities: the packed h images of the previous step and the packed x slab are read exactly once
       // per consumer and are dead afterwards (the state blocks ping-pong) -> evict first; the weights are re-read by
@@ -290,6 +331,45 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         const uint8_t* wbase = f.w;
         const uint8_t* a_in = f.a_in;
         if (layer0) a_in += (size_t)nt * p.row_tiles * kb_in * (2u * TC_A_IMG);
+        if (p.head_mega && f.type != PH_LSTM) {
+          // Head item: K = H is short and N <= 256 narrow, so ALL its k-blocks fit the ring at once ([A k-blocks |
+          // this CTA's weight halves], one transaction on the first slot's barrier).  A staged head paid the ring's
+          // fill latency per k-block (~1 us each for ~0.1 us of tensor work) at the very end of the step's dependency
+          // chain; now it pays it once.  Every ring position is consumed so the phase bookkeeping of the three roles
+          // stays in lock step.
+          const uint32_t wbytes = nparts * b_half;
+          int s0 = 0;
+          for (int q = 0; q < p.stages; ++q) {
+            ptx::mbar_wait(empty_bar(s), phs ^ 1u);
+            if (q == 0) {
+              s0 = s;
+              ptx::mbar_expect_tx(full_bar(s0), (uint32_t)KB * (a_bytes + wbytes));
+            } else {
+              ptx::mbar_arrive(full_bar(s));
+            }
+            if (++s == p.stages) { s = 0; phs ^= 1u; }
+          }
+          const uint32_t wb0 = base + (uint32_t)KB * a_bytes;
+          for (int kb = 0; kb < KB; ++kb) {          // weights never depend on this launch: request them first
+            const uint8_t* bsrc = wbase + (size_t)(nt * KB + kb) * (2u * b_part) + rank * b_half;
+            ptx::bulk_g2s_hint(wb0 + (uint32_t)kb * wbytes, bsrc, b_half, full_bar(s0), pol_keep);
+            if (nparts == 2) ptx::bulk_g2s_hint(wb0 + (uint32_t)kb * wbytes + b_half, bsrc + b_part, b_half, full_bar(s0), pol_keep);
+          }
+          {
+            uint32_t ready = 0;
+            for (int kb = 0; kb < KB; ++kb) poll_deps(wait_flags + rg * kb_in, kb_in, kb, 2, ready, item);
+          }
+          if (pm < 3) TRACE(2 + pm * 8 + 1);
+          for (int kb = 0; kb < KB; ++kb)
+            ptx::bulk_g2s(base + (uint32_t)kb * a_bytes, a_in + (size_t)(rt * kb_in + kb) * (2u * TC_A_IMG), a_bytes, full_bar(s0));
+          if (pm < 3) TRACE(2 + pm * 8 + 7);
+          ++pm;
+          continue;
+        }
+        uint32_t ready = 0;                                // input k-blocks whose dependency has been acknowledged
+#ifdef DVG_TRACE
+        if (dep_item < 0 && !layer0) dep_item = pm;        // first dependent item of this CTA: poll phases are traced
+#endif
         for (int i = 0; i < KB; ++i) {
           const bool rec = i < kb_rec;
           const int kb = rec ? i : i - kb_rec;
@@ -306,8 +386,19 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           if (nparts == 2) ptx::bulk_g2s_hint(sb + b_half, bsrc + b_part, b_half, full_bar(s), pol_keep);
           if (!rec) {
             if (!layer0) {
-              poll_ge(wait_flags + rg * kb_in + kb, 2, item);
-              ptx::fence_proxy_async_all();       // generic-proxy writes of the producing pair -> visible to our TMA
+#ifdef DVG_TRACE
+              if (pm == dep_item && kb < 4) {
+                TRACE(112 + kb * 4 + 0);
+                const int* fl = wait_flags + rg * kb_in + kb;
+                while (ptx::ld_relaxed_gpu(fl) < 2) {}
+                TRACE(112 + kb * 4 + 1);
+                (void)ptx::ld_acquire_gpu(fl);
+                TRACE(112 + kb * 4 + 2);
+                ptx::fence_proxy_async_all();
+                TRACE(112 + kb * 4 + 3);
+              } else
+#endif
+              poll_deps(wait_flags + rg * kb_in, kb_in, kb, 2, ready, item);
             } else if (kb == 0) {
               ptx::mbar_wait(xready_bar(xj), 0);   // our own epilogue warps packed this item's x rows
               ptx::fence_proxy_async_all();
@@ -336,7 +427,45 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         const StepPhase& f = p.ph[phase_of(item)];
         const int kb_rec = f.kb_rec, in_ksteps = f.in_ksteps;
         const int KB = kb_rec + f.kb_in;
-        if (rank == 0) {
+        const bool mega = p.head_mega && f.type != PH_LSTM;
+        if (rank == 0 && mega) {
+          // ===================== MMA issuer, head item with all k-blocks resident =====================
+          const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, f.n_tile);
+          const uint32_t b_half = (uint32_t)f.n_tile * 64u;
+          const uint32_t wbytes = nparts * b_half;
+          const int acc = mit & 1;
+          const uint32_t aph = (uint32_t)(mit >> 1) & 1u;
+          ptx::mbar_wait(tempty_bar(acc), aph ^ 1u);
+          for (int q = 0; q < p.stages; ++q) {
+            ptx::mbar_wait(full_bar(s), phs);
+            ptx::mbar_wait(pfull_bar(s), phs);
+            if (++s == p.stages) { s = 0; phs ^= 1u; }
+          }
+          if (mit < 3) TRACE(2 + mit * 8 + 2);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+          uint32_t accum = 0;
+          for (int i = 0; i < KB; ++i) {
+            const int left = in_ksteps - i * (TC_KBLK / 16);
+            const int ks = left < TC_KBLK / 16 ? left : TC_KBLK / 16;
+            const uint32_t sa = base + (uint32_t)i * a_bytes;
+            const uint32_t sw = base + (uint32_t)KB * a_bytes + (uint32_t)i * wbytes;
+            const uint64_t a_hi = ptx::make_sw128_desc(sa), a_lo = ptx::make_sw128_desc(sa + TC_A_IMG);
+            const uint64_t b_hi = ptx::make_sw128_desc(sw), b_lo = ptx::make_sw128_desc(sw + b_half);
+            for (int kk = 0; kk < ks; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 2);
+              ptx::umma2_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
+              accum = 1u;
+              if (nparts == 2) {
+                ptx::umma2_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                ptx::umma2_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+          }
+          for (int q = 0; q < p.stages; ++q) ptx::umma2_commit_mcast(empty_bar(q), 3);
+          ptx::umma2_commit_mcast(tfull_bar(acc), 3);
+          if (mit < 3) TRACE(2 + mit * 8 + 3);
+        } else if (rank == 0) {
           // ===================== MMA issuer (leader CTA) =====================
           const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, f.n_tile);
           const uint32_t b_half = (uint32_t)f.n_tile * 64u;
@@ -378,7 +507,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           if (mit < 3) TRACE(2 + mit * 8 + 3);
         } else {
           // ===================== relay (peer CTA): "my stage landed" -> leader's pfull =====================
-          for (int i = 0; i < KB; ++i) {
+          const int n_pos = mega ? p.stages : KB;
+          for (int i = 0; i < n_pos; ++i) {
             ptx::mbar_wait(full_bar(s), phs);
             ptx::mbar_arrive_remote(pfull_bar(s), 0);
             if (++s == p.stages) { s = 0; phs ^= 1u; }
@@ -547,8 +677,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       // 16-byte chunks) so that every global access covers whole row segments; the head tiles use 4 KB buffers of
       // the first 8 epilogue warps.
       const int sub = ew >> 2;                             // which STEP_UPW units of the tile this warp owns
-      const int half = sub;                                // head tiles: column half (warps with sub < 2 only)
-      uint8_t* eb = s_ebuf + (f.type == PH_LSTM ? ew * (32 * STEP_RB) : ew * 4096);
+      const int half = sub;                                // gaussian head tiles: column half (warps with sub < 2 only)
+      uint8_t* eb = s_ebuf + ew * (32 * STEP_RB);
       auto swz = [](int row) { return STEP_RB == 128 ? (row & 7) : ((row >> 1) & 3); };
       const int er = lane / STEP_CPR, ec = lane % STEP_CPR;   // coalesced mapping: (32 / CPR) rows x CPR chunks per instruction
       constexpr int RPI = 32 / STEP_CPR;                   // rows per instruction
@@ -695,43 +825,39 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         }
         __syncwarp();
         if (etid == 0 && tm == 0) TRACE(29);
-      } else if (f.type == PH_TANH && sub < 2) {
-        // y = tanh(acc + b): this warp owns rows q*32.. and columns half*n_tile/2 ..; groups of <= 32 columns go
-        // through the transpose buffer so the [rows, G] output is written in full row segments.
-        const int ncol_half = f.n_tile / 2;
-        const int c_begin = half * ncol_half;
+      } else if (f.type == PH_TANH) {
+        // y = tanh(acc + b): the STEP_NSUB warps of a TMEM lane quarter split the tile's columns; 8 columns per trip go
+        // through a warp-private 32 x 32 B transpose buffer so that the [rows, G] output is written in row segments
+        // (4 lanes per row, 8 rows per store instruction).  The next trip's accumulators are fetched from TMEM while
+        // the current trip is computed.  (This code runs once per head tile, at the very end of the step's dependency
+        // chain: all epilogue warps take part and the loop body is small -- it is cold in the instruction caches.)
+        const int ncw = f.n_tile / STEP_NSUB;          // columns of this warp (n_tile is a multiple of 32)
+        const int c_begin = sub * ncw;
         float* const yout = f.y;
         const int ldy = f.ldy, n_valid = f.n_valid, n_rows = p.rows;
-        const bool vec2 = (ldy & 1) == 0 && (n_valid & 1) == 0;
-        // (rolled loops: this code runs once per head tile and is cold in the instruction caches -- unrolled it was
-        // ~10 KB of straight-line code and the head epilogue took 4.4 us for 128 x 96 outputs)
+        const bool vec2 = (ldy & 1) == 0 && (n_valid & 1) == 0 && (reinterpret_cast<uintptr_t>(yout) & 7) == 0;
+        uint8_t* hb = s_ebuf + ew * (32 * STEP_RB);    // the warp's own LSTM transpose buffer (>= 1 KB)
+        const int lr = lane >> 2, cc = (lane & 3) * 2;
+        uint32_t cur[8], nxt[8];
+        ptx::tmem_ld8(tacc + c_begin, cur);
+        ptx::tmem_ld_wait8(cur);
 #pragma unroll 1
-        for (int g0 = 0; g0 < ncol_half; g0 += 32) {
-          const int gw = ncol_half - g0 < 32 ? ncol_half - g0 : 32;   // 32 or 16
-#pragma unroll 1
-          for (int c16 = 0; c16 < gw; c16 += 16) {
-            float v[16];
-            ptx::tmem_ld16_wait(tacc + c_begin + g0 + c16, v);
+        for (int c8 = 0; c8 < ncw; c8 += 8) {
+          const int cn = c8 + 8 < ncw ? c8 + 8 : c8;   // last trip: harmless re-read
+          ptx::tmem_ld8(tacc + c_begin + cn, nxt);
+          float v[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i)      // XU bound: every other exponential goes to the FMA pipe
-              v[i] = (i & 1) ? tanh_fast_prescaled_poly(v[i], sb[c_begin + g0 + c16 + i])
-                             : tanh_fast_prescaled(v[i], sb[c_begin + g0 + c16 + i]);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)
-              *reinterpret_cast<float4*>(eb + lane * 128 + ((((c16 >> 2) + c4) ^ (lane & 7)) << 4)) =
-                  make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-          }
+          for (int i = 0; i < 8; ++i)                   // XU bound: every other exponential goes to the FMA pipe
+            v[i] = (i & 1) ? tanh_fast_prescaled_poly(__uint_as_float(cur[i]), sb[c_begin + c8 + i])
+                           : tanh_fast_prescaled(__uint_as_float(cur[i]), sb[c_begin + c8 + i]);
+          *reinterpret_cast<float4*>(hb + lane * 32) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(hb + lane * 32 + 16) = make_float4(v[4], v[5], v[6], v[7]);
           __syncwarp();
-          if (etid == 0 && tm == 2) TRACE(g0 == 0 ? 35 : 37);
-          const int lpr = gw >> 1;              // lanes per row (one float2 each): 16 or 8
-          const int rpi = 32 / lpr;             // rows per instruction
-          const int lr = gw == 32 ? lane >> 4 : lane >> 3;
-          const int cc = (gw == 32 ? lane & 15 : lane & 7) * 2;
-#pragma unroll 4
-          for (int i = 0; i < 32 / rpi; ++i) {
-            const int rr = i * rpi + lr;
-            const float2 t = *reinterpret_cast<const float2*>(eb + rr * 128 + (((cc >> 2) ^ (rr & 7)) << 4) + (cc & 3) * 4);
-            const int col = c_begin + g0 + cc;
+          const int col = c_begin + c8 + cc;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + lr;
+            const float2 t = *reinterpret_cast<const float2*>(hb + rr * 32 + cc * 4);
             const int grow = row_w0 + rr;
             if (grow < n_rows && col < n_valid) {
               float* dst = yout + (size_t)grow * ldy + col;
@@ -740,8 +866,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
             }
           }
           __syncwarp();
-          if (etid == 0 && tm == 2) TRACE(g0 == 0 ? 36 : 38);
+          ptx::tmem_ld_wait8(nxt);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
+        if (etid == 0 && tm == 2) TRACE(38);
       } else if (f.type == PH_GAUSS && sub < 2) {
         const int nchunks = f.n_tile / 16;
 #pragma unroll 1
@@ -772,8 +901,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
           else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
         }
-        // head tiles borrow 4 KB transpose buffers that overlap the LSTM buffers of other warps
-        if (STEP_EW > 8) ptx::named_bar_sync(1, STEP_EW * 32);
       }
       if (etid == 0 && tm < 3) {
         TRACE(2 + tm * 8 + 5);
@@ -1095,7 +1222,7 @@ bool lstm_step_usable(const dvg_lstm_s* h, int rows) {
   if (!h->tc_ok || !use_fused()) return false;
   const int RT = ceil_div(rows, TC_ROWS), groups = ceil_div(RT, 2), hk = h->dims.hidden_size / 64;
   const int pairs = h->sm_count / 2;
-  if (RT < 2 || pairs < 1) return false;
+  if (RT < 2 || pairs < 1 || hk > 16) return false;    // poll_deps samples at most 16 k-block flags per item
   return ceil_div(groups * hk, pairs) <= STEP_XMAX;
 }
 
@@ -1171,6 +1298,15 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   int stages = (int)((227 * 1024 - tail) / stage_bytes);
   if (stages > STEP_MAX_STAGES) stages = STEP_MAX_STAGES;
   a.stages = stages; a.stage_bytes = (uint32_t)stage_bytes;
+  {
+    static int mega = -1;
+    if (mega < 0) {
+      const char* e = getenv("DVG_STEP_HEAD_MEGA");   // developer switch: 0 = head k-blocks staged through the ring
+      mega = (e && e[0] == '0') ? 0 : 1;
+    }
+    const size_t head_bytes = (size_t)hk * nparts * ((size_t)TC_A_IMG + (size_t)h->tc_head.n_tile * 64);
+    a.head_mega = (mega && head_bytes <= (size_t)stages * stage_bytes) ? 1 : 0;
+  }
   const size_t smem = stages * stage_bytes + tail;
   static bool configured = false;
   if (!configured) {
@@ -1225,7 +1361,7 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
               (int)cfg.gridDim.x, a.total_items, stages, a.restore);
       for (int b = 0; b < (int)cfg.gridDim.x; ++b) {
         fprintf(stderr, "cta %3d:", b);
-        for (int i = 0; i < 112; ++i) {
+        for (int i = 0; i < 128; ++i) {
           unsigned long long v = hbuf[b * TRACE_SLOTS + i];
           if (i == 2 || i == 10 || i == 18 || i == 26) fprintf(stderr, " |");
           if (v >= 1000000ull && v < 2000000ull) fprintf(stderr, " #%lld", (long long)(v - 1000000ull));

@@ -182,7 +182,8 @@ static int run(const char* name, int mode, int stages, int row_bytes, int nparts
   a.n_src_stages = (int)(src_bytes / stage_bytes);
   a.src = src; a.sink = sink; a.cycles = cycles;
   const size_t smem = stages * stage_bytes + (noise ? EW * 2048 : 0);
-  cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t ae = cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ae != cudaSuccess) { printf("{\"probe\": \"%s\", \"error\": \"set attribute: %s\"}\n", name, cudaGetErrorString(ae)); return 1; }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);

@@ -17,6 +17,9 @@ for m in range(3):
     for i in range(8):
         names[64 + m * 8 + i] = f"it{m} kb{i} full@mma"
         names[88 + m * 8 + i] = f"it{m} kb{i} issued"
+for kb in range(4):
+    for j, n in enumerate(["poll start", "relaxed ok", "acquire done", "proxy fence done"]):
+        names[112 + kb * 4 + j] = f"dep kb{kb} {n}"
 for s in range(a.shape[1]):
     col = a[:, s]
     v = col[col >= 0]
