@@ -48,6 +48,8 @@ static void lstm_free_all(dvg_lstm_s* h) {
   fr(h->f_embed_wt); fr(h->f_embed_b); fr(h->f_head_wt); fr(h->f_head_b);
   for (int l = 0; l < MAX_LAYERS; ++l) { fr(h->f_layer_wt[l]); fr(h->f_layer_b[l]); }
   fr(h->scratch_e); fr(h->tc_xp); fr(h->tc_ep); fr(h->rs_buf);
+  for (void* q : h->retired) cudaFree(q);
+  h->retired.clear();
   for (int i = 0; i < 16; ++i)
     if (h->prof_ev[i]) { cudaEventDestroy(h->prof_ev[i]); h->prof_ev[i] = nullptr; }
   lstm_tc_free(h);
@@ -114,8 +116,10 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
   DVG_REQUIRE(h && rows > 0, "bad argument");
   if (rows <= h->reserved_rows) return DVG_OK;
   DVG_CUDA(cudaDeviceSynchronize());
-  auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
-  fr(h->scratch_e); fr(h->tc_xp); fr(h->tc_ep); fr(h->rs_buf);
+  // Never free scratch that an already captured CUDA graph may reference: retire it until destroy.
+  auto fr = [&](auto*& p) { if (p) h->retired.push_back((void*)p); p = nullptr; };
+  fr(h->scratch_e); fr(h->tc_xp); fr(h->tc_ep); fr(h->rs_buf); fr(h->fused_flags); fr(h->sched_dev);
+  h->sched_len = h->sched_rows = h->sched_pairs = 0;
   h->reserved_rows = 0;
   DVG_CUDA(cudaMalloc(&h->scratch_e, sizeof(float) * (size_t)rows * h->dims.hidden_size));
   if (h->tc_ok) {
@@ -126,8 +130,6 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
     DVG_CUDA(cudaMalloc(&h->rs_buf, sizeof(float) * (size_t)rows * h->dims.output_size));
     DVG_CUDA(cudaMalloc(&h->tc_ep, lstm_tc_scratch_bytes_ep(h, rows)));
     DVG_CUDA(cudaMemset(h->tc_ep, 0, lstm_tc_scratch_bytes_ep(h, rows)));
-    if (h->fused_flags) cudaFree(h->fused_flags);
-    h->fused_flags = nullptr;
     DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * lstm_step_flag_words(h, rows)));
     DVG_CUDA(cudaMemset(h->fused_flags, 0, sizeof(int) * lstm_step_flag_words(h, rows)));
     int rc = lstm_step_build_schedule(h, rows);

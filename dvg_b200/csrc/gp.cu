@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128) gp_predict_kernel(int n_rows, int D, int 
 // this store and the finalize loads are coalesced.  Phase 2 (the last CTA to finish, atomic ticket): one thread
 // per rollout loads its D variances in register batches of 32 (independent loads, one L2 round trip per batch),
 // sums them in numpy's sequential fp32 order, updates the window, thresholds, decides, and appends fired
-// rollouts to the compacted list used by gp_rsample_list_kernel.  (History: thread-per-task without the v/w split
+// rollouts to the compacted list used by the fused step kernel.  (History: thread-per-task without the v/w split
 // was 10 us + 2 more launches; a warp-per-task variant was issue-bound at 33 us.)
 template <int MREG>
 __global__ void __launch_bounds__(256) gp_trigger_kernel(int S, int D, int mp, const float* __restrict__ x, int ldx,
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) gp_trigger_kernel(int S, int D, int mp, c
                                                          int warmup, float factor, float* value, float* thr,
                                                          uint8_t* mask, int* trig_list, int* trig_count) {
   extern __shared__ __align__(16) float smf[];
-  __shared__ int s_last;
+  __shared__ int s_last, s_cnt;
   const int d = blockIdx.y, tid = threadIdx.x;
   const int MP = MREG > 0 ? MREG : mp;
   float* s_linv = smf;
@@ -286,7 +286,9 @@ __global__ void __launch_bounds__(256) gp_trigger_kernel(int S, int D, int mp, c
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int cnt = count[0];
+  if (tid == 0) s_cnt = count[0];               // read once, before thread 0 may advance it below
+  __syncthreads();
+  const int cnt = s_cnt;
   for (int s = tid; s < S; s += 256)
     gp_trig_finalize_rollout(s, S, D, var_rows, window, W, cnt, warmup, factor, value, thr, mask, trig_list, trig_count);
   if (tid == 0) {
@@ -310,12 +312,14 @@ __global__ void __launch_bounds__(RS_THREADS) gp_rsample_kernel(int S, int N, in
                   lqt_all, alpha_all, hyp, out, ldo);
 }
 
-// grid (D, splits): driven by the compacted list of triggered rollouts written by gp_trigger_kernel, so a step
-// in which nothing fired costs D*splits empty CTAs instead of S*D.
-__global__ void __launch_bounds__(RS_THREADS) gp_rsample_list_kernel(int N, int D, int mp, const float* __restrict__ x, int ldx,
+// grid (D, splits): CTA (d, j) scans the mask and solves dim d of every masked rollout s with s % splits == j, so a step
+// in which nothing fired costs D*splits near-empty CTAs instead of S*D launches with 200 KB of shared memory each.
+// The mask CONTENTS decide (an earlier version replayed the fired list of the last trigger call whenever the same
+// mask pointer came back; a caller that edits or zeroes that buffer, or an allocator that hands the address to another
+// mask, then resampled a stale list).
+__global__ void __launch_bounds__(RS_THREADS) gp_rsample_scan_kernel(int S, int N, int D, int mp, const float* __restrict__ x, int ldx,
                                                               const float* __restrict__ eps,
-                                                              const int* __restrict__ trig_list,
-                                                              const int* __restrict__ trig_count,
+                                                              const uint8_t* __restrict__ mask,
                                                               const float* __restrict__ zall,
                                                               const float* __restrict__ linv_all,
                                                               const float* __restrict__ lqt_all,
@@ -323,9 +327,9 @@ __global__ void __launch_bounds__(RS_THREADS) gp_rsample_list_kernel(int N, int 
                                                               const float* __restrict__ hyp, float* __restrict__ out,
                                                               int ldo) {
   extern __shared__ __align__(16) float smf[];
-  const int n = *trig_count;
-  for (int i = blockIdx.y; i < n; i += gridDim.y) {
-    gp_rsample_body<RS_THREADS>(smf, (int)threadIdx.x, [] { __syncthreads(); }, trig_list[i], blockIdx.x, N, D, mp, x, ldx, eps, zall,
+  for (int s = blockIdx.y; s < S; s += gridDim.y) {
+    if (mask[s] == 0) continue;                      // CTA-uniform
+    gp_rsample_body<RS_THREADS>(smf, (int)threadIdx.x, [] { __syncthreads(); }, s, blockIdx.x, N, D, mp, x, ldx, eps, zall,
                     linv_all, lqt_all, alpha_all, hyp, out, ldo);
     __syncthreads();   // shared memory is reused by the next rollout
   }
@@ -402,8 +406,6 @@ int gp_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t
                                                       h->var_rows, h->ticket, window, W, count, warmup, factor, value,
                                                       thr, mask, h->trig_list, h->trig_count);
   DVG_LAUNCH_CHECK();
-  h->last_mask = mask;   // dvg_gp_rsample(mask == this pointer) may use the compacted list
-  h->last_mask_rollouts = S;
   return DVG_OK;
 }
 
@@ -415,12 +417,12 @@ int gp_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const 
   static bool configured = false;
   if (!configured) {
     DVG_CUDA(cudaFuncSetAttribute(gp_rsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DVG_CUDA(cudaFuncSetAttribute(gp_rsample_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DVG_CUDA(cudaFuncSetAttribute(gp_rsample_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  if (mask != nullptr && mask == h->last_mask && S == h->last_mask_rollouts) {
-    gp_rsample_list_kernel<<<dim3(D, 4), RS_THREADS, smem, stream>>>(N, D, mp, x, ldx, eps, h->trig_list, h->trig_count, h->z,
-                                                               h->linv, h->lqt, h->alpha, h->hyp, out, ldo);
+  if (mask != nullptr && S > 8) {
+    gp_rsample_scan_kernel<<<dim3(D, 4), RS_THREADS, smem, stream>>>(S, N, D, mp, x, ldx, eps, mask, h->z, h->linv, h->lqt,
+                                                               h->alpha, h->hyp, out, ldo);
   } else {
     gp_rsample_kernel<<<dim3(S, D), RS_THREADS, smem, stream>>>(S, N, D, mp, x, ldx, eps, mask, h->z, h->linv, h->lqt, h->alpha,
                                                          h->hyp, out, ldo);

@@ -264,8 +264,6 @@ int gp_big_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int
   gp_trigger_finalize_kernel<<<1, 1024, 0, stream>>>(S, h->dims.num_dims, h->var_rows, window, W, count, warmup, factor,
                                                      value, thr, mask, h->trig_list, h->trig_count);
   DVG_LAUNCH_CHECK();
-  h->last_mask = mask;
-  h->last_mask_rollouts = S;
   return DVG_OK;
 }
 

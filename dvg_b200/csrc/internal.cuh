@@ -53,6 +53,9 @@ struct dvg_lstm_s {
   uint8_t* tc_xp = nullptr;      // packed x            [RT][kbx][2][16 KB]
   uint8_t* tc_ep = nullptr;      // packed embed output [RT][H/64][2][16 KB]
   float* rs_buf = nullptr;       // [rows][G_out] side buffer of the step kernel's in-launch GP resample
+  // Scratch outgrown by a later reserve(): CUDA graphs captured before the growth have the old device pointers baked
+  // in, so the old allocations stay alive (and self-consistent: own flags, own packed-x slab) until destroy.
+  std::vector<void*> retired;
 
   // --- optional per-kernel timing (dvg_lstm_profile): events recorded between launches ------------
   bool prof_on = false;
@@ -80,8 +83,6 @@ struct dvg_gp_s {
   unsigned int* ticket = nullptr;   // [1 + max groups] last-CTA tickets of the fused trigger kernel (self-resetting)
   int* trig_list = nullptr;         // [max_rollouts] compacted rollouts that fired in the last trigger call
   int* trig_count = nullptr;
-  const uint8_t* last_mask = nullptr;  // mask buffer the list corresponds to
-  int last_mask_rollouts = 0;
   // large inducing sets (gp_big.cu): factors loaded pre-computed, mp = M rounded up to 64, tiled FP32 GEMM kernels
   bool big = false;
   float* partial = nullptr;   // [D][mp/64][n_pad][3] row-block partial sums

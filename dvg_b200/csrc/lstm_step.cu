@@ -1164,7 +1164,7 @@ static bool sched_pattern_two_layer(int P, int groups, int hk, std::vector<std::
 }
 
 int lstm_step_build_schedule(dvg_lstm_s* h, int rows) {
-  if (h->sched_dev) { cudaFree(h->sched_dev); h->sched_dev = nullptr; }
+  if (h->sched_dev) { h->retired.push_back(h->sched_dev); h->sched_dev = nullptr; }   // captured graphs may hold it
   h->sched_len = h->sched_rows = h->sched_pairs = 0;
   // DVG_STEP_SCHED: 0 / unset = layer-major identity order, 1 = list scheduler on the cost model, 2 = the two-layer
   // pattern above.  Both alternatives are experimental: on kth_s100 neither beat the identity order (2.28 ms per rollout
@@ -1395,8 +1395,6 @@ int lstm_tc_rollout_step(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const
   t.rs_eps = rs_eps;
   t.S = S; t.W = W; t.warmup = warmup; t.factor = factor; t.stat_rows = stat_rows; t.window = window; t.count = count;
   t.value = value; t.thr = thr; t.mask = mask;
-  g->last_mask = mask;
-  g->last_mask_rollouts = S;
   return lstm_step_launch(h, g, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, nullptr, nullptr,
                           nullptr, nullptr, nullptr, rows / S, stream, &t);
 }

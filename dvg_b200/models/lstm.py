@@ -193,6 +193,13 @@ class _FastLstmBase(nn.Module):
     def _use_fast_path(self, x):
         if not x.is_cuda:
             raise _capi.DvgError("dvg_b200 hot path is CUDA-only (no CPU fallback); got a CPU tensor")
+        # eval() mode always takes the kernels: every rollout loop of the reference that runs in eval mode without
+        # torch.no_grad() (GPtrigger_gen, generate_frames.py:249-300; plot(), train.py:256-289 after :372) detaches
+        # the prediction at once (generate_frames.py:222, train.py:280), so the autograd graph a stock module would
+        # build there is never used.  train() mode with autograd on delegates to the stock torch ops on the GPU.
+        # (``eval_uses_kernels = False`` on an instance restores grad-in-eval.)
+        if not self.training and getattr(self, "eval_uses_kernels", True):
+            return True
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return False
         return True

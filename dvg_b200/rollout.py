@@ -43,6 +43,7 @@ class RolloutConfig:
     stat_col: int = 3             # generate_frames.py:230 hard-coded column
     stat_col_warmup: Optional[Sequence[int]] = None   # generate_frames.py:275 uses ``index``; default = stat_col
     variant: str = "bf16x3"
+    trigger: bool = True          # False: manual-resample drivers only (make_gifs / plot); no trigger scratch, no stat_col
 
 
 class RolloutEngine:
@@ -72,9 +73,18 @@ class RolloutEngine:
         self.mask = torch.zeros(S, dtype=torch.uint8, device=dev)
         self._mask_buf, self._value_buf = self.mask, self.value     # where the trigger writes (see latent_rollout)
         base = torch.arange(S, dtype=torch.int32) * B
+        if not cfg.trigger:
+            self.stat_rows = self.stat_rows_warmup = None
+            self.reset()
+            return
+        # the reference indexes ``variance[:, 3]`` / ``[:, index]`` (generate_frames.py:230,275) and raises IndexError
+        # for a batch that is too small; here an out-of-range column would read another rollout's row
+        wcols = list(cfg.stat_col_warmup) if cfg.stat_col_warmup is not None else [cfg.stat_col] * S
+        if not 0 <= cfg.stat_col < B or len(wcols) != S or any(not 0 <= int(c) < B for c in wcols):
+            raise IndexError(f"trigger statistic column out of range for n_points={B}: stat_col={cfg.stat_col}, "
+                             f"stat_col_warmup={cfg.stat_col_warmup}")
         self.stat_rows = (base + cfg.stat_col).to(dev)
-        wcols = cfg.stat_col_warmup if cfg.stat_col_warmup is not None else [cfg.stat_col] * S
-        self.stat_rows_warmup = (base + torch.tensor(list(wcols), dtype=torch.int32)).to(dev)
+        self.stat_rows_warmup = (base + torch.tensor(wcols, dtype=torch.int32)).to(dev)
         # trigger scratch must exist before any graph capture
         _capi.check(self.lib.dvg_gp_trigger(self.grt.handle, S, _capi.ptr(torch.zeros(self.R, self.D, device=dev)),
                                             self.D, _capi.ptr(self.stat_rows), _capi.ptr(self.window), cfg.window,
@@ -110,6 +120,8 @@ class RolloutEngine:
         return t.stride(0)
 
     def trigger(self, h, warmup: bool):
+        if self.stat_rows is None:
+            raise _capi.DvgError("this RolloutEngine was built with trigger=False")
         rows = self.stat_rows_warmup if warmup else self.stat_rows
         _capi.check(self.lib.dvg_gp_trigger(self.grt.handle, self.S, _capi.ptr(h), self._ld(h), _capi.ptr(rows),
                                             _capi.ptr(self.window), self.cfg.window, _capi.ptr(self.count),
@@ -135,6 +147,8 @@ class RolloutEngine:
     def step_trigger_mode(self, h, eps, out, warmup: bool, resample: bool = True):
         """One GPtrigger_gen step (generate_frames.py:266-298) for all rollouts: ``out`` [S*B, G] receives
         the decoder input (LSTM prediction, or the GP sample for triggered rollouts)."""
+        if self.stat_rows is None:
+            raise _capi.DvgError("this RolloutEngine was built with trigger=False")
         rows = self.stat_rows_warmup if warmup else self.stat_rows
         nxt = 1 - self.cur
         rs = None
@@ -412,7 +426,7 @@ def diverse_rollout(frame_predictor, gp_layer, likelihood, encoder, decoder, x, 
         x_in = x[i]
         i += 1
     eng = engine if engine is not None else RolloutEngine(
-        frame_predictor, gp_layer, likelihood, RolloutConfig(n_points=B, n_rollouts=S, variant=variant))
+        frame_predictor, gp_layer, likelihood, RolloutConfig(n_points=B, n_rollouts=S, variant=variant, trigger=False))
     eng.cur = 0
     eng.load_broadcast_state(frame_predictor.hidden)
     n_ctx = i
@@ -488,7 +502,7 @@ class PixelRollout:
         self.hits = resample_steps(n_past, n_eval, resample_every, resample_at)
         self.codec = BatchedCodec(encoder, decoder, n_points, dtype=codec_dtype, chunk_rows=chunk_rows)
         self.engine = RolloutEngine(frame_predictor, gp_layer, likelihood,
-                                    RolloutConfig(n_points=n_points, n_rollouts=nsample, variant=variant))
+                                    RolloutConfig(n_points=n_points, n_rollouts=nsample, variant=variant, trigger=False))
         self.x = torch.zeros(self.n_ctx, n_points, *frame_shape, device=dev)
         self.eps = torch.zeros(max(1, len(self.hits)), nsample, D, n_points, device=dev)
         self.frames = torch.empty(n_eval - self.n_ctx, nsample * n_points, *frame_shape, device=dev)

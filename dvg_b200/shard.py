@@ -71,6 +71,11 @@ def gather_winners(local_frames: torch.Tensor, best: torch.Tensor, n_rollouts: i
     mine = (best >= first) & (best < first + cnt)
     local = (best - first).clamp(0, max(cnt - 1, 0))
     cols = torch.arange(B, device=best.device)
+    if cnt == 0:          # more ranks than rollouts: this rank owns nothing and contributes zeros
+        out = torch.zeros((B,) + tuple(local_frames.shape[2:]), dtype=local_frames.dtype, device=local_frames.device)
+        if world > 1:
+            dist.all_reduce(out, group=group)
+        return out
     out = local_frames[local, cols]
     out = torch.where(mine.reshape((B,) + (1,) * (out.dim() - 1)), out, torch.zeros((), dtype=out.dtype, device=out.device))
     if world > 1:

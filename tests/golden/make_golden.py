@@ -36,6 +36,64 @@ def roll_lstm(mod, xs):
     return ys, hs
 
 
+def sd_checksum(sd):
+    import hashlib
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def big_cases():
+    """Reference-class goldens at the REAL sizes (G90 / H256 / L2, 300 rows, 12 free-running steps) so that they reach
+    the persistent tcgen05 step kernel (>= 2 row tiles).  The 4.4 MB of weights are not stored: they come from
+    ``oracle.lstm_ref.random_lstm_state_dict(seed)``, are loaded into the reference class with ``load_state_dict`` and
+    pinned by a SHA-256 (the test regenerates them and checks the hash).  Stored: inputs' seed, y at steps 0 / 5 / 11,
+    the final hidden state (h of the top layer, c of layer 0), and for gaussian_lstm the noise and (z, mu, logvar)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import lstm_ref
+    import models.lstm as ref
+    G, H, L, R, T = 90, 256, 2, 300, 12
+    keep = (0, 5, 11)
+    sd = lstm_ref.random_lstm_state_dict(G, G, H, L, seed=21)
+    sd["embed.bias"].uniform_(-0.1, 0.1, generator=torch.Generator().manual_seed(5))
+    sd["output.0.bias"].uniform_(-0.1, 0.1, generator=torch.Generator().manual_seed(6))
+    mod = ref.lstm(G, G, H, L, R)
+    mod.load_state_dict(sd)
+    mod.eval()
+    gen = torch.Generator().manual_seed(77)
+    xs = [torch.tanh(torch.randn(R, G, generator=gen)) for _ in range(T)]
+    ys, hs = roll_lstm(mod, xs)
+    torch.save({"kind": "lstm_big", "dims": (G, G, H, L, R), "steps": T, "weights_seed": 21, "x_seed": 77,
+                "sha256": sd_checksum(sd), "keep": keep, "y": {t: ys[t] for t in keep},
+                "h_top": hs[-1][L - 1][0], "c0": hs[-1][0][1]}, os.path.join(HERE, "big_lstm_g90_h256_r300.pt"))
+    Z = 10
+    gsd = lstm_ref.random_lstm_state_dict(G, Z, H, L, seed=22, gaussian=True)
+    for k, sdd in (("embed.bias", 7), ("mu_net.bias", 8), ("logvar_net.bias", 9)):
+        gsd[k].uniform_(-0.2, 0.2, generator=torch.Generator().manual_seed(sdd))
+    gm = ref.gaussian_lstm(G, Z, H, L, R)
+    gm.load_state_dict(gsd)
+    gm.eval()
+    gm.hidden = gm.init_hidden()
+    gen = torch.Generator().manual_seed(78)
+    xs = [torch.tanh(torch.randn(R, G, generator=gen)) for _ in range(T)]
+    outs, epss = [], []
+    with torch.no_grad():
+        for t, x in enumerate(xs):
+            torch.manual_seed(300 + t)
+            z, mu, logvar = gm(x)
+            torch.manual_seed(300 + t)
+            eps = torch.empty(R, Z).normal_()          # models/lstm.py:163 draws eps with .normal_() first
+            assert torch.equal(z, eps.mul(logvar.mul(0.5).exp()).add(mu))
+            outs.append((z.clone(), mu.clone(), logvar.clone()))
+            epss.append(eps)
+    torch.save({"kind": "gauss_big", "dims": (G, Z, H, L, R), "steps": T, "weights_seed": 22, "x_seed": 78,
+                "sha256": sd_checksum(gsd), "eps": epss, "out": outs,
+                "h_top": gm.hidden[L - 1][0].clone(), "c0": gm.hidden[0][1].clone()},
+               os.path.join(HERE, "big_gauss_g90_z10_h256_r300.pt"))
+
+
 def main():
     sys.path.insert(0, REF)
     torch.Tensor.cuda = lambda self, *a, **k: self
@@ -84,6 +142,7 @@ def main():
         torch.save({"kind": "gaussian_lstm", "dims": (gi, Z, H, L, B), "state_dict": mod.state_dict(),
                     "x": xs, "eps": eps_list, "out": out, "hidden": hs},
                    os.path.join(HERE, f"gauss_{name}.pt"))
+    big_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

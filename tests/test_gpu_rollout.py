@@ -55,7 +55,7 @@ def test_diverse_rollout_matches_sequential_oracle(variant):
     assert len(got) == n_eval
     for t in range(n_eval):
         for s in range(S):
-            assert relerr(got[t][s], ref[s][t]) < 3e-4, (t, s)
+            assert relerr(got[t][s], ref[s][t]) < 1e-4, (t, s)
     # samples are identical until the first resample step and differ afterwards
     assert torch.equal(got[4][0], got[4][1])
     assert not torch.equal(got[6][0], got[6][1])
@@ -92,8 +92,8 @@ def test_trigger_rollout_matches_sequential_oracle():
                 break                                   # inside the tolerance band: histories may fork
             assert bool(trig[i, s]) == bool(ref["triggers"][i]), (s, i)
             n_fired += int(trig[i, s])
-            assert relerr(got["latents"][i][s], ref["latents"][i]) < 5e-4, (s, i)
-            assert relerr(got["gen_seq"][i][s], ref["gen_seq"][i]) < 5e-4, (s, i)
+            assert relerr(got["latents"][i][s], ref["latents"][i]) < 1e-4, (s, i)
+            assert relerr(got["gen_seq"][i][s], ref["gen_seq"][i]) < 1e-4, (s, i)
     # (the closed toy loop settles quickly, so triggers are rare here; the trigger -> hold -> rsample
     #  semantics are pinned by test_latent_trigger_rollout_crafted below)
 
@@ -120,6 +120,28 @@ def test_latent_trigger_rollout_crafted(variant):
     assert checked > 100
     # a jump fires unless an earlier jump of the same rollout still sits in the 6-step window
     assert fired >= 4, (fired, sorted(jumps), masks.cpu().nonzero().tolist())
+
+
+def test_kth_shaped_trigger_rollout_vs_oracle():
+    """The bench's own shape per rollout (B = 50 points: the in-kernel resample solves 50 x 50 problems; 8 rollouts =
+    400 rows = 4 row tiles -> lstm_step_kernel, window 12 as in generate_frames.py:266) with crafted fires, through
+    dvg_rollout_step, against the sequential oracle."""
+    from dvg_b200.rollout import RolloutConfig, RolloutEngine
+    from util import check_latent_rollout, crafted_trigger_case
+    B, S, T, W = 50, 8, 30, 12
+    sd = lstm_ref.random_lstm_state_dict(G, G, H, L, seed=16)
+    gp_sd, lik_sd, lat, eps, jumps = crafted_trigger_case(G, M, B, S, T, W, seed=4, n_jumps=6)
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=W, variant="bf16x3"))
+    out = torch.empty(T, S * B, G, device="cuda")
+    masks = torch.zeros(T, S, dtype=torch.uint8, device="cuda")
+    values = torch.zeros(T, S, device="cuda")
+    with torch.no_grad():
+        eng.latent_rollout(lat.cuda(), eps.cuda(), out, masks=masks, values=values)
+    torch.cuda.synchronize()
+    checked, fired = check_latent_rollout(sd, gp_sd, lik_sd, lat, eps, out.cpu(), masks.cpu(), values.cpu(), B, W)
+    assert checked > 100 and fired >= 1, (checked, fired, sorted(jumps), masks.cpu().nonzero().tolist())
 
 
 def test_cuda_graph_latent_rollout_equals_eager():
@@ -253,7 +275,7 @@ def test_plot_rollout_matches_sequential_oracle():
     sse = torch.zeros(S, B, dtype=torch.float64)
     for s in range(S):
         for t in range(n_eval):
-            assert relerr(got["samples"][t][s], ref[s][t]) < 5e-4, (s, t)
+            assert relerr(got["samples"][t][s], ref[s][t]) < 1e-4, (s, t)
             sse[s] += (x[t].double() - ref[s][t]).pow(2).reshape(B, -1).sum(1)
     assert relerr(got["sse"], sse) < 1e-3
     assert got["best"].cpu().tolist() == sse.argmin(0).tolist()

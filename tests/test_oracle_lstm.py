@@ -37,6 +37,32 @@ def test_gaussian_lstm_oracle_matches_reference(path):
         torch.testing.assert_close(z, rz, rtol=1e-6, atol=1e-7)
 
 
+def test_oracle_matches_reference_at_full_size():
+    """G90 / H256 / L2, 300 rows, 12 free-running steps of the REAL reference classes (big_* goldens)."""
+    from util import big_golden_weights
+    g = torch.load(os.path.join(GOLD, "big_lstm_g90_h256_r300.pt"), weights_only=False)
+    sd, xs = big_golden_weights(g)
+    gi, go, H, L, R = g["dims"]
+    hidden = lstm_ref.init_hidden(L, R, H)
+    for t, x in enumerate(xs):
+        y, hidden = lstm_ref.lstm_forward(sd, x, hidden)
+        if t in g["keep"]:
+            torch.testing.assert_close(y, g["y"][t], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(hidden[L - 1][0], g["h_top"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(hidden[0][1], g["c0"], rtol=1e-5, atol=1e-6)
+    g = torch.load(os.path.join(GOLD, "big_gauss_g90_z10_h256_r300.pt"), weights_only=False)
+    sd, xs = big_golden_weights(g)
+    gi, Z, H, L, R = g["dims"]
+    hidden = lstm_ref.init_hidden(L, R, H)
+    for t, x in enumerate(xs):
+        z, mu, logvar, hidden = lstm_ref.gaussian_lstm_forward(sd, x, hidden, g["eps"][t])
+        rz, rmu, rlv = g["out"][t]
+        torch.testing.assert_close(mu, rmu, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(logvar, rlv, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(z, rz, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(hidden[L - 1][0], g["h_top"], rtol=1e-5, atol=1e-6)
+
+
 def test_fp64_oracle_brackets_fp32():
     sd = lstm_ref.random_lstm_state_dict(90, 90, 256, 2, seed=3)
     x = torch.tanh(torch.randn(50, 90, generator=torch.Generator().manual_seed(0)))

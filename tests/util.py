@@ -8,6 +8,44 @@ def relerr(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
+def elemerr(a, b, rtol=1e-4, atol=None):
+    """Element-wise error  max_i |a_i - b_i| / (atol + rtol |b_i|)  (<= 1 passes).  ``atol`` defaults to
+    rtol * rms(b): an element may be off by rtol of its own magnitude plus rtol of the tensor's typical magnitude
+    (hidden states and latents live in (-1, 1); exact zeros and sign changes make a pure relative test meaningless)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    if atol is None:
+        atol = rtol * b.pow(2).mean().sqrt().clamp_min(1e-30).item()
+    return ((a - b).abs() / (atol + rtol * b.abs())).max().item()
+
+
+def sd_checksum(sd):
+    """SHA-256 over a state_dict (tests/golden/make_golden.py: pins seeded weights that are not stored)."""
+    import hashlib
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def big_golden_weights(g):
+    """Regenerate the weights of a ``big_*`` golden from its seed and check them against the stored hash."""
+    from oracle import lstm_ref
+    gi, go, H, L, R = g["dims"]
+    gauss = g["kind"] == "gauss_big"
+    sd = lstm_ref.random_lstm_state_dict(gi, go, H, L, seed=g["weights_seed"], gaussian=gauss)
+    if gauss:
+        for k, sdd in (("embed.bias", 7), ("mu_net.bias", 8), ("logvar_net.bias", 9)):
+            sd[k].uniform_(-0.2, 0.2, generator=torch.Generator().manual_seed(sdd))
+    else:
+        sd["embed.bias"].uniform_(-0.1, 0.1, generator=torch.Generator().manual_seed(5))
+        sd["output.0.bias"].uniform_(-0.1, 0.1, generator=torch.Generator().manual_seed(6))
+    assert sd_checksum(sd) == g["sha256"], "seeded weights differ from the ones the golden was made with"
+    gen = torch.Generator().manual_seed(g["x_seed"])
+    xs = [torch.tanh(torch.randn(R, gi, generator=gen)) for _ in range(g["steps"])]
+    return sd, xs
+
+
 def make_lstm(sd, gaussian=False, rows=1, variant="fp32"):
     """dvg_b200 drop-in module on cuda:0 loaded with a reference-layout state_dict."""
     from dvg_b200.models.lstm import gaussian_lstm, lstm
@@ -58,7 +96,7 @@ def crafted_trigger_case(G, M, B, S, T, W, seed=0, n_jumps=6):
     return gp_sd, lik_sd, lat, eps, jumps
 
 
-def check_latent_rollout(sd, gp_sd, lik_sd, lat, eps, out, masks, values, B, W, stat_col=3, tol=3e-4):
+def check_latent_rollout(sd, gp_sd, lik_sd, lat, eps, out, masks, values, B, W, stat_col=3, tol=1e-4):
     """Replay a latent-space trigger rollout on the CPU oracle, one rollout at a time (the reference's
     sequential loop, generate_frames.py:249-300), following the device's decisions where the statistic is
     within tolerance of the threshold and asserting them elsewhere.  Returns (#checked decisions, #fired)."""
