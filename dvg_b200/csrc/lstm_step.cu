@@ -70,7 +70,10 @@ constexpr int STEP_NPOLY = DVG_STEP_NPOLY;   // sigmoid exponentials on the FMA 
 #endif
 constexpr bool STEP_TRIG_EARLY = DVG_STEP_TRIG_EARLY != 0;   // trigger partial sums before the first tile epilogue
 #ifndef DVG_STEP_POLL_BATCH
-#define DVG_STEP_POLL_BATCH 0     // measured slower (fence.acq_rel.gpu + 16-wide sampling): kth_s100 +1.2 us per step
+#define DVG_STEP_POLL_BATCH 0     // measured: sampling 4 flags per poll + grouped acquires is SLOWER (kth_s100 45.1 vs 43.9 us per step)
+#endif
+#ifndef DVG_STEP_WFENCE
+#define DVG_STEP_WFENCE 1
 #endif
 constexpr int STEP_BAR_BYTES = 384;     // mbarriers + tmem slot + misc words
 
@@ -112,6 +115,9 @@ struct StepArgs {
 // Spin with relaxed loads (an acquire load drags a CCTL.IVALL -- an L1 invalidate -- through the SM on every
 // iteration); one acquire load after the condition holds orders the subsequent reads.
 __device__ __forceinline__ void poll_ge(const int* flag, int target, int item) {
+  // fast path: the flag is usually at target already (the tiles of a row group publish close together, and the
+  // producer lane gets here one k-block at a time): ONE acquire load instead of relaxed load + acquire load
+  if (ptx::ld_acquire_gpu(flag) >= target) return;
   if (ptx::ld_relaxed_gpu(flag) < target) {
     const long long t0 = clock64();
     while (ptx::ld_relaxed_gpu(flag) < target) {
@@ -124,38 +130,45 @@ __device__ __forceinline__ void poll_ge(const int* flag, int target, int item) {
   (void)ptx::ld_acquire_gpu(flag);
 }
 
-// Dependency wait of a consumer item: k-block `j` of flags[0..n) must have reached `target`.  Every not yet
-// acknowledged flag is sampled in the same poll iteration (independent relaxed loads: one L2 round trip for all of
-// them), one acquire fence + one generic->async proxy fence follow, and every flag seen at target BEFORE the fences is
-// recorded in `ready` so the k-blocks it covers skip both the poll and the fences.  (One poll + ld.acquire +
-// fence.proxy.async per k-block cost the producer lane ~1.1 us each -- three dependent L2 round trips -- although the
-// four producing tiles of a row group publish within ~1 us of each other: traces of round 2, profiles/r02_*.)
+// Dependency wait of a consumer item: k-block `j` of flags[0..n) must have reached `target`.
+// Traced cost of the round-1 form (per k-block: relaxed poll, ld.acquire, fence.proxy.async, each a dependent L2 round
+// trip or worse -- the proxy fence alone ~0.45 us) was ~1.2 us per k-block on the producer lane although the four
+// producing tiles of a row group publish within ~1 us of each other (profiles/r02_step_trace.md).  Now:
+//   * DVG_STEP_WFENCE: the generic->async proxy fence sits on the WRITER side (every epilogue thread fences its own
+//     stores of the packed h' image before the CTA barrier that precedes the release) -- it is on the causality path
+//     from the writes to our TMA reads either way, but there it is paid once per tile, in parallel, not per k-block
+//     on the consumer's serial path;
+//   * DVG_STEP_POLL_BATCH: the flags of up to four k-blocks are sampled per poll iteration (independent relaxed
+//     loads, one round trip), the ones found at target are acquired together (independent ld.acquire, one round
+//     trip) and remembered in `ready`, so their k-blocks skip the wait entirely.
 __device__ __forceinline__ void poll_deps(const int* flags, int n, int j, int target, uint32_t& ready, int item) {
   if ((ready >> j) & 1u) return;
 #if !DVG_STEP_POLL_BATCH
   poll_ge(flags + j, target, item);
-  ptx::fence_proxy_async_all();
-  return;
-#endif
+#else
   const long long t0 = clock64();
   for (;;) {
-    int v[16];
+    int v[4];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = (q < n && !((ready >> q) & 1u)) ? ptx::ld_relaxed_gpu(flags + q) : 0;
-    uint32_t m = 0;
+    for (int q = 0; q < 4; ++q) v[q] = j + q < n ? ptx::ld_relaxed_gpu(flags + j + q) : 0;
+    if (v[0] >= target) {
+      int a[4];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) m |= (v[q] >= target ? 1u : 0u) << q;
-    if ((m >> j) & 1u) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      ptx::fence_proxy_async_all();       // generic-proxy writes of the producing pairs -> visible to our TMA
-      ready |= m;
-      return;
+      for (int q = 0; q < 4; ++q) a[q] = v[q] >= target ? ptx::ld_acquire_gpu(flags + j + q) : 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (a[q] >= target) ready |= 1u << (j + q);
+      break;
     }
     if (clock64() - t0 > 4000000000LL) {
       printf("dvg_b200: dependency wait timed out (block %d item %d k-block %d)\n", (int)blockIdx.x, item, j);
       __trap();
     }
   }
+#endif
+#if !DVG_STEP_WFENCE
+  ptx::fence_proxy_async_all();       // generic-proxy writes of the producing pairs -> visible to our TMA
+#endif
 }
 
 __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid_constant__ StepArgs p) {
@@ -392,9 +405,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
                 const int* fl = wait_flags + rg * kb_in + kb;
                 while (ptx::ld_relaxed_gpu(fl) < 2) {}
                 TRACE(112 + kb * 4 + 1);
-                (void)ptx::ld_acquire_gpu(fl);
-                TRACE(112 + kb * 4 + 2);
+                const int acq = ptx::ld_acquire_gpu(fl);
+                if (acq >= 2) TRACE(112 + kb * 4 + 2);
+#if !DVG_STEP_WFENCE
                 ptx::fence_proxy_async_all();
+#endif
                 TRACE(112 + kb * 4 + 3);
               } else
 #endif
@@ -788,6 +803,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         // (CTA barrier, then ONE thread fences at gpu scope and bumps the counter: the release is cumulative over
         // the stores the barrier ordered before it -- no per-thread membar)
         if (etid == 0 && tm == 0) TRACE(33);
+#if DVG_STEP_WFENCE
+        ptx::fence_proxy_async_global();          // our stores of the image -> visible to the consumers' TMA loads
+#endif
         ptx::named_bar_sync(1, STEP_EW * 32);
         if (etid == 0) {
           if (tm == 0) TRACE(34);
@@ -1301,8 +1319,8 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   {
     static int mega = -1;
     if (mega < 0) {
-      const char* e = getenv("DVG_STEP_HEAD_MEGA");   // developer switch: 0 = head k-blocks staged through the ring
-      mega = (e && e[0] == '0') ? 0 : 1;
+      const char* e = getenv("DVG_STEP_HEAD_MEGA");   // developer switch: 1 = all head k-blocks resident at once
+      mega = (e && e[0] == '1') ? 1 : 0;              // measured slower than the staged head (+0.5..0.9 us per step)
     }
     const size_t head_bytes = (size_t)hk * nparts * ((size_t)TC_A_IMG + (size_t)h->tc_head.n_tile * 64);
     a.head_mega = (mega && head_bytes <= (size_t)stages * stage_bytes) ? 1 : 0;
