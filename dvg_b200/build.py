@@ -26,7 +26,7 @@ if os.environ.get("DVG_STEP_TRIG_EARLY"):   # developer build: 0 = trigger parti
     NVCC_FLAGS.append("-DDVG_STEP_TRIG_EARLY=" + os.environ["DVG_STEP_TRIG_EARLY"])
 if os.environ.get("DVG_STEP_EW"):        # developer build: 8 or 16 epilogue warps in the step kernel
     NVCC_FLAGS.append("-DDVG_STEP_EW=" + os.environ["DVG_STEP_EW"])
-for _k in ("DVG_STEP_POLL_BATCH", "DVG_STEP_WFENCE", "DVG_STEP_X"):      # developer builds: A/B switches of the step kernel
+for _k in ("DVG_STEP_POLL_BATCH", "DVG_STEP_WFENCE", "DVG_STEP_WARM", "DVG_STEP_X"):      # developer builds: A/B switches of the step kernel
     if os.environ.get(_k):
         NVCC_FLAGS.append("-D%s=%s" % (_k, os.environ[_k]))
 if os.environ.get("DVG_TRACE"):          # developer build: per-CTA timestamps in the tensor-core kernel

@@ -18,6 +18,7 @@
 //   warps 2-17   x-pack prologue of the pair's own layer-0 items, GP trigger partial sums (4 threads per
 //                (rollout, dim) task, in the idle window before the first accumulator is ready), tile epilogues;
 //                after the CTA's last tile: GP resample problems of the fired rollouts from a dynamic queue
+//   warp 19      weight-stream producer (one lane): cp.async.bulk of every stage's weight half, L2 evict_last
 //   warp 18      auxiliary: in the last ceil(S/32) CTAs it finalises the GP trigger (window / threshold / decision)
 //                once the partial variances have been delivered, and publishes the mask
 //
@@ -57,8 +58,9 @@ constexpr int STEP_UPW = 64 / STEP_NSUB;             // hidden units per warp an
 constexpr int STEP_RB = STEP_UPW * 4;                // bytes per row of a warp's transpose buffer: 128 or 64
 constexpr int STEP_CPR = STEP_UPW / 4;               // 16-byte chunks per row: 8 or 4
 constexpr int STEP_EBUF_BYTES = STEP_EW * 32 * STEP_RB;   // 32 KB either way
-constexpr int STEP_THREADS = 64 + STEP_EW * 32 + 32;
+constexpr int STEP_THREADS = 64 + STEP_EW * 32 + 64;
 constexpr int AUX_WARP = 2 + STEP_EW;
+constexpr int WPROD_WARP = 3 + STEP_EW;     // weight-stream producer
 constexpr int STEP_MAX_STAGES = 6;
 constexpr int STEP_XMAX = 8;            // layer-0 items per pair (one x-ready mbarrier each)
 #ifndef DVG_STEP_NPOLY
@@ -74,6 +76,9 @@ constexpr bool STEP_TRIG_EARLY = DVG_STEP_TRIG_EARLY != 0;   // trigger partial 
 #endif
 #ifndef DVG_STEP_WFENCE
 #define DVG_STEP_WFENCE 1
+#endif
+#ifndef DVG_STEP_WARM
+#define DVG_STEP_WARM 0      // measured: no gain (kth_s100 +0.3 us, trigger steps of bair_s32 +1.2 us)
 #endif
 constexpr int STEP_BAR_BYTES = 384;     // mbarriers + tmem slot + misc words
 
@@ -99,7 +104,6 @@ struct StepTrig {
 };
 struct StepArgs {
   int rows, row_tiles, groups, nsplit, stages, n_phases, total_items, H, L, G, ldx, kbx, rows_per_flag, restore;
-  int head_mega;                  // head items load ALL their k-blocks into the (drained) ring at once, see the producer
   uint32_t stage_bytes;
   const float* x; uint8_t* xp;
   const uint8_t* hold;            // mask known BEFORE the launch (plain dvg_lstm_step); nullptr in trigger-fused steps
@@ -128,6 +132,51 @@ __device__ __forceinline__ void poll_ge(const int* flag, int target, int item) {
     }
   }
   (void)ptx::ld_acquire_gpu(flag);
+}
+
+// Head tile epilogue  y = tanh(acc + b)  of one warp (see the call site).  Deliberately NOT inlined: the step kernel
+// calls it once per head tile, at the very end of the step's dependency chain, where its instructions were cold in
+// the instruction caches (a 128 x 96 tile took 2.3 us); every epilogue warp therefore also runs it once as a dry run
+// (n_rows = 0: nothing is stored) in the idle window before its first accumulator is ready, which only works if both
+// calls execute the same code.
+__device__ __noinline__ void head_tanh_tile(uint32_t tacc, int n_tile, int sub, int lane, const float* sb, uint8_t* hb,
+                                            float* yout, int ldy, int n_valid, int n_rows, int row_w0) {
+  const int ncw = n_tile / STEP_NSUB;          // columns of this warp (n_tile is a multiple of 32)
+  const int c_begin = sub * ncw;
+  const bool vec2 = (ldy & 1) == 0 && (n_valid & 1) == 0 && (reinterpret_cast<uintptr_t>(yout) & 7) == 0;
+  const int lr = lane >> 2, cc = (lane & 3) * 2;
+  uint32_t cur[8], nxt[8];
+  ptx::tmem_ld8(tacc + c_begin, cur);
+  ptx::tmem_ld_wait8(cur);
+#pragma unroll 1
+  for (int c8 = 0; c8 < ncw; c8 += 8) {
+    const int cn = c8 + 8 < ncw ? c8 + 8 : c8;   // last trip: harmless re-read
+    ptx::tmem_ld8(tacc + c_begin + cn, nxt);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)                   // XU bound: every other exponential goes to the FMA pipe
+      v[i] = (i & 1) ? tanh_fast_prescaled_poly(__uint_as_float(cur[i]), sb[c_begin + c8 + i])
+                     : tanh_fast_prescaled(__uint_as_float(cur[i]), sb[c_begin + c8 + i]);
+    *reinterpret_cast<float4*>(hb + lane * 32) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(hb + lane * 32 + 16) = make_float4(v[4], v[5], v[6], v[7]);
+    __syncwarp();
+    const int col = c_begin + c8 + cc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = i * 8 + lr;
+      const float2 t = *reinterpret_cast<const float2*>(hb + rr * 32 + cc * 4);
+      const int grow = row_w0 + rr;
+      if (grow < n_rows && col < n_valid) {
+        float* dst = yout + (size_t)grow * ldy + col;
+        if (vec2) __stcs(reinterpret_cast<float2*>(dst), t);
+        else { dst[0] = t.x; if (col + 1 < n_valid) dst[1] = t.y; }
+      }
+    }
+    __syncwarp();
+    ptx::tmem_ld_wait8(nxt);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+  }
 }
 
 // Dependency wait of a consumer item: k-block `j` of flags[0..n) must have reached `target`.
@@ -282,7 +331,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
   if (threadIdx.x == 0) {
     TRACE(0);
     for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(full_bar(s), 2);        // activation producer + weight producer, each with its own expect_tx
       ptx::mbar_init(empty_bar(s), 1);
       ptx::mbar_init(pfull_bar(s), 1);
     }
@@ -322,7 +371,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       // per consumer and are dead afterwards (the state blocks ping-pong) -> evict first; the weights are re-read by
       // every row group of every step -> evict last.  (Measured neutral on kth_s100, where both state blocks and the
       // weights already stay in the 126 MB L2; it matters when the caller's conv nets stream through L2 in between.)
-      const uint64_t pol_stream = ptx::l2_policy_evict_first(), pol_keep = ptx::l2_policy_evict_last();
+      const uint64_t pol_stream = ptx::l2_policy_evict_first();
       for (int k = 0;; ++k) {
         const int item = item_at(k);
         if (item < 0) break;
@@ -337,48 +386,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         //  constant-bank loads inside the k-block loops were ~100 cycles each on the issue path)
         const int kb_rec = f.kb_rec, kb_in = f.kb_in;
         const int KB = kb_rec + kb_in;
-        const uint32_t b_half = (uint32_t)f.n_tile * 64u, b_part = (uint32_t)f.n_tile * 128u;
         const int* wait_flags = f.wait_flags;
         const bool layer0 = wait_flags == nullptr;
         const uint8_t* a_rec = f.a_rec;
-        const uint8_t* wbase = f.w;
         const uint8_t* a_in = f.a_in;
         if (layer0) a_in += (size_t)nt * p.row_tiles * kb_in * (2u * TC_A_IMG);
-        if (p.head_mega && f.type != PH_LSTM) {
-          // Head item: K = H is short and N <= 256 narrow, so ALL its k-blocks fit the ring at once ([A k-blocks |
-          // this CTA's weight halves], one transaction on the first slot's barrier).  A staged head paid the ring's
-          // fill latency per k-block (~1 us each for ~0.1 us of tensor work) at the very end of the step's dependency
-          // chain; now it pays it once.  Every ring position is consumed so the phase bookkeeping of the three roles
-          // stays in lock step.
-          const uint32_t wbytes = nparts * b_half;
-          int s0 = 0;
-          for (int q = 0; q < p.stages; ++q) {
-            ptx::mbar_wait(empty_bar(s), phs ^ 1u);
-            if (q == 0) {
-              s0 = s;
-              ptx::mbar_expect_tx(full_bar(s0), (uint32_t)KB * (a_bytes + wbytes));
-            } else {
-              ptx::mbar_arrive(full_bar(s));
-            }
-            if (++s == p.stages) { s = 0; phs ^= 1u; }
-          }
-          const uint32_t wb0 = base + (uint32_t)KB * a_bytes;
-          for (int kb = 0; kb < KB; ++kb) {          // weights never depend on this launch: request them first
-            const uint8_t* bsrc = wbase + (size_t)(nt * KB + kb) * (2u * b_part) + rank * b_half;
-            ptx::bulk_g2s_hint(wb0 + (uint32_t)kb * wbytes, bsrc, b_half, full_bar(s0), pol_keep);
-            if (nparts == 2) ptx::bulk_g2s_hint(wb0 + (uint32_t)kb * wbytes + b_half, bsrc + b_part, b_half, full_bar(s0), pol_keep);
-          }
-          {
-            uint32_t ready = 0;
-            for (int kb = 0; kb < KB; ++kb) poll_deps(wait_flags + rg * kb_in, kb_in, kb, 2, ready, item);
-          }
-          if (pm < 3) TRACE(2 + pm * 8 + 1);
-          for (int kb = 0; kb < KB; ++kb)
-            ptx::bulk_g2s(base + (uint32_t)kb * a_bytes, a_in + (size_t)(rt * kb_in + kb) * (2u * TC_A_IMG), a_bytes, full_bar(s0));
-          if (pm < 3) TRACE(2 + pm * 8 + 7);
-          ++pm;
-          continue;
-        }
         uint32_t ready = 0;                                // input k-blocks whose dependency has been acknowledged
 #ifdef DVG_TRACE
         if (dep_item < 0 && !layer0) dep_item = pm;        // first dependent item of this CTA: poll phases are traced
@@ -386,17 +398,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         for (int i = 0; i < KB; ++i) {
           const bool rec = i < kb_rec;
           const int kb = rec ? i : i - kb_rec;
-          // The weight half of a stage never depends on this launch: request it as soon as the stage is free, THEN
-          // wait for the activation k-block (dependency counter / x-pack) -- half of the stage's bytes are already in
-          // flight while the producing pair is still in its epilogue.
+          // (the weight half of the stage is requested by the weight producer warp as soon as the stage is free --
+          //  it never depends on this launch -- so half of the stage's bytes are already in flight while we wait for
+          //  the activation k-block: dependency counter / x-pack)
           ptx::mbar_wait(empty_bar(s), phs ^ 1u);
-          const int wk = rec ? kb_in + kb : kb;            // weight K order: [input | recurrent]
-          const uint8_t* bsrc = wbase + (size_t)(nt * KB + wk) * (2u * b_part) + rank * b_half;
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
-          const uint32_t sb = sa + a_bytes;
-          ptx::mbar_expect_tx(full_bar(s), a_bytes + nparts * b_half);
-          ptx::bulk_g2s_hint(sb, bsrc, b_half, full_bar(s), pol_keep);
-          if (nparts == 2) ptx::bulk_g2s_hint(sb + b_half, bsrc + b_part, b_half, full_bar(s), pol_keep);
           if (!rec) {
             if (!layer0) {
 #ifdef DVG_TRACE
@@ -423,6 +429,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           }
           const uint8_t* asrc = rec ? a_rec + (size_t)(rt * kb_rec + kb) * (2u * TC_A_IMG)
                                     : a_in + (size_t)(rt * kb_in + kb) * (2u * TC_A_IMG);
+          ptx::mbar_expect_tx(full_bar(s), a_bytes);
           if (rec || layer0) ptx::bulk_g2s_hint(sa, asrc, a_bytes, full_bar(s), pol_stream);
           else ptx::bulk_g2s(sa, asrc, a_bytes, full_bar(s));        // h' of the layer below: re-read by every N tile
           if (pm < 3 && i < 8) TRACE(88 + pm * 8 + i);
@@ -442,45 +449,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         const StepPhase& f = p.ph[phase_of(item)];
         const int kb_rec = f.kb_rec, in_ksteps = f.in_ksteps;
         const int KB = kb_rec + f.kb_in;
-        const bool mega = p.head_mega && f.type != PH_LSTM;
-        if (rank == 0 && mega) {
-          // ===================== MMA issuer, head item with all k-blocks resident =====================
-          const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, f.n_tile);
-          const uint32_t b_half = (uint32_t)f.n_tile * 64u;
-          const uint32_t wbytes = nparts * b_half;
-          const int acc = mit & 1;
-          const uint32_t aph = (uint32_t)(mit >> 1) & 1u;
-          ptx::mbar_wait(tempty_bar(acc), aph ^ 1u);
-          for (int q = 0; q < p.stages; ++q) {
-            ptx::mbar_wait(full_bar(s), phs);
-            ptx::mbar_wait(pfull_bar(s), phs);
-            if (++s == p.stages) { s = 0; phs ^= 1u; }
-          }
-          if (mit < 3) TRACE(2 + mit * 8 + 2);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
-          uint32_t accum = 0;
-          for (int i = 0; i < KB; ++i) {
-            const int left = in_ksteps - i * (TC_KBLK / 16);
-            const int ks = left < TC_KBLK / 16 ? left : TC_KBLK / 16;
-            const uint32_t sa = base + (uint32_t)i * a_bytes;
-            const uint32_t sw = base + (uint32_t)KB * a_bytes + (uint32_t)i * wbytes;
-            const uint64_t a_hi = ptx::make_sw128_desc(sa), a_lo = ptx::make_sw128_desc(sa + TC_A_IMG);
-            const uint64_t b_hi = ptx::make_sw128_desc(sw), b_lo = ptx::make_sw128_desc(sw + b_half);
-            for (int kk = 0; kk < ks; ++kk) {
-              const uint64_t adv = (uint64_t)(kk * 2);
-              ptx::umma2_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
-              accum = 1u;
-              if (nparts == 2) {
-                ptx::umma2_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                ptx::umma2_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-              }
-            }
-          }
-          for (int q = 0; q < p.stages; ++q) ptx::umma2_commit_mcast(empty_bar(q), 3);
-          ptx::umma2_commit_mcast(tfull_bar(acc), 3);
-          if (mit < 3) TRACE(2 + mit * 8 + 3);
-        } else if (rank == 0) {
+        if (rank == 0) {
           // ===================== MMA issuer (leader CTA) =====================
           const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_ROWS, f.n_tile);
           const uint32_t b_half = (uint32_t)f.n_tile * 64u;
@@ -522,12 +491,42 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           if (mit < 3) TRACE(2 + mit * 8 + 3);
         } else {
           // ===================== relay (peer CTA): "my stage landed" -> leader's pfull =====================
-          const int n_pos = mega ? p.stages : KB;
-          for (int i = 0; i < n_pos; ++i) {
+          for (int i = 0; i < KB; ++i) {
             ptx::mbar_wait(full_bar(s), phs);
             ptx::mbar_arrive_remote(pfull_bar(s), 0);
             if (++s == p.stages) { s = 0; phs ^= 1u; }
           }
+        }
+      }
+    }
+  } else if (warp == WPROD_WARP) {
+    // ===================== weight-stream producer (both CTAs of the pair) =====================
+    // Weights never depend on anything produced in this launch: their half of every stage is requested the moment the
+    // stage is free, by a lane of its own, so the dependency polls / x-ready waits of the activation producer (each a
+    // chain of L2 round trips) neither delay them nor are delayed by their issue cost.
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phs = 0;
+      const uint64_t pol_keep = ptx::l2_policy_evict_last();   // re-read by every row group of every step
+      for (int k = 0;; ++k) {
+        const int item = item_at(k);
+        if (item < 0) break;
+        const StepPhase& f = p.ph[phase_of(item)];
+        const int j = item - f.item_begin;
+        const int nt = j % f.n_tiles;
+        const int kb_rec = f.kb_rec, kb_in = f.kb_in;
+        const int KB = kb_rec + kb_in;
+        const uint32_t b_half = (uint32_t)f.n_tile * 64u, b_part = (uint32_t)f.n_tile * 128u;
+        const uint8_t* wbase = f.w + (size_t)nt * KB * (2u * b_part) + rank * b_half;
+        for (int i = 0; i < KB; ++i) {
+          const int wk = i < kb_rec ? kb_in + i : i - kb_rec;     // weight K order: [input | recurrent]
+          ptx::mbar_wait(empty_bar(s), phs ^ 1u);
+          const uint32_t sb = base + (uint32_t)s * stage_bytes + a_bytes;
+          const uint8_t* bsrc = wbase + (size_t)wk * (2u * b_part);
+          ptx::mbar_expect_tx(full_bar(s), nparts * b_half);
+          ptx::bulk_g2s_hint(sb, bsrc, b_half, full_bar(s), pol_keep);
+          if (nparts == 2) ptx::bulk_g2s_hint(sb + b_half, bsrc + b_part, b_half, full_bar(s), pol_keep);
+          if (++s == p.stages) { s = 0; phs ^= 1u; }
         }
       }
     }
@@ -575,6 +574,21 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         }
       }
     }
+    // Decision steps: the auxiliary lane of EVERY CTA fetches the fired count as soon as the mask is published (long
+    // before the CTA's last tile), so the end-of-kernel restore check reads shared memory instead of paying three
+    // dependent global round trips (fence, mask poll, count load ~1.3 us) on the tail of every decision step.
+    if (p.restore && lane == 0) {
+      const long long t0 = clock64();
+      while (ptx::ld_relaxed_gpu(p.mask_ready) < 1) {
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000LL) {
+          printf("dvg_b200: mask wait timed out (block %d)\n", (int)blockIdx.x);
+          __trap();
+        }
+      }
+      (void)ptx::ld_acquire_gpu(p.mask_ready);
+      s_misc[0] = *reinterpret_cast<volatile int*>(p.trig.trig_count);
+    }
   } else {
     // ===================== epilogue / SIMT worker warps (2 .. 2+STEP_EW-1) =====================
     const int ew = warp - 2;
@@ -583,6 +597,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
     const uint32_t r_in_tile = (uint32_t)(q * 32 + lane);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const int etid = ew * 32 + lane;
+#if DVG_STEP_WARM
+    // instruction-cache warm-up of the head epilogue (see head_tanh_tile): reads this warp's (unwritten) TMEM lanes and
+    // whatever the bias staging holds, stores nothing
+    if (p.ph[p.n_phases - 1].type == PH_TANH)
+      head_tanh_tile(tmem_base + tlane, p.ph[p.n_phases - 1].n_tile, ew >> 2, lane, s_bias, s_ebuf + ew * (32 * STEP_RB),
+                     p.ph[p.n_phases - 1].y, p.ph[p.n_phases - 1].ldy, p.ph[p.n_phases - 1].n_valid, 0, 0);
+#endif
     // x-pack of every layer-0 item of this pair, in item order
     {
       int xj = 0;
@@ -849,45 +870,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         // (4 lanes per row, 8 rows per store instruction).  The next trip's accumulators are fetched from TMEM while
         // the current trip is computed.  (This code runs once per head tile, at the very end of the step's dependency
         // chain: all epilogue warps take part and the loop body is small -- it is cold in the instruction caches.)
-        const int ncw = f.n_tile / STEP_NSUB;          // columns of this warp (n_tile is a multiple of 32)
-        const int c_begin = sub * ncw;
-        float* const yout = f.y;
-        const int ldy = f.ldy, n_valid = f.n_valid, n_rows = p.rows;
-        const bool vec2 = (ldy & 1) == 0 && (n_valid & 1) == 0 && (reinterpret_cast<uintptr_t>(yout) & 7) == 0;
-        uint8_t* hb = s_ebuf + ew * (32 * STEP_RB);    // the warp's own LSTM transpose buffer (>= 1 KB)
-        const int lr = lane >> 2, cc = (lane & 3) * 2;
-        uint32_t cur[8], nxt[8];
-        ptx::tmem_ld8(tacc + c_begin, cur);
-        ptx::tmem_ld_wait8(cur);
-#pragma unroll 1
-        for (int c8 = 0; c8 < ncw; c8 += 8) {
-          const int cn = c8 + 8 < ncw ? c8 + 8 : c8;   // last trip: harmless re-read
-          ptx::tmem_ld8(tacc + c_begin + cn, nxt);
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)                   // XU bound: every other exponential goes to the FMA pipe
-            v[i] = (i & 1) ? tanh_fast_prescaled_poly(__uint_as_float(cur[i]), sb[c_begin + c8 + i])
-                           : tanh_fast_prescaled(__uint_as_float(cur[i]), sb[c_begin + c8 + i]);
-          *reinterpret_cast<float4*>(hb + lane * 32) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(hb + lane * 32 + 16) = make_float4(v[4], v[5], v[6], v[7]);
-          __syncwarp();
-          const int col = c_begin + c8 + cc;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = i * 8 + lr;
-            const float2 t = *reinterpret_cast<const float2*>(hb + rr * 32 + cc * 4);
-            const int grow = row_w0 + rr;
-            if (grow < n_rows && col < n_valid) {
-              float* dst = yout + (size_t)grow * ldy + col;
-              if (vec2) __stcs(reinterpret_cast<float2*>(dst), t);
-              else { dst[0] = t.x; if (col + 1 < n_valid) dst[1] = t.y; }
-            }
-          }
-          __syncwarp();
-          ptx::tmem_ld_wait8(nxt);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-        }
+        head_tanh_tile(tacc, f.n_tile, sub, lane, sb, s_ebuf + ew * (32 * STEP_RB), f.y, f.ldy, f.n_valid, p.rows, row_w0);
         if (etid == 0 && tm == 2) TRACE(38);
       } else if (f.type == PH_GAUSS && sub < 2) {
         const int nchunks = f.n_tile / 16;
@@ -943,16 +926,15 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
   // Rare, so it is handled after the fact: once every CTA has finished its items, the state rows of the fired
   // rollouts are copied back from the input block (fp32 h, c and the packed h images), spread over all CTAs.
   if (p.restore) {
-    if (threadIdx.x == 0) {
-      __threadfence();                 // cumulative over this CTA's stores (ordered by the barrier above)
-      atomicAdd(p.done_ctr, 1);
-      poll_ge(p.mask_ready, 1, -1);
-      s_misc[0] = *reinterpret_cast<volatile int*>(p.trig.trig_count);
-    }
-    __syncthreads();
+    // (s_misc[0] = fired count, written by the auxiliary lane once the mask was published; the barrier of the
+    //  teardown above ordered it before us.  done_ctr is only waited for when something fired.)
     const int n_fired = s_misc[0];
     if (threadIdx.x == 0) TRACE(39);
     if (n_fired > 0) {
+      if (threadIdx.x == 0) {
+        __threadfence();               // cumulative over this CTA's stores (ordered by the barrier above)
+        atomicAdd(p.done_ctr, 1);
+      }
       // Phase A -- their decoder input becomes a GP posterior sample of the encoder latent instead of the LSTM
       // prediction (generate_frames.py:291-292).  The (fired rollout, latent dim) problems only need the step's INPUT,
       // so they start as soon as the mask is known, taken from a dynamic queue by whichever CTAs have finished their
@@ -1184,12 +1166,12 @@ static bool sched_pattern_two_layer(int P, int groups, int hk, std::vector<std::
 int lstm_step_build_schedule(dvg_lstm_s* h, int rows) {
   if (h->sched_dev) { h->retired.push_back(h->sched_dev); h->sched_dev = nullptr; }   // captured graphs may hold it
   h->sched_len = h->sched_rows = h->sched_pairs = 0;
-  // DVG_STEP_SCHED: 0 / unset = layer-major identity order, 1 = list scheduler on the cost model, 2 = the two-layer
-  // pattern above.  Both alternatives are experimental: on kth_s100 neither beat the identity order (2.28 ms per rollout
-  // either way) -- the tail only moves from the heads of the last row groups to those of the (L1, L1) pairs, because three
-  // ~6 us tile epilogues per pair plus the ~10 us head chain bound the launch, not the order.
+  // DVG_STEP_SCHED: 0 = layer-major identity order, 1 = list scheduler on the cost model (experimental: its cost model
+  // dates from round 1 and it measures +1.3 us on kth_s100), 2 / unset = the two-layer pattern above where it applies
+  // (a few more tiles per layer than pairs; identity order otherwise).  Measured on kth_s100, round 2: 43.4 vs 43.8 us
+  // per plain step, 43.5 vs 44.2 us per decision step.
   const char* e = getenv("DVG_STEP_SCHED");
-  const int mode = e ? atoi(e) : 0;
+  const int mode = e ? atoi(e) : 2;       // round 2: the two-layer pattern is the default where it applies (kth_s100 -0.5 us)
   if (mode == 0) return DVG_OK;
   const int L = h->dims.n_layers, hk = h->dims.hidden_size / 64;
   const int RT = ceil_div(rows, TC_ROWS), groups = ceil_div(RT, 2);
@@ -1316,15 +1298,6 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   int stages = (int)((227 * 1024 - tail) / stage_bytes);
   if (stages > STEP_MAX_STAGES) stages = STEP_MAX_STAGES;
   a.stages = stages; a.stage_bytes = (uint32_t)stage_bytes;
-  {
-    static int mega = -1;
-    if (mega < 0) {
-      const char* e = getenv("DVG_STEP_HEAD_MEGA");   // developer switch: 1 = all head k-blocks resident at once
-      mega = (e && e[0] == '1') ? 1 : 0;              // measured slower than the staged head (+0.5..0.9 us per step)
-    }
-    const size_t head_bytes = (size_t)hk * nparts * ((size_t)TC_A_IMG + (size_t)h->tc_head.n_tile * 64);
-    a.head_mega = (mega && head_bytes <= (size_t)stages * stage_bytes) ? 1 : 0;
-  }
   const size_t smem = stages * stage_bytes + tail;
   static bool configured = false;
   if (!configured) {
