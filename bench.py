@@ -12,10 +12,19 @@ held for triggered rollouts) -> masked GP rsample.  The encoder/decoder convolut
 PyTorch path (north_star) and are NOT part of the timed hot path; the latents they would produce are
 synthetic tensors resident in HBM.  frames = S * B * n_future per rollout.
 
-JSON keys beyond the base contract: ``roofline`` (dominant kernel = the tcgen05 LSTM layer GEMM, timed
-live with CUDA events between launches), ``cpu_baseline`` (oracle port on the host cores, bounded sample),
-``e2e`` (same metric through the public Python API with pinned HOST buffers, H2D + D2H inside the timed
-region), ``gpu_launches``, ``clocks``.
+JSON keys beyond the base contract:
+``roofline``          dominant kernel = ``lstm_step_kernel`` (ONE persistent tcgen05 launch per time step: x-pack, all
+                      LSTM layers, head, GP trigger, restore/resample of fired rollouts); launch duration = CUDA-graph
+                      replay of the T step launches of one rollout / T, CUDA events on the launching stream
+``cpu_baseline``      the reference's CPU path on the host cores, bounded sample (LSTM stage: the reference's own
+                      ``models/lstm.py`` when present under baseline/_ref or /root/reference, GP stage: oracle port)
+``e2e``               the same metric through the public Python API with pinned HOST buffers, H2D + D2H in the timed region
+``stock_torch_b200``  BASELINE.md section 3's practical bar: the reference ``lstm`` module with stock PyTorch ops (cuBLAS sgemm +
+                      ATen LSTM-cell pointwise) ON THE SAME B200, same rows / steps, allow_tf32 off and on, eager and as a CUDA
+                      graph, next to our plain LSTM step (no trigger) timed the same way
+``pixel_e2e``         SURVEY 8d (i): generated frames/s of the same workload in PIXEL space (stock cuDNN encoder / decoder +
+                      the hot path, ``PixelRollout``), with the hot path's share of that time
+``gpu_launches``, ``clocks``.
 """
 from __future__ import annotations
 
@@ -135,6 +144,202 @@ def flops_bytes(w, R):
     f_row = 2 * (G * H + L * (2 * H) * (4 * H) + H * G)
     b_row = 4 * (2 * (2 * L * H) + 2 * G)
     return f_row, b_row, 2 * R * (2 * H) * (4 * H)   # last: one LSTM-layer GEMM launch
+
+
+# ---------------------------------------------------------------------------------------------------------
+def reference_lstm_module():
+    """The reference's own ``models/lstm.py`` (unmodified file), from baseline/_ref (written by
+    ``__graft_entry__.build()`` where /root/reference exists; git-ignored, travels to the GPU box) or /root/reference.
+    Returns (module, where) or (None, why)."""
+    import importlib.util
+    for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        path = os.path.join(root, "models", "lstm.py")
+        if os.path.exists(path):
+            spec = importlib.util.spec_from_file_location("_dvg_reference_models_lstm", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod, path
+    return None, "models/lstm.py not found under baseline/_ref or /root/reference"
+
+
+def graph_time_us(fn, n_steps, reps=10):
+    """CUDA-graph replay of ``fn`` (which enqueues n_steps steps) timed with CUDA events: us per step (best, mean)."""
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.no_grad():
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g), torch.no_grad():
+        fn()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best, tot = 1e30, 0.0
+    for _ in range(reps):
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        best, tot = min(best, ms), tot + ms
+    return best * 1e3 / n_steps, tot / reps * 1e3 / n_steps
+
+
+def stock_torch_b200(w, R, T, device, eng, lat):
+    """BASELINE.md section 3 "also measure": the reference ``lstm`` (models/lstm.py:42-72) with stock PyTorch ops on
+    this GPU -- embed addmm, 2 x (2 sgemm + ATen fused LSTM-cell pointwise), output addmm + tanh -- at the bench's
+    rows and time steps, against our plain LSTM step (no trigger, same rows), both timed as CUDA-graph replays of T
+    steps; the stock module also eagerly (what a user gets with no effort: launch overhead included)."""
+    from dvg_b200.init import init_lstm_state_dict
+    res = {"rows": R, "time_steps": T, "what": "LSTM step only (the reference's GP stage needs gpytorch, absent here)"}
+    mod, where = reference_lstm_module()
+    sd = init_lstm_state_dict(w["G"], w["G"], w["H"], w["L"], 1)
+    if mod is not None:
+        m = mod.lstm(w["G"], w["G"], w["H"], w["L"], R)          # the constructor calls .cuda() (models/lstm.py:61-62)
+        res["source"] = "reference models/lstm.py, unmodified (%s)" % where
+    else:
+        import torch.nn as nn
+
+        class _Restated(nn.Module):                               # same modules and call order as models/lstm.py:42-72
+            def __init__(s_, G, H, L):
+                super().__init__()
+                s_.embed = nn.Linear(G, H)
+                s_.lstm = nn.ModuleList([nn.LSTMCell(H, H) for _ in range(L)])
+                s_.output = nn.Sequential(nn.Linear(H, G), nn.Tanh())
+                s_.n_layers, s_.hidden_size = L, H
+
+            def init_hidden(s_):
+                return [(torch.zeros(R, s_.hidden_size, device=device), torch.zeros(R, s_.hidden_size, device=device))
+                        for _ in range(s_.n_layers)]
+
+            def forward(s_, x):
+                h_in = s_.embed(x.view(-1, x.shape[-1]))
+                for i in range(s_.n_layers):
+                    s_.hidden[i] = s_.lstm[i](h_in, s_.hidden[i])
+                    h_in = s_.hidden[i][0]
+                return s_.output(h_in)
+        m = _Restated(w["G"], w["H"], w["L"])
+        res["source"] = "restated torch modules (%s)" % where
+    m.load_state_dict(sd)
+    m = m.to(device).eval()
+    x = lat[:T]
+
+    def stock_steps(init=True):
+        if init:
+            m.hidden = m.init_hidden()          # (zeros on the host + .cuda(): not capturable, done outside the graph)
+        for t in range(T):
+            m(x[t])
+
+    def stock_steps_graphed():
+        m.hidden = h0                           # static initial state: every replay starts from the same tensors
+        stock_steps(init=False)
+
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(2):
+                    stock_steps()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    stock_steps()
+                e1.record()
+                torch.cuda.synchronize()
+            res["eager_us_per_step_" + name] = e0.elapsed_time(e1) * 1e3 / (3 * T)
+            h0 = m.init_hidden()
+            res["graph_us_per_step_" + name] = graph_time_us(stock_steps_graphed, T)[0]
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            torch.backends.cuda.matmul.allow_tf32 = False
+            with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+                stock_steps()
+                torch.cuda.synchronize()
+            n_k = sum(e.count for e in prof.key_averages() if getattr(e, "device_type", None) is not None
+                      and "cuda" in str(e.device_type).lower())
+            res["launches_per_step"] = round(n_k / T, 2)
+        except Exception as e:                                    # noqa: BLE001
+            res["launches_per_step"] = "profiler unavailable: %s" % type(e).__name__
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    out = torch.empty(T, R, w["G"], device=device)
+
+    def ours_steps():
+        eng.reset()
+        for t in range(T):
+            eng.step_manual_mode(x[t], None, out[t], resample=False)
+
+    res["ours_us_per_step"] = graph_time_us(ours_steps, T)[0]
+    res["ours_launches_per_step"] = 1
+    # numerics of the two arms on the same inputs (stock fp32 as the reference)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        m.hidden = m.init_hidden()
+        ys = torch.stack([m(x[t]) for t in range(T)])
+        ours_steps()
+    torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    torch.cuda.synchronize()
+    res["ours_vs_stock_fp32_max_rel_err"] = ((out - ys).abs().max() / ys.abs().max()).item()
+    res["speedup_vs_stock_fp32_graph"] = res["graph_us_per_step_fp32"] / res["ours_us_per_step"]
+    res["speedup_vs_stock_tf32_graph"] = res["graph_us_per_step_tf32"] / res["ours_us_per_step"]
+    res["speedup_vs_stock_fp32_eager"] = res["eager_us_per_step_fp32"] / res["ours_us_per_step"]
+    eng.reset()
+    return res
+
+
+PIXEL = {   # workload -> (conv nets, channels, width): the reference's encoder / decoder for that data set
+    "smmnist_b16": ("dcgan_64", 1, 64), "kth_s100": ("vgg_64", 1, 64), "bair_s32": ("vgg_64", 3, 64),
+}
+
+
+def pixel_e2e(w, name, device, variant, hot_ms_per_rollout):
+    """the same workload in pixel space -- context frames in, S*B*n_future generated frames out, the
+    reference's conv nets on the stock cuDNN path (sample-batched through dvg_b200.codec.BatchedCodec, bf16, one CUDA
+    graph) around the hot path (make_gifs pass B, generate_frames.py:138-178: resample every 15th step)."""
+    if name not in PIXEL:
+        return {"skipped": "no conv-net table entry for %s" % name}
+    from dvg_b200.convnets import make_codec
+    from dvg_b200.rollout import PixelRollout
+    model, nc, width = PIXEL[name]
+    B, S = w["B"], w["S"]
+    n_past, n_eval = w["n_past"], w["n_past"] + w["n_future"]
+    fp, gp, lik = build_models(w, device, variant)
+    torch.manual_seed(1)
+    enc, dec = make_codec(model, w["G"], nc)
+    enc, dec = enc.to(device).eval(), dec.to(device).eval()
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(n_past, B, nc, width, width, generator=g).to(device)
+    pr = PixelRollout(fp, gp, lik, enc, dec, (nc, width, width), B, S, n_past, n_eval, variant=variant,
+                      codec_dtype=torch.bfloat16, graph=True)
+    pr.x.copy_(x[:pr.n_ctx])
+    pr.eps.normal_()
+    pr.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    e0.record()
+    for _ in range(reps):
+        pr.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    frames = S * B * w["n_future"]
+    res = {"value": frames / (ms * 1e-3), "unit": "frames/s", "ms_per_rollout": ms, "frames_per_rollout": frames,
+           "conv_nets": model + " (reference architecture, random init, eval; stock cuDNN via BatchedCodec bf16, channels-last, "
+                        "BatchNorm folded, skip half of the decoder convs shared across the S futures)",
+           "frame": "%dx%dx%d" % (nc, width, width), "cuda_graph": True,
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2),
+           "hot_path_share": hot_ms_per_rollout / ms,
+           "note": "the convolutions are out of the hot path's scope (north_star: they stay on the PyTorch path) and take "
+                   "all but hot_path_share of this time"}
+    del pr, fp, gp, lik, enc, dec
+    torch.cuda.empty_cache()
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -284,6 +489,18 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_rollout(w, T, budget_s=args.cpu_budget, threads=os.cpu_count())
+    stock = pix = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            stock = stock_torch_b200(w, R, T, device, eng, lat)
+        except Exception as e:                                    # noqa: BLE001
+            stock = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        try:
+            del pipe
+            torch.cuda.empty_cache()
+            pix = pixel_e2e(w, args.workload, device, args.variant, ms_per_step)
+        except Exception as e:                                    # noqa: BLE001
+            pix = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0:
         f_row, b_row, _ = flops_bytes(w, R)
         line = {
@@ -313,6 +530,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "stock_torch_b200": stock,
+            "pixel_e2e": pix,
             "hot_path_algorithmic": {"flops_per_row_step": f_row, "bytes_per_row_step": b_row},
         }
         print(json.dumps(line))
@@ -403,12 +622,27 @@ def cpu_rollout(w, T, budget_s, threads):
     sd = init_lstm_state_dict(w["G"], w["G"], w["H"], w["L"], 1)
     gsd, lsd = init_gp_state_dicts(w["G"], w["M"], 1)
     B, W = w["B"], w["window"]
+    # LSTM stage: the reference's own module where its file is available (models/lstm.py:42-72; its constructor and
+    # init_hidden call .cuda(), shimmed to a no-op for this CPU run), else the oracle restatement
+    ref_mod, where = reference_lstm_module()
+    ref_fp = None
+    if ref_mod is not None:
+        orig_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        try:
+            ref_fp = ref_mod.lstm(w["G"], w["G"], w["H"], w["L"], B)
+            ref_fp.load_state_dict(sd)
+            ref_fp.eval()
+        finally:
+            pass          # restored after the timed loop (init_hidden calls .cuda() too)
     g = torch.Generator().manual_seed(5)
     lat = torch.tanh(torch.randn(T, B, w["G"], generator=g))
     done, t0 = 0, time.perf_counter()
     with torch.no_grad():
         while True:
             hid = lstm_ref.init_hidden(w["L"], B, w["H"])
+            if ref_fp is not None:
+                ref_fp.hidden = ref_fp.init_hidden()
             ctx = []
             for t in range(T):
                 pred = gp_ref.predictive(gsd, lsd, gp_ref.latent_to_gp_input(lat[t]), torch.float32, "gpytorch",
@@ -424,13 +658,20 @@ def cpu_rollout(w, T, budget_s, threads):
                 if fired:
                     pc = gp_ref.predictive(gsd, lsd, gp_ref.latent_to_gp_input(lat[t]), torch.float32, "gpytorch")
                     gp_ref.rsample(pc["mean"], pc["covar"], torch.randn(w["G"], B))
+                elif ref_fp is not None:
+                    ref_fp(lat[t])
                 else:
                     _, hid = lstm_ref.lstm_forward(sd, lat[t], hid)
             done += 1
             el = time.perf_counter() - t0
             if el > budget_s or done >= w["S"]:
                 break
-    return {"value": done * B * w["n_future"] / el, "unit": "frames/s", "cores": threads, "kind": "port",
+    if ref_mod is not None:
+        torch.Tensor.cuda = orig_cuda
+    return {"value": done * B * w["n_future"] / el, "unit": "frames/s", "cores": threads,
+            "kind": "port",       # mixed: LSTM stage = the reference's own module when available, GP stage = port (see below)
+            "lstm_stage": ("reference models/lstm.py, unmodified (%s)" % where) if ref_fp is not None else "oracle/lstm_ref.py (%s)" % where,
+            "gp_stage": "oracle/gp_ref.py + oracle/trigger_ref.py (port: the reference's GP arithmetic is gpytorch, absent)",
             "sample": "%d of %d samples (sequential in S like generate_frames.py:143), B=%d, %d time steps, %.1f s"
                       % (done, w["S"], B, T, el)}
 
@@ -456,8 +697,10 @@ def run_reference(args):
             "value": v, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": args.workload, "scope": "hot path only; CPU oracle port, bounded sample per step"},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
+            "config": {"workload": args.workload, "scope": "hot path only; the reference's CPU path (LSTM: its own module "
+                       "where the file is available, GP: oracle port), bounded sample per step"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": vals[-1]["kind"],
+                             "lstm_stage": vals[-1]["lstm_stage"], "gp_stage": vals[-1]["gp_stage"],
                              "sample": vals[-1]["sample"]},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -473,6 +716,7 @@ def main():
     ap.add_argument("--workload", default="kth_s100", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the stock_torch_b200 and pixel_e2e measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
