@@ -353,6 +353,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = shard.bind_to_gpu_numa_node(local) if world > 1 else None     # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     w = WORKLOADS[args.workload]
@@ -361,7 +362,9 @@ def run_ours(args):
     R = S * B
     fp, gp, lik = build_models(w, device, args.variant)
     eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=w["window"], variant=args.variant))
-    lat_h, eps_h = synth_latents(w, T, R, device, seed=100 + rank)
+    # every rank draws the SAME synthetic latents (weak scaling with identical per-GPU work): with rank-dependent draws
+    # the slowest rank's number of fired rollouts, not the kernels, set the multi-GPU time
+    lat_h, eps_h = synth_latents(w, T, R, device, seed=100)
     lat_h, eps_h = lat_h.pin_memory(), eps_h.pin_memory()
     lat, eps = lat_h.to(device), eps_h.to(device)
     out = torch.empty(T, R, w["G"], device=device)
@@ -372,10 +375,19 @@ def run_ours(args):
     target = lat[:, :B].clone()
     held = {}
 
+    # The cross-rank selection (ONE all-gather of the [S, B] score matrix + arg-best) is captured INSIDE the rollout
+    # graph, in stream order after the last step.  Round 1 ran it on a side stream under the next rollout: an NCCL
+    # kernel waiting for a slower peer then held an SM that the persistent step kernel (one CTA per SM, all pairs
+    # co-resident) needs, and the device-timed scaling lost 8 % at 8 GPUs.  In stream it costs one small collective
+    # (~tens of us) per 1.9 ms rollout and never overlaps a step kernel.
+    nccl_in_graph = world > 1 and not os.environ.get("DVG_BENCH_SIDE_STREAM")
+
     def score_in_graph():
         held["sc"] = score_rollouts(out, target, S, B)       # [S_local, B], one fused pass over `out`
         if world == 1:
             held["best"] = shard.select_best(held["sc"], higher_is_better=False)
+        elif nccl_in_graph:
+            held["best"] = shard.select_best(shard.gather_scores(held["sc"], world * S), higher_is_better=False)
 
     graph = eng.capture_latent_rollout(lat, eps, out, masks=masks, post=score_in_graph)
 
@@ -391,7 +403,7 @@ def run_ours(args):
 
     def one_step():
         graph.replay()
-        if world == 1 or os.environ.get("DVG_BENCH_NOSEL"):      # (debug switch: skip the cross-rank selection)
+        if world == 1 or nccl_in_graph or os.environ.get("DVG_BENCH_NOSEL"):   # (NOSEL: debug switch, no selection)
             return held.get("best")
         main = torch.cuda.current_stream()
         snap = held["sc"].clone()                            # ordered after the graph on the compute stream
@@ -449,7 +461,7 @@ def run_ours(args):
         winners = shard.gather_winners(o.view(T, S, B, w["G"]).permute(1, 2, 0, 3), best, world * S)   # [B, T, G]
         return sc, best, winners
 
-    pipe = LatentRolloutPipeline(eng, T, post=e2e_post, full_output=False, capture_post=(world == 1))
+    pipe = LatentRolloutPipeline(eng, T, post=e2e_post, full_output=False, capture_post=(world == 1 or nccl_in_graph))
     # correctness of the pipelined path first (host-injected noise == the device-resident run), untimed
     graph.replay()
     torch.cuda.synchronize()
@@ -518,7 +530,12 @@ def run_ours(args):
                        "row_steps_per_s": world * R * T / (ms_per_step * 1e-3),
                        "variant": args.variant, "cuda_graph": True,
                        "l2": "inputs+outputs per rollout = %.0f MB > 126 MB L2" % ((lat.numel() + out.numel()) * 4 / 1e6),
-                       "triggered_rollout_steps": n_trig, "scope": "hot path only; encoder/decoder convs excluded"},
+                       "triggered_rollout_steps": n_trig, "scope": "hot path only; encoder/decoder convs excluded",
+                       "multi_gpu": None if world == 1 else {
+                           "collective": "one ncclAllGather of the [S,B] score matrix per rollout (+ one all-reduce of the "
+                                         "winners' [B,T,G] decoder inputs in the e2e pipeline), " +
+                                         ("captured in the rollout graph, in stream order" if nccl_in_graph else "side stream"),
+                           "same_inputs_on_every_rank": True, "numa_binding_rank0": numa}},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms2.item() / args.steps, "wall_ms_per_step": wall_ms / args.steps,
                     "how": "LatentRolloutPipeline: pinned host in/out, H2D / compute graph / D2H on three streams, two buffer "
@@ -534,9 +551,15 @@ def run_ours(args):
             "pixel_e2e": pix,
             "hot_path_algorithmic": {"flops_per_row_step": f_row, "bytes_per_row_step": b_row},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL work keep the communicator busy: destroy_process_group() was seen to hang
+        # for minutes with them alive.  Everything is measured and printed: synchronise, meet once more, leave.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def measure_roofline(eng, w, R, lat, args):

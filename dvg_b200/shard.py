@@ -81,3 +81,31 @@ def gather_winners(local_frames: torch.Tensor, best: torch.Tensor, n_rollouts: i
     if world > 1:
         dist.all_reduce(out, group=group)
     return out
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that pinned host buffers allocated
+    afterwards are node-local (first touch) and the launch thread does not cross sockets.  With 8 ranks streaming
+    tens of MB per rollout each, buffers that all sit on one node made the host memory system the limiter of the
+    end-to-end numbers (round 1: e2e scaling 0.68 at 8 GPUs).  Best effort: returns what it did."""
+    import os
+    info = {"local_rank": local_rank}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info.update(pci=bdf, numa_node=node)
+        if node < 0:
+            return info
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = f"{allowed[0]}-{allowed[-1]} ({len(allowed)})"
+    except Exception as e:                                        # noqa: BLE001
+        info["error"] = f"{type(e).__name__}: {e}"[:200]
+    return info
