@@ -231,6 +231,7 @@ class LatentRolloutPipeline:
         dev, R, G, S, D, B = engine.dev, engine.R, engine.G, engine.S, engine.D, engine.B
         self.T, self.full_output = T, full_output
         self.lat = [torch.empty(T, R, G, device=dev) for _ in range(2)]
+        self.lat16 = [None, None]
         self.eps = [torch.empty(T, S, D, B, device=dev) for _ in range(2)]
         self.out = [torch.empty(T, R, G, device=dev) for _ in range(2)]
         self.masks = [torch.zeros(T, S, dtype=torch.uint8, device=dev) for _ in range(2)]
@@ -265,7 +266,15 @@ class LatentRolloutPipeline:
         k = self.n & 1
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_cmp[k])               # the graph that read buffer set k two rollouts ago is done
-            self.lat[k].copy_(lat_host, non_blocking=True)
+            if lat_host.dtype == torch.bfloat16:
+                # half-width transport: bf16 on the wire, expanded to the fp32 the kernels read on the device (exact
+                # when the caller's latents are bf16-representable; the H2D copy is what bounds 8 ranks on one host)
+                if self.lat16[k] is None:
+                    self.lat16[k] = torch.empty(self.lat[k].shape, dtype=torch.bfloat16, device=self.lat[k].device)
+                self.lat16[k].copy_(lat_host, non_blocking=True)
+                self.lat[k].copy_(self.lat16[k])
+            else:
+                self.lat[k].copy_(lat_host, non_blocking=True)
             if eps_host is not None:
                 self.eps[k].copy_(eps_host, non_blocking=True)
             self.ev_in[k].record()
