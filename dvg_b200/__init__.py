@@ -31,4 +31,14 @@ def install_dropin():
     sys.modules["models.lstm"] = lstm
     sys.modules["models.gp_models"] = gp_models
     sys.modules.setdefault("gp_models", gp_models)   # generate_frames.py:14 imports it without the prefix
+    # train.py / generate_frames.py also ``import gpytorch`` (likelihoods.GaussianLikelihood, mlls.VariationalELBO,
+    # settings.*): where the real library is absent a shim with exactly those names takes its place
+    try:
+        import gpytorch  # noqa: F401
+    except ImportError:
+        from .models import gp_train
+        shim = gp_train.gpytorch_shim()
+        sys.modules["gpytorch"] = shim
+        for sub in ("likelihoods", "mlls", "settings"):
+            sys.modules["gpytorch." + sub] = getattr(shim, sub)
     return pkg

@@ -20,8 +20,9 @@ three is read, and each read is a single C-ABI call (``dvg_gp_predict`` / ``dvg_
 eval-mode constants the reference recomputes on every call (K_ZZ, its Cholesky factor, K_ZZ^-1(m-c)) are
 hoisted into ``dvg_gp_prepare`` and refreshed only when a parameter changes.
 
-Eval-mode only; the training-mode branch (diag-only data covariance, KL memo, VariationalELBO) is out
-of scope for the kernels.
+The kernels own the eval-mode predictive.  In ``train()`` mode ``forward`` delegates to ``gp_train.train_forward``
+(plain torch ops with autograd on the GPU: diag-only data covariance, KL memo, VariationalELBO), so the reference's
+training steps (train.py:146-248) run against these classes (minimal form; no backward kernels).
 """
 from __future__ import annotations
 
@@ -50,7 +51,9 @@ class GaussianLikelihood(nn.Module):
     def noise(self):
         return nn.functional.softplus(self.noise_covar.raw_noise) + self.noise_lower_bound
 
-    def forward(self, pred: "GPPrediction") -> "GPPrediction":
+    def forward(self, pred):
+        """``likelihood(gp_layer(x))``: eval -> lazy GPPrediction with the noise folded in; train -> the autograd
+        prediction with ``noise`` added to its variance."""
         return pred.with_likelihood(self)
 
 
@@ -222,7 +225,7 @@ class GPRegressionLayer1(nn.Module):
         self.num_dims, self.num_inducing_points = D, M
         vs = _Holder()
         vs.inducing_points = nn.Parameter(torch.rand(D, M, 1))                       # models/gp_models.py:13
-        vs.register_buffer("variational_params_initialized", torch.tensor(1))
+        vs.register_buffer("variational_params_initialized", torch.tensor(0))    # gpytorch: set on the first call
         vd = _Holder()
         vd.variational_mean = nn.Parameter(torch.zeros(D, M))
         vd.chol_variational_covar = nn.Parameter(torch.eye(M).repeat(D, 1, 1))
@@ -237,10 +240,12 @@ class GPRegressionLayer1(nn.Module):
 
     def __getstate__(self):
         state = dict(self.__dict__)
-        state.pop("_dvg_rts", None)
+        for k in ("_dvg_rts", "_dvg_vinit", "_dvg_kl_memo"):
+            state.pop(k, None)
         return state
 
     def _runtime(self, likelihood) -> _GpRuntime:
+        self._ensure_variational_init()
         rts = self.__dict__.setdefault("_dvg_rts", {})
         key = id(likelihood) if likelihood is not None else 0
         rt = rts.get(key)
@@ -251,8 +256,25 @@ class GPRegressionLayer1(nn.Module):
             rt.refresh(self, likelihood)
         return rt
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.__dict__.pop("_dvg_vinit", None)          # the loaded flag decides again
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _ensure_variational_init(self):
+        """gpytorch's ``VariationalStrategy.__call__`` initialises the variational distribution from the prior on the
+        first call of a layer whose ``variational_params_initialized`` buffer is still 0 (a freshly constructed layer;
+        checkpoints carry 1).  The flag is read from the device once per (construction / load_state_dict)."""
+        if self.__dict__.get("_dvg_vinit"):
+            return
+        vs = self.variational_strategy
+        if int(vs.variational_params_initialized.item()) == 0:
+            from . import gp_train
+            gp_train.initialize_variational_dist(self)
+        self.__dict__["_dvg_vinit"] = True
+
     def forward(self, x):
+        self._ensure_variational_init()
         if self.training:
-            raise NotImplementedError("dvg_b200 implements the eval-mode GP predictive only; call .eval() "
-                                      "(training-mode ELBO is out of scope, SURVEY 8f)")
+            from . import gp_train
+            return gp_train.train_forward(self, x)
         return GPPrediction(self, x)
