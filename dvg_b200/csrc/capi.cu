@@ -433,6 +433,24 @@ int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows, const floa
     if (rc || rs_in_kernel || rs_eps == nullptr || warmup) return rc;
     return dvg_gp_rsample(g, n_rollouts, n_points, x, ldx, rs_eps, mask, y, ldy, stream);
   }
+  if (tc && rows <= h->reserved_rows && window_len >= 1 && window_len <= 128 && ldx >= h->dims.input_size &&
+      ldy >= h->dims.output_size && state_in != state_out && lstm_small_can_fuse_trigger(h, g, rows, n_rollouts)) {
+    // small batches (<= 64 rows): the 16-CTA cluster kernel computes the trigger in its idle window and applies the
+    // decision to its own cell updates; only the (rare) resample of fired rollouts is a second launch
+    const size_t lsz = (size_t)h->dims.n_layers * rows * h->dims.hidden_size;
+    const size_t poff = dvg_lstm_state_packed_offset(h, rows);
+    const float* h_in = (const float*)state_in;
+    float* h_out = (float*)state_out;
+    StepTrigHost t{};
+    t.S = n_rollouts; t.W = window_len; t.warmup = warmup; t.factor = factor; t.stat_rows = stat_rows; t.window = window;
+    t.count = count; t.value = value; t.thr = thr; t.mask = mask;
+    const bool rs_in_kernel = rs_eps != nullptr && !warmup && h->dims.output_size == g->dims.num_dims;
+    t.rs_eps = rs_in_kernel ? rs_eps : nullptr;          // fired rollouts are resampled at the end of the same launch
+    int rc = lstm_small_launch(h, variant == DVG_BF16 ? 1 : 3, rows, x, ldx, h_in, h_in + lsz, (const uint8_t*)state_in + poff,
+                               h_out, h_out + lsz, (uint8_t*)state_out + poff, y, ldy, nullptr, n_points, s, g, &t);
+    if (rc || rs_in_kernel || rs_eps == nullptr || warmup) return rc;
+    return dvg_gp_rsample(g, n_rollouts, n_points, x, ldx, rs_eps, mask, y, ldy, stream);
+  }
   // not fusable (fp32 variant, single row tile, large inducing set, scratch not reserved): separate calls, same semantics
   int rc = dvg_gp_trigger(g, n_rollouts, x, ldx, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,
                           stream);

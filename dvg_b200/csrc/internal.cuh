@@ -123,6 +123,14 @@ struct StepTrigHost {
   float* window; int32_t* count; float* value; float* thr; uint8_t* mask;
   const float* rs_eps;   // non-null: fired rollouts are resampled inside the launch
 };
+// lstm_small.cu: one 16-CTA cluster per step for <= 64 rows (gate columns split over the cluster, DSMEM exchange)
+bool lstm_small_usable(const dvg_lstm_s* h, int rows);
+bool lstm_small_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows, int S);
+int lstm_small_launch(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in, const float* c_in,
+                      const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out, float* y, int ldy,
+                      const uint8_t* hold, int rows_per_flag, cudaStream_t stream, dvg_gp_s* g = nullptr,
+                      const StepTrigHost* trig = nullptr);
+
 bool lstm_step_usable(const dvg_lstm_s* h, int rows);
 size_t lstm_step_flag_words(const dvg_lstm_s* h, int rows);
 size_t lstm_step_xp_bytes(const dvg_lstm_s* h, int rows);

@@ -878,6 +878,9 @@ int lstm_tc_step(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, c
   if (lstm_step_usable(h, rows))
     return lstm_step_launch(h, nullptr, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, eps, z,
                             mu, logvar, hold, rows_per_flag, stream, nullptr);
+  if (lstm_small_usable(h, rows))
+    return lstm_small_launch(h, nsplit, rows, x, ldx, h_in, c_in, hp_in, h_out, c_out, hp_out, y, ldy, hold, rows_per_flag,
+                             stream);
   h->prof_mark(stream);
   tc_pack_rows_kernel<<<dim3(RT, kbx), 256, 0, stream>>>(h->tc_xp, x, ldx, rows, G, kbx);
   DVG_LAUNCH_CHECK();

@@ -144,6 +144,29 @@ def test_kth_shaped_trigger_rollout_vs_oracle():
     assert checked > 100 and fired >= 1, (checked, fired, sorted(jumps), masks.cpu().nonzero().tolist())
 
 
+@pytest.mark.parametrize("B,S", [(16, 1), (30, 2), (64, 1), (5, 1)])
+def test_small_batch_trigger_rollout_vs_oracle(B, S):
+    """<= 64 rows (BASELINE configs[0]: batch 16, one rollout; configs[3]: batch 64): the 16-CTA cluster kernel with the
+    trigger fused (lstm_small.cu), crafted fires, against the sequential oracle."""
+    from dvg_b200.rollout import RolloutConfig, RolloutEngine
+    from util import check_latent_rollout, crafted_trigger_case
+    T, W = 26, 6
+    sd = lstm_ref.random_lstm_state_dict(G, G, H, L, seed=26)
+    gp_sd, lik_sd, lat, eps, jumps = crafted_trigger_case(G, M, B, S, T, W, seed=7, n_jumps=3)
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=W, variant="bf16x3", stat_col=min(3, B - 1)))
+    out = torch.empty(T, S * B, G, device="cuda")
+    masks = torch.zeros(T, S, dtype=torch.uint8, device="cuda")
+    values = torch.zeros(T, S, device="cuda")
+    with torch.no_grad():
+        eng.latent_rollout(lat.cuda(), eps.cuda(), out, masks=masks, values=values)
+    torch.cuda.synchronize()
+    checked, fired = check_latent_rollout(sd, gp_sd, lik_sd, lat, eps, out.cpu(), masks.cpu(), values.cpu(), B, W,
+                                          stat_col=min(3, B - 1))
+    assert checked >= 10 and fired >= 1, (checked, fired, sorted(jumps), masks.cpu().nonzero().tolist())
+
+
 def test_cuda_graph_latent_rollout_equals_eager():
     from dvg_b200.rollout import RolloutConfig, RolloutEngine
     from util import crafted_trigger_case
