@@ -41,6 +41,7 @@ struct dvg_lstm_s {
   // --- tensor-core packed weights -----------------------------------------------------------------
   dvg::TcGemmPlan tc_embed, tc_layer[dvg::MAX_LAYERS], tc_head;
   dvg::TcGemmPlan tc_layer0f;    // layer 0 with the embed Linear folded in (fused step kernel)
+  uint8_t* small_w[2] = {nullptr, nullptr};   // lstm_small.cu: per-(32-unit tile, k-block) contiguous 128-row A images of layers 0 / 1
   float* fold_wx = nullptr;      // [4H][G]  W_ih0 W_e
   float* fold_bx = nullptr;      // [4H]     W_ih0 b_e + b_ih0 + b_hh0
   int* fused_flags = nullptr;    // dependency counters of the persistent step kernel (lstm_step.cu), self-resetting
@@ -125,6 +126,8 @@ struct StepTrigHost {
 };
 // lstm_small.cu: one 16-CTA cluster per step for <= 64 rows (gate columns split over the cluster, DSMEM exchange)
 bool lstm_small_usable(const dvg_lstm_s* h, int rows);
+int lstm_small_pack(dvg_lstm_s* h, cudaStream_t stream);
+void lstm_small_free(dvg_lstm_s* h);
 bool lstm_small_can_fuse_trigger(const dvg_lstm_s* h, const dvg_gp_s* g, int rows, int S);
 int lstm_small_launch(dvg_lstm_s* h, int nsplit, int rows, const float* x, int ldx, const float* h_in, const float* c_in,
                       const uint8_t* hp_in, float* h_out, float* c_out, uint8_t* hp_out, float* y, int ldy,

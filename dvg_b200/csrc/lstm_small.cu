@@ -36,12 +36,13 @@ constexpr int SM_MAX_STAGES = 6;
 constexpr int SM_H = 256, SM_HK = 4;
 
 struct SmallArgs {
-  int rows, N, G, ldx, ldy, n_valid, nparts, rows_per_flag, kbx, x_ksteps, stages, head_rows;
+  int rows, N, G, ldx, ldy, n_valid, nparts, rows_per_flag, kbx, x_ksteps, stages, head_rows, debug_stop;
   const float* x; const float* h_in; const float* c_in; float* h_out; float* c_out;
   const uint8_t* hp_in; uint8_t* hp_out;          // packed state images [L][1][4][2][16 KB]
   const uint8_t* w[2]; const uint8_t* wh;         // packed weights: layer 0 (embed folded), layer 1, head
   const float* b[2]; const float* bh;
   float* y; const uint8_t* hold;
+  unsigned long long* trace;      // developer timeline (DVG_SMALL_TRACE=1): [16 CTAs][32 slots] of %globaltimer
   // fused GP variance trigger (generate_frames.py:227-232,275,283-289); enabled = 0: plain LSTM step
   struct {
     int enabled, S, D, W, warmup;
@@ -84,6 +85,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     }
   }
 }
+
+#define STRACE(slot)                                                                       \
+  do {                                                                                     \
+    if (p.trace) {                                                                         \
+      unsigned long long _t;                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)::"memory");                     \
+      p.trace[(size_t)blockIdx.x * 32 + (slot)] = _t;                                      \
+    }                                                                                      \
+  } while (0)
 
 __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_constant__ SmallArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -131,7 +141,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 128);
+    ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
   // this tile's gate biases, pre-scaled for lstm_cell_fast (-log2e for i, f, o; -2 log2e for g); head bias for tanh
@@ -148,10 +158,18 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   ptx::griddep_launch_dependents();
+  if (threadIdx.x == 0) STRACE(0);
   ptx::griddep_wait();                     // the previous step (same stream) wrote our state
+  if (threadIdx.x == 0) STRACE(1);
 
   const bool is_head = c == 0;
   const int n_kb_lstm = layer == 0 ? SM_HK + p.kbx : 2 * SM_HK;
+  if (p.debug_stop == 1) {                 // developer timing switch (results invalid): launch + set-up + teardown only
+    __syncthreads();
+    ptx::cluster_sync_all();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+    return;
+  }
 
   if (warp == 0) {
     // ===================== producer: own activation images, then this CTA's weight k-blocks =====================
@@ -172,15 +190,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
         ptx::mbar_wait(empty_bar(s), phs ^ 1u);
         const uint32_t dst = base + (uint32_t)s * SM_STAGE;
         if (i < KB) {
-          // weight K order [input | recurrent]; recurrent k-blocks are consumed first.  The 128 rows of this tile are four
-          // 32-row chunks (one per gate) of the 256-row packed image of N tile (tile >> 1): rows g*64 + 32*(tile&1) ..
+          // weight K order [input | recurrent]; recurrent k-blocks are consumed first
           const int wk = i < SM_HK ? kb_in + i : i - SM_HK;
+          // (the tile's 128 gate rows are stored contiguously per (tile, k-block): [hi image | lo image], one bulk copy --
+          //  gathering them as eight 4 KB chunks of the large-batch weight images cost ~0.6 us of issue time per k-block)
           ptx::mbar_expect_tx(full_bar(s), nparts * (uint32_t)TC_A_IMG);
-          const uint8_t* src = wl + (size_t)((tile >> 1) * KB + wk) * (2u * 256u * 128u);
-          for (uint32_t part = 0; part < nparts; ++part)
-            for (int g = 0; g < 4; ++g)
-              ptx::bulk_g2s_hint(dst + part * TC_A_IMG + g * 4096, src + (size_t)part * (256u * 128u) + (size_t)(g * 64 + (tile & 1) * 32) * 128u,
-                                 4096, full_bar(s), pol_keep);
+          ptx::bulk_g2s_hint(dst, wl + (size_t)(tile * KB + wk) * SM_STAGE, nparts * (uint32_t)TC_A_IMG, full_bar(s), pol_keep);
         } else {
           const int kb = i - KB;
           const uint32_t hb = (uint32_t)p.head_rows * 128u;
@@ -194,7 +209,11 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, N);
+      // bf16x3 as TWO MMAs per k-step: the hi and lo images of a B operand are adjacent in shared memory, so
+      //   A_hi x [X_hi ; X_lo]  (one MMA, N' = 2N: columns [0,N) get hi*hi, [N,2N) hi*lo)  +  A_lo x X_hi  (columns [2N,3N))
+      // give all three split products; the epilogue adds the three column groups.  At these sizes an MMA costs ~80 cycles
+      // whatever its N, so dropping one of three shortens every GEMM phase of the step's dependency chain by a third.
+      const uint32_t idesc = ptx::make_idesc_bf16(128, N), idesc2 = ptx::make_idesc_bf16(128, 2 * N);
       int s = 0;
       uint32_t phs = 0;
       auto kblock = [&](uint32_t d_tmem, int slot, int ks, uint32_t& accum) {
@@ -202,24 +221,30 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
         ptx::tc_fence_after();
         const uint32_t sa = base + (uint32_t)s * SM_STAGE;
         const uint64_t a_hi = ptx::make_sw128_desc(sa), a_lo = ptx::make_sw128_desc(sa + TC_A_IMG);
-        const uint64_t b_hi = ptx::make_sw128_desc(act(slot, 0)), b_lo = ptx::make_sw128_desc(act(slot, 1));
+        const uint64_t b_hi = ptx::make_sw128_desc(act(slot, 0));
         for (int kk = 0; kk < ks; ++kk) {
           const uint64_t adv = (uint64_t)(kk * 2);
-          ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
-          accum = 1u;
           if (nparts == 2) {
-            ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-            ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            // (separate accumulators: interleaving two instruction shapes on ONE accumulator serialised them at ~140
+            //  cycles each; two independent accumulate chains pipeline)
+            ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc2, accum);              // B = [hi ; lo], 2N rows -> cols [0, 2N)
+            ptx::umma_bf16(d_tmem + 2 * N, a_lo + adv, b_hi + adv, idesc, accum);       // lo * hi -> cols [2N, 3N)
+          } else {
+            ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, accum);
           }
+          accum = 1u;
         }
         ptx::umma_commit(empty_bar(s));
         if (++s == p.stages) { s = 0; phs ^= 1u; }
       };
       uint32_t accum = 0;
       ptx::mbar_wait(bar_act, 0);
-      for (int kb = 0; kb < SM_HK; ++kb) kblock(tmem_base, kb, 4, accum);        // recurrent half (previous step's h_l)
+      STRACE(2);
+      for (int kb = 0; kb < SM_HK; ++kb) { kblock(tmem_base, kb, 4, accum); if (kb == 0) STRACE(3); }   // recurrent half (previous step's h_l)
+      STRACE(4);
       if (layer == 0) {
         ptx::mbar_wait(bar_x, 0);
+        STRACE(5);
         ptx::fence_proxy_async();
         for (int kb = 0; kb < p.kbx; ++kb) {
           const int left = p.x_ksteps - 4 * kb;
@@ -227,16 +252,20 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
         }
       } else {
         mbar_wait_cluster(bar_in, 0);                                             // h'_0 from the eight layer-0 CTAs
+        STRACE(5);
         ptx::fence_proxy_async();
         for (int kb = 0; kb < SM_HK; ++kb) kblock(tmem_base, SM_HK + kb, 4, accum);
       }
       ptx::umma_commit(bar_acc);
+      STRACE(6);
       if (is_head) {
         mbar_wait_cluster(bar_in, 0);                                             // h'_1 from the eight layer-1 CTAs
+        STRACE(7);
         ptx::fence_proxy_async();
         accum = 0;
-        for (int kb = 0; kb < SM_HK; ++kb) kblock(tmem_base + 64, kb, 4, accum);
+        for (int kb = 0; kb < SM_HK; ++kb) kblock(tmem_base + 256, kb, 4, accum);
         ptx::umma_commit(bar_acc2);
+        STRACE(8);
       }
     }
   } else if (warp == 6) {
@@ -296,6 +325,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_x);
+      if (et == 0) STRACE(10);
     }
     // c of the previous step for this thread's cells: unit = et & 31, rows (et >> 5) + 4 j
     const int u = et & 31;
@@ -361,7 +391,9 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
       // (nobody waits for the decision here: the LSTM advances every rollout and the few that fired are restored from
       //  the input state at the end of the launch -- waiting cost the decision steps ~9 us on the critical path)
     }
+    if (et == 0) STRACE(11);
     ptx::mbar_wait(bar_acc, 0);
+    if (et == 0) STRACE(12);
     ptx::tc_fence_after();
 #pragma unroll
     for (int rc = 0; rc < 4; ++rc) {
@@ -369,6 +401,13 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
       if (r0 >= N) break;
       float v[16];
       ptx::tmem_ld16_wait(tmem_base + tlane + (uint32_t)r0, v);       // gate q, unit = lane, batch rows r0 .. r0+15
+      if (nparts == 2) {                                              // + the hi*lo and lo*hi column groups
+        float v2[16], v3[16];
+        ptx::tmem_ld16_wait(tmem_base + tlane + (uint32_t)(N + r0), v2);
+        ptx::tmem_ld16_wait(tmem_base + tlane + (uint32_t)(2 * N + r0), v3);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += v2[j] + v3[j];
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) s_gate[(q * 16 + j) * 32 + lane] = v[j];
       ptx::named_bar_sync(1, 128);
@@ -397,6 +436,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
       }
       ptx::named_bar_sync(1, 128);
     }
+    if (et == 0) STRACE(13);
     ptx::tc_fence_before();
     // distribute this tile's h' (N rows x 32 units, bf16 hi / lo): 16-byte chunks into the B-operand images of the
     // consumers (layer 0 -> the eight layer-1 CTAs, slots 4..7; layer 1 -> the head CTA, slots 0..3) through
@@ -417,8 +457,14 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
       }
       ptx::fence_proxy_async_all();
       __syncwarp();
-      if (lane == 0)
-        for (int q2 = 0; q2 < n_cons; ++q2) mbar_arrive_remote_addr(mapa(bar_in, layer == 0 ? 8u + q2 : 0u));
+      if (lane == 0) {
+        // one release fence for the warp's remote stores, then relaxed arrives (a release-arrive per consumer waits for
+        // the stores to be performed each time: the eight arrives took ~2 us and reached the consumers 0.3 us apart)
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        for (int q2 = 0; q2 < n_cons; ++q2)
+          asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa(bar_in, layer == 0 ? 8u + q2 : 0u)) : "memory");
+      }
+      if (et == 0) STRACE(14);
     }
     const bool rs_fused = p.trig.enabled && !p.trig.warmup && p.trig.rs_eps != nullptr;
     const bool decide = p.trig.enabled && !p.trig.warmup;
@@ -448,11 +494,19 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
     if (is_head) {
       // y^T [head rows x N] = tanh(W_o h'_1 + b_o): lane = output column, TMEM column = batch row
       ptx::mbar_wait(bar_acc2, 0);
+      if (et == 0) STRACE(15);
       ptx::tc_fence_after();
       const int jcol = q * 32 + lane;
       for (int r0 = 0; r0 < N; r0 += 16) {
         float v[16];
-        ptx::tmem_ld16_wait(tmem_base + 64 + tlane + (uint32_t)r0, v);
+        ptx::tmem_ld16_wait(tmem_base + 256 + tlane + (uint32_t)r0, v);
+        if (nparts == 2) {
+          float v2[16], v3[16];
+          ptx::tmem_ld16_wait(tmem_base + 256 + tlane + (uint32_t)(N + r0), v2);
+          ptx::tmem_ld16_wait(tmem_base + 256 + tlane + (uint32_t)(2 * N + r0), v3);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += v2[j] + v3[j];
+        }
         if (jcol < p.n_valid) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -481,18 +535,52 @@ __global__ void __launch_bounds__(SM_THREADS, 1) lstm_small_kernel(const __grid_
     }
   }
   // ---- teardown: nobody leaves while a peer may still store into its shared memory or arrive on its barriers ----
+  if (threadIdx.x == 64) STRACE(16);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync_all();
+  if (threadIdx.x == 64) STRACE(17);
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 128);
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Weight images of the small-batch kernel: [tile 0..7][k-block][hi | lo][128 rows x 128 B], the 128 rows being the four
+// 32-row chunks (one per gate) of units 32 tile .. 32 tile + 31 taken from the 256-row image of N tile (tile >> 1) of the
+// large-batch packing (rows g*64 + 32 (tile & 1) ..; multiples of 8 rows, so the 128-byte swizzle pattern is unchanged).
+__global__ void small_repack_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int KB) {
+  const int tile = blockIdx.x, wk = blockIdx.y;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)((tile >> 1) * KB + wk) * (2u * 256u * 128u));
+  uint4* d4 = reinterpret_cast<uint4*>(dst + (size_t)(tile * KB + wk) * SM_STAGE);
+  for (int i = threadIdx.x; i < SM_STAGE / 16; i += blockDim.x) {
+    const int part = i / (TC_A_IMG / 16), rem = i % (TC_A_IMG / 16);
+    const int row = rem >> 3, ch = rem & 7;                 // 128-byte rows of 8 chunks
+    const int g = row >> 5, r32 = row & 31;
+    d4[i] = s4[(size_t)part * (256 * 8) + (size_t)(g * 64 + (tile & 1) * 32 + r32) * 8 + ch];
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------
+int lstm_small_pack(dvg_lstm_s* h, cudaStream_t stream) {
+  if (!h->tc_ok || h->dims.hidden_size != SM_H || h->dims.n_layers != 2 || h->dims.kind != DVG_LSTM) return DVG_OK;
+  const TcGemmPlan* pl[2] = {&h->tc_layer0f, &h->tc_layer[1]};
+  for (int l = 0; l < 2; ++l) {
+    const int KB = pl[l]->kb0 + pl[l]->kb1;
+    if (!h->small_w[l]) DVG_CUDA(cudaMalloc(&h->small_w[l], (size_t)8 * KB * SM_STAGE));
+    small_repack_kernel<<<dim3(8, KB), 256, 0, stream>>>(pl[l]->w, h->small_w[l], KB);
+    DVG_LAUNCH_CHECK();
+  }
+  return DVG_OK;
+}
+void lstm_small_free(dvg_lstm_s* h) {
+  for (int l = 0; l < 2; ++l) {
+    if (h->small_w[l]) cudaFree(h->small_w[l]);
+    h->small_w[l] = nullptr;
+  }
+}
 static size_t small_smem_bytes(int N, int stages) {
   return (size_t)stages * SM_STAGE + (size_t)16 * N * 128 + 8192 + (size_t)128 * N + 2 * 128 * sizeof(float) + 256 + 64;
 }
@@ -503,7 +591,7 @@ bool lstm_small_usable(const dvg_lstm_s* h, int rows) {
     const char* e = getenv("DVG_TC_SMALL");          // developer switch: 0 = one launch per GEMM for small batches
     off = (e && e[0] == '0') ? 1 : 0;
   }
-  if (off || !h->tc_ok || h->dims.kind != DVG_LSTM) return false;
+  if (off || !h->tc_ok || h->dims.kind != DVG_LSTM || h->small_w[0] == nullptr) return false;
   if (h->dims.hidden_size != SM_H || h->dims.n_layers != 2) return false;
   if (h->dims.input_size > 128 || h->tc_head.n_tile > 128 || h->sm_count < SM_CL) return false;
   return rows >= 1 && rows <= 64;
@@ -534,9 +622,10 @@ int lstm_small_launch(dvg_lstm_s* h, int nsplit, int rows, const float* x, int l
   a.n_valid = h->dims.output_size; a.nparts = nsplit == 1 ? 1 : 2; a.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
   a.kbx = ceil_div(a.G, 64); a.x_ksteps = ceil_div(a.G, 16); a.head_rows = h->tc_head.n_tile;
   a.x = x; a.h_in = h_in; a.c_in = c_in; a.h_out = h_out; a.c_out = c_out; a.hp_in = hp_in; a.hp_out = hp_out;
-  a.w[0] = h->tc_layer0f.w; a.w[1] = h->tc_layer[1].w; a.wh = h->tc_head.w;
+  a.w[0] = h->small_w[0]; a.w[1] = h->small_w[1]; a.wh = h->tc_head.w;
   a.b[0] = h->tc_layer0f.bias; a.b[1] = h->tc_layer[1].bias; a.bh = h->tc_head.bias;
   a.y = y; a.hold = hold;
+  { const char* e = getenv("DVG_SMALL_STOP"); a.debug_stop = e ? atoi(e) : 0; }
   int stages = SM_MAX_STAGES;
   while (stages > 2 && small_smem_bytes(a.N, stages) > 227 * 1024) --stages;
   a.stages = stages;
@@ -562,9 +651,32 @@ int lstm_small_launch(dvg_lstm_s* h, int nsplit, int rows, const float* x, int l
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 2;
+  static unsigned long long* tbuf = nullptr;
+  static int n_launch = 0;
+  const bool tr = getenv("DVG_SMALL_TRACE") != nullptr;
+  if (tr) {
+    if (!tbuf) cudaMalloc(&tbuf, 16 * 32 * 8);
+    cudaMemsetAsync(tbuf, 0, 16 * 32 * 8, stream);
+    a.trace = tbuf;
+  }
   h->prof_mark(stream);
   DVG_CUDA(cudaLaunchKernelEx(&cfg, lstm_small_kernel, (const SmallArgs)a));
   h->prof_mark(stream);
+  if (tr) {
+    cudaStreamSynchronize(stream);
+    if (n_launch++ == 6) {
+      unsigned long long hb[16 * 32];
+      cudaMemcpy(hb, tbuf, sizeof(hb), cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull;
+      for (int b = 0; b < 16; ++b) if (hb[b * 32] && hb[b * 32] < t0) t0 = hb[b * 32];
+      fprintf(stderr, "SMALL TRACE (ns): cta: 0 start 1 depwait | mma: 2 act 3 kb0 4 rec-done 5 in-ready 6 issued 7 head-in 8 head-issued | epi: 10 xpack 11 pre-acc 12 acc 13 cells 14 sent 15 head-acc 16 done 17 exit\n");
+      for (int b = 0; b < 16; ++b) {
+        fprintf(stderr, "cta %2d:", b);
+        for (int i = 0; i < 18; ++i) fprintf(stderr, " %lld", hb[b * 32 + i] ? (long long)(hb[b * 32 + i] - t0) : -1ll);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return DVG_OK;
 }
 

@@ -733,7 +733,7 @@ int lstm_tc_pack(dvg_lstm_s* h, const float* embed_w, const float* embed_b, cons
   } else {
     if ((rc = plan_pack(h->tc_head, head0_w, H, nullptr, 0, head0_b, nullptr, n_head, 0, H, stream))) return rc;
   }
-  return DVG_OK;
+  return lstm_small_pack(h, stream);       // weight images of the small-batch cluster kernel (lstm_small.cu)
 }
 
 void lstm_tc_free(dvg_lstm_s* h) {
@@ -742,6 +742,7 @@ void lstm_tc_free(dvg_lstm_s* h) {
     if (p.bias) cudaFree(p.bias);
     p.w = nullptr; p.bias = nullptr;
   };
+  lstm_small_free(h);
   fr(h->tc_embed);
   fr(h->tc_head);
   fr(h->tc_layer0f);
