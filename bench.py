@@ -52,8 +52,8 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-# capture (profiles/r01_lstm_step.md); keyed by (workload, variant).
-NCU_TRAFFIC_BYTES = {("kth_s100", "bf16x3"): 33.2e6}
+# capture (profiles/r02_lstm_step.md, profiles/r02_lstm_step_ncu_raw.csv); keyed by (workload, variant).
+NCU_TRAFFIC_BYTES = {("kth_s100", "bf16x3"): 34.0e6}
 
 
 def peaks():
@@ -630,7 +630,7 @@ def measure_roofline(eng, w, R, lat, args):
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % how,
             "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant)),
-            "traffic_source": "profiles/r01_lstm_step.md (ncu --set full, dram read+write bytes per launch)",
+            "traffic_source": "profiles/r02_lstm_step.md (ncu --set full, dram read+write bytes per launch)",
             "algorithmic_bytes_per_launch": b_row * R,
             "tensor_issue_frac": achieved * issued / peak,
             "hbm_frac_of_state_io": (b_row * R / (step_ms * 1e-3) / 1e9) / hbm,
