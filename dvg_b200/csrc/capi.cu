@@ -238,6 +238,8 @@ static void gp_free_all(dvg_gp_s* h) {
   auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
   fr(h->z); fr(h->linv); fr(h->lqt); fr(h->alpha); fr(h->hyp); fr(h->work); fr(h->var_rows);
   fr(h->ticket); fr(h->trig_list); fr(h->trig_count); fr(h->linvT); fr(h->lq); fr(h->partial);
+  for (void* q : h->retired) cudaFree(q);
+  h->retired.clear();
 }
 
 int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* var_mean,
@@ -389,8 +391,7 @@ int dvg_gp_rsample(dvg_gp_t h, int n_rollouts, int n_points, const float* x, int
   DVG_REQUIRE(n_points <= 128, "rsample correlates at most 128 points per call (got %d): the [N,N] covariance is factorised "
               "in shared memory", n_points);
   DVG_REQUIRE(ldx >= h->dims.num_dims && ldo >= h->dims.num_dims, "bad leading dimension");
-  DVG_REQUIRE(!h->big, "rsample with a large inducing set (pre-computed factors, M=%d) is not implemented yet",
-              h->dims.num_inducing);
+  if (h->big) return gp_big_rsample_launch(h, n_rollouts, n_points, x, ldx, eps, mask, out, ldo, (cudaStream_t)stream);
   return gp_rsample_launch(h, n_rollouts, n_points, x, ldx, eps, mask, out, ldo, (cudaStream_t)stream);
 }
 

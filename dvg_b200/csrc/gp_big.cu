@@ -211,7 +211,7 @@ static int gp_big_reserve_partial(dvg_gp_s* h, size_t floats, cudaStream_t strea
   cudaStreamIsCapturing(stream, &st);
   DVG_REQUIRE(st == cudaStreamCaptureStatusNone, "GP scratch must be grown before stream capture (call once eagerly)");
   DVG_CUDA(cudaDeviceSynchronize());
-  if (h->partial) cudaFree(h->partial);
+  if (h->partial) h->retired.push_back(h->partial);     // CUDA graphs captured earlier may still reference it
   h->partial = nullptr; h->partial_cap = 0;
   DVG_CUDA(cudaMalloc(&h->partial, sizeof(float) * floats));
   h->partial_cap = floats;
@@ -249,6 +249,208 @@ int gp_big_predict_launch(dvg_gp_s* h, int n_rows, const float* x, int ldx, cons
                                                    var ? var + (size_t)c0 * var_sn : nullptr, var_sn, var_sd);
     DVG_LAUNCH_CHECK();
   }
+  return DVG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// .rsample() for large inducing sets (generate_frames.py:171,292 at BASELINE configs[4] sizes): one CTA per
+// (rollout, latent dim), masked rollouts only.  The [N,N] predictive covariance of the rollout's N <= 128 points
+//   Sigma_y = K_xx + noise I + sum_jb ( W_jb^T W_jb - V_jb^T V_jb ),   V = Linv K_zx,  W = L_q^T K_zx  (row blocks jb of 64)
+// is accumulated row block by row block: the 64 x N tiles of V and W are produced exactly like gp_big_partial_kernel
+// does (K tile rebuilt on the fly, only the non-zero triangular m tiles visited), parked in shared memory, and folded
+// into register-resident 4 x 4 blocks of the lower triangle of the Gram difference; mean = c + V^T beta on the way.
+// Then an in-place Cholesky in shared memory and  out = mean + L eps.  Everything in a fixed order: deterministic.
+// Work per CTA: M^2 N FMAs (M = 4096, N = 50: 0.84 G) -- a rare event (fired rollouts only), D CTAs per fired rollout.
+// ---------------------------------------------------------------------------------------------------
+constexpr int GR_NMAX = 128;
+constexpr int GR_LDV = 132;      // row stride of the parked V / W tiles and of Sigma (floats)
+
+__global__ void __launch_bounds__(256) gp_big_rsample_kernel(int S, int N, int D, int Mp, const float* __restrict__ x, int ldx,
+                                                             const float* __restrict__ eps, const uint8_t* __restrict__ mask,
+                                                             const float* __restrict__ zall, const float* __restrict__ linv_all,
+                                                             const float* __restrict__ lqt_all, const float* __restrict__ beta_all,
+                                                             const float* __restrict__ hyp, float* __restrict__ out, int ldo) {
+  const int sidx = blockIdx.x, d = blockIdx.y;
+  if (mask != nullptr && mask[sidx] == 0) return;
+  extern __shared__ __align__(16) float smf[];
+  float* Ks = smf;                           // [64 m][GB_LD]
+  float* Lt = Ks + GB_T * GB_LD;             // [64 m][GB_LD]  Linv tile transposed
+  float* Qt = Lt + GB_T * GB_LD;             // [64 m][GB_LD]  L_q^T tile transposed
+  float* Vs = Qt + GB_T * GB_LD;             // [64 j][GR_LDV] V row block, all N points
+  float* Ws = Vs + GB_T * GR_LDV;            // [64 j][GR_LDV]
+  float* Sg = Ws + GB_T * GR_LDV;            // [GR_NMAX][GR_LDV] Sigma_y (lower triangle) / Cholesky factor
+  float* xs = Sg + GR_NMAX * GR_LDV;         // [GR_NMAX] the rollout's latents of this dim
+  float* mn = xs + GR_NMAX;                  // [GR_NMAX] predictive mean
+  float* bt = mn + GR_NMAX;                  // [64] beta of the current row block
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int MT = Mp / GB_T, NT = (N + GB_T - 1) / GB_T;
+  const float ell = hyp[d * 4 + 0], sc = hyp[d * 4 + 1], cst = hyp[d * 4 + 2], noise = hyp[d * 4 + 3];
+  const float inv_ell = 1.0f / ell;
+  const float* linv = linv_all + (size_t)d * Mp * Mp;
+  const float* lqt = lqt_all + (size_t)d * Mp * Mp;
+  const float* z = zall + (size_t)d * Mp;
+  if (tid < GR_NMAX) {
+    xs[tid] = tid < N ? __ldg(x + (size_t)(sidx * N + tid) * ldx + d) : 0.f;
+    mn[tid] = 0.f;
+  }
+  // this thread's 4 x 4 blocks of the lower triangle of G = sum_jb (W^T W - V^T V): block (bi, bj), bj <= bi, NB = ceil(N/4)
+  const int NB = (N + 3) / 4;
+  const int n_blocks = NB * (NB + 1) / 2;
+  constexpr int MAXB = 3;                    // 528 blocks at N = 128 over 256 threads
+  float g[MAXB][4][4];
+  int gbi[MAXB], gbj[MAXB];
+#pragma unroll
+  for (int q = 0; q < MAXB; ++q) {
+    const int b = tid + q * 256;
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+    gbi[q] = bi; gbj[q] = b - bi * (bi + 1) / 2;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) g[q][a][c2] = 0.f;
+  }
+  __syncthreads();
+  for (int jb = 0; jb < MT; ++jb) {
+    const int j0 = jb * GB_T;
+    if (tid < GB_T) bt[tid] = __ldg(beta_all + (size_t)d * Mp + j0 + tid);
+    for (int nt = 0; nt < NT; ++nt) {
+      float accV[4][4], accW[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { accV[a][b] = 0.f; accW[a][b] = 0.f; }
+      for (int mt = 0; mt < MT; ++mt) {
+        const int m0 = mt * GB_T;
+        const bool doV = mt <= jb, doW = mt >= jb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = tid + i * 256;
+          const int jj = e >> 4, m4 = (e & 15) * 4;
+          if (doV) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(linv + (size_t)(j0 + jj) * Mp + m0 + m4));
+            Lt[(m4 + 0) * GB_LD + jj] = v.x; Lt[(m4 + 1) * GB_LD + jj] = v.y;
+            Lt[(m4 + 2) * GB_LD + jj] = v.z; Lt[(m4 + 3) * GB_LD + jj] = v.w;
+          }
+          if (doW) {
+            const float4 q4 = __ldg(reinterpret_cast<const float4*>(lqt + (size_t)(j0 + jj) * Mp + m0 + m4));
+            Qt[(m4 + 0) * GB_LD + jj] = q4.x; Qt[(m4 + 1) * GB_LD + jj] = q4.y;
+            Qt[(m4 + 2) * GB_LD + jj] = q4.z; Qt[(m4 + 3) * GB_LD + jj] = q4.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int e = tid + i * 256;
+          const int mm = e >> 6, n = e & 63;
+          const float t = (xs[nt * GB_T + n] - __ldg(z + m0 + mm)) * inv_ell;
+          Ks[mm * GB_LD + n] = sc * expf(-0.5f * t * t);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < GB_T; ++kk) {
+          const float4 b4 = *reinterpret_cast<const float4*>(Ks + kk * GB_LD + tx * 4);
+          const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+          if (doV) {
+            const float4 a4 = *reinterpret_cast<const float4*>(Lt + kk * GB_LD + ty * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) accV[a][b] = fmaf(av[a], bv[b], accV[a][b]);
+          }
+          if (doW) {
+            const float4 q4 = *reinterpret_cast<const float4*>(Qt + kk * GB_LD + ty * 4);
+            const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) accW[a][b] = fmaf(qv[a], bv[b], accW[a][b]);
+          }
+        }
+        __syncthreads();
+      }
+      // park the 64 x 64 tiles: rows ty*4 + a, points nt*64 + tx*4 + b
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        *reinterpret_cast<float4*>(Vs + (ty * 4 + a) * GR_LDV + nt * GB_T + tx * 4) = make_float4(accV[a][0], accV[a][1], accV[a][2], accV[a][3]);
+        *reinterpret_cast<float4*>(Ws + (ty * 4 + a) * GR_LDV + nt * GB_T + tx * 4) = make_float4(accW[a][0], accW[a][1], accW[a][2], accW[a][3]);
+      }
+    }
+    __syncthreads();
+    // mean += V_jb^T beta_jb  (rows in order: deterministic)
+    if (tid < N) {
+      float m = mn[tid];
+      for (int r = 0; r < GB_T; ++r) m = fmaf(Vs[r * GR_LDV + tid], bt[r], m);
+      mn[tid] = m;
+    }
+    // G += W^T W - V^T V on this thread's blocks
+#pragma unroll
+    for (int q = 0; q < MAXB; ++q) {
+      if (tid + q * 256 >= n_blocks) continue;
+      const int i0 = gbi[q] * 4, c0 = gbj[q] * 4;
+      for (int r = 0; r < GB_T; ++r) {
+        const float4 vi = *reinterpret_cast<const float4*>(Vs + r * GR_LDV + i0), vj = *reinterpret_cast<const float4*>(Vs + r * GR_LDV + c0);
+        const float4 wi = *reinterpret_cast<const float4*>(Ws + r * GR_LDV + i0), wj = *reinterpret_cast<const float4*>(Ws + r * GR_LDV + c0);
+        const float via[4] = {vi.x, vi.y, vi.z, vi.w}, vja[4] = {vj.x, vj.y, vj.z, vj.w};
+        const float wia[4] = {wi.x, wi.y, wi.z, wi.w}, wja[4] = {wj.x, wj.y, wj.z, wj.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c2 = 0; c2 < 4; ++c2) g[q][a][c2] = fmaf(wia[a], wja[c2], fmaf(-via[a], vja[c2], g[q][a][c2]));
+      }
+    }
+    __syncthreads();
+  }
+  // Sigma_y (lower triangle) = K_xx + noise I + G
+#pragma unroll
+  for (int q = 0; q < MAXB; ++q) {
+    if (tid + q * 256 >= n_blocks) continue;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) {
+        const int i = gbi[q] * 4 + a, j = gbj[q] * 4 + c2;
+        if (i < N && j <= i) {
+          const float t = (xs[i] - xs[j]) * inv_ell;
+          Sg[i * GR_LDV + j] = (i == j ? sc + noise : sc * expf(-0.5f * t * t)) + g[q][a][c2];
+        }
+      }
+  }
+  __syncthreads();
+  // right-looking Cholesky, column by column (N <= 128)
+  for (int k = 0; k < N; ++k) {
+    if (tid == 0) Sg[k * GR_LDV + k] = sqrtf(Sg[k * GR_LDV + k]);
+    __syncthreads();
+    const float inv = 1.0f / Sg[k * GR_LDV + k];
+    for (int i = k + 1 + tid; i < N; i += 256) Sg[i * GR_LDV + k] *= inv;
+    __syncthreads();
+    const int rem = N - k - 1;
+    for (int e = tid; e < rem * rem; e += 256) {
+      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+      if (j <= i) Sg[i * GR_LDV + j] = fmaf(-Sg[i * GR_LDV + k], Sg[j * GR_LDV + k], Sg[i * GR_LDV + j]);
+    }
+    __syncthreads();
+  }
+  if (tid < N) {
+    const float* e = eps + ((size_t)sidx * D + d) * N;
+    float acc = cst + mn[tid];
+    for (int j = 0; j <= tid; ++j) acc = fmaf(Sg[tid * GR_LDV + j], __ldg(e + j), acc);
+    out[(size_t)(sidx * N + tid) * ldo + d] = acc;
+  }
+}
+
+int gp_big_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const float* eps, const uint8_t* mask,
+                          float* out, int ldo, cudaStream_t stream) {
+  DVG_REQUIRE(N >= 1 && N <= GR_NMAX, "rsample correlates at most %d points per call (got %d)", GR_NMAX, N);
+  const size_t smem = sizeof(float) * ((size_t)3 * GB_T * GB_LD + 2 * GB_T * GR_LDV + (size_t)GR_NMAX * GR_LDV + 2 * GR_NMAX + GB_T);
+  static bool configured = false;
+  if (!configured) {
+    DVG_CUDA(cudaFuncSetAttribute(gp_big_rsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  gp_big_rsample_kernel<<<dim3(S, h->dims.num_dims), 256, smem, stream>>>(S, N, h->dims.num_dims, h->mp, x, ldx, eps, mask, h->z,
+                                                                          h->linv, h->lqt, h->alpha, h->hyp, out, ldo);
+  DVG_LAUNCH_CHECK();
   return DVG_OK;
 }
 

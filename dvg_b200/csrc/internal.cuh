@@ -88,6 +88,7 @@ struct dvg_gp_s {
   bool big = false;
   float* partial = nullptr;   // [D][mp/64][n_pad][3] row-block partial sums
   size_t partial_cap = 0;
+  std::vector<void*> retired; // outgrown scratch kept alive for already captured graphs (freed by destroy)
 };
 
 namespace dvg {
@@ -168,6 +169,8 @@ int gp_big_load_factors(dvg_gp_s* h, const float* inducing, const float* linv, c
 int gp_big_predict_launch(dvg_gp_s* h, int n_rows, const float* x, int ldx, const int32_t* row_index, float* mean,
                           long long mean_sn, long long mean_sd, float* var, long long var_sn, long long var_sd,
                           cudaStream_t stream);
+int gp_big_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const float* eps, const uint8_t* mask,
+                          float* out, int ldo, cudaStream_t stream);
 int gp_big_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t* stat_rows, float* window, int W,
                           int32_t* count, int warmup, float factor, float* value, float* thr, uint8_t* mask,
                           cudaStream_t stream);

@@ -207,6 +207,39 @@ def test_predict_large_inducing_set(params, D, M, N):
         assert relerr(mean, ref["mean"]) < 1e-4
 
 
+@pytest.mark.parametrize("D,M,N", [(3, 256, 50), (2, 129, 7), (2, 512, 128), (2, 200, 65)])
+def test_rsample_large_inducing_set(D, M, N):
+    """.rsample() on a handle with pre-computed factors (M > 128, BASELINE configs[4]; gp_big_rsample_kernel):
+    the same bar as test_rsample, plus the mask semantics (unmasked rollouts untouched)."""
+    from dvg_b200 import _capi
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=3 + M, trained_like=True, smooth_mean=True)
+    gp, lik = make_gp(gp_sd, lik_sd)
+    g = torch.Generator().manual_seed(N)
+    h = torch.tanh(torch.randn(N, D, generator=g))
+    eps = torch.randn(D, N, generator=g)
+    ref = gp_ref.predictive(gp_sd, lik_sd, gp_ref.latent_to_gp_input(h), torch.float64, "direct")
+    want = gp_ref.rsample(ref["mean"], ref["covar"], eps.double())
+    with torch.no_grad():
+        got = lik(gp(h.cuda().transpose(0, 1).view(D, N, 1))).rsample(eps=eps.cuda())
+    assert gp._runtime(lik).M == M and M > 128
+    assert relerr(got, want) < 1e-4
+    # three rollouts, only the middle one masked
+    rt = gp._runtime(lik)
+    S = 3
+    x = torch.tanh(torch.randn(S * N, D, generator=g))
+    x[N:2 * N] = h
+    e3 = torch.randn(S, D, N, generator=g)
+    e3[1] = eps
+    out = torch.full((S * N, D), 7.0, device="cuda")
+    mask = torch.tensor([0, 1, 0], dtype=torch.uint8, device="cuda")
+    xc, ec = x.cuda(), e3.cuda()
+    _capi.check(rt.lib.dvg_gp_rsample(rt.handle, S, N, _capi.ptr(xc), D, _capi.ptr(ec), _capi.ptr(mask), _capi.ptr(out), D,
+                                      _capi.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.all(out[:N] == 7.0) and torch.all(out[2 * N:] == 7.0)
+    assert relerr(out[N:2 * N].transpose(0, 1), want) < 1e-4
+
+
 def test_large_and_small_paths_agree_at_the_boundary():
     """M = 128 runs the shared-memory kernels, the same parameters padded to M = 129 (one extra far-away inducing
     point with zero variational weight) run the tiled path: both must give the same predictive."""
