@@ -238,6 +238,7 @@ static void gp_free_all(dvg_gp_s* h) {
   auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
   fr(h->z); fr(h->linv); fr(h->lqt); fr(h->alpha); fr(h->hyp); fr(h->work); fr(h->var_rows);
   fr(h->ticket); fr(h->trig_list); fr(h->trig_count); fr(h->linvT); fr(h->lq); fr(h->partial);
+  fr(h->tc_img_v); fr(h->tc_img_w); fr(h->tc_alpha2);
   for (void* q : h->retired) cudaFree(q);
   h->retired.clear();
 }

@@ -202,7 +202,7 @@ int gp_big_load_factors(dvg_gp_s* h, const float* inducing, const float* linv, c
   gp_big_pad_vec_kernel<<<vg, 128, 0, stream>>>(M, Mp, beta, h->alpha);
   DVG_LAUNCH_CHECK();
   DVG_CUDA(cudaMemcpyAsync(h->hyp, hyp, sizeof(float) * D * 4, cudaMemcpyDeviceToDevice, stream));
-  return DVG_OK;
+  return gp_tc_pack(h, stream);          // bf16 hi/lo k-block images for the tensor-core path (gp_tc.cu)
 }
 
 static int gp_big_reserve_partial(dvg_gp_s* h, size_t floats, cudaStream_t stream) {
@@ -232,6 +232,23 @@ int gp_big_predict_launch(dvg_gp_s* h, int n_rows, const float* x, int ldx, cons
   }
   // bound the partial-sum scratch: process the points in chunks
   const int chunk_max = 4096;
+  const bool tc = gp_tc_enabled() && h->tc_img_v != nullptr;
+  for (int c0 = 0; tc && c0 < n_rows; c0 += chunk_max) {
+    // tensor-core path: 128-point x 256-row tiles, same scratch layout and finalize kernel (JB = row tiles of 256)
+    const int nc = n_rows - c0 < chunk_max ? n_rows - c0 : chunk_max;
+    const int n_pad = ceil_div(nc, 128) * 128;
+    int rc = gp_big_reserve_partial(h, (size_t)D * h->tc_JT * n_pad * 3, stream);
+    if (rc) return rc;
+    const float* xc = row_index ? x : x + (size_t)c0 * ldx;
+    const int32_t* ric = row_index ? row_index + c0 : nullptr;
+    if ((rc = gp_tc_partial_launch(h, nc, n_pad, xc, ldx, ric, mean != nullptr ? 1 : 0, stream))) return rc;
+    dim3 g2(ceil_div(nc, 128), D);
+    gp_big_finalize_kernel<<<g2, 128, 0, stream>>>(nc, D, h->tc_JT, n_pad, h->partial, h->hyp,
+                                                   mean ? mean + (size_t)c0 * mean_sn : nullptr, mean_sn, mean_sd,
+                                                   var ? var + (size_t)c0 * var_sn : nullptr, var_sn, var_sd);
+    DVG_LAUNCH_CHECK();
+  }
+  if (tc) return DVG_OK;
   for (int c0 = 0; c0 < n_rows; c0 += chunk_max) {
     const int nc = n_rows - c0 < chunk_max ? n_rows - c0 : chunk_max;
     const int n_pad = ceil_div(nc, GB_T) * GB_T;

@@ -89,6 +89,12 @@ struct dvg_gp_s {
   float* partial = nullptr;   // [D][mp/64][n_pad][3] row-block partial sums
   size_t partial_cap = 0;
   std::vector<void*> retired; // outgrown scratch kept alive for already captured graphs (freed by destroy)
+  // tensor-core path of the large-M predictive (gp_tc.cu): bf16 hi/lo k-block images of Linv / L_q^T
+  uint8_t* tc_img_v = nullptr; uint8_t* tc_img_w = nullptr;
+  size_t tc_img_bytes = 0;
+  int tc_JT = 0, tc_MT = 0;
+  float* tc_alpha2 = nullptr;   // [D][mp] Linv^T beta
+  size_t tc_alpha2_n = 0;
 };
 
 namespace dvg {
@@ -162,6 +168,12 @@ int gp_trigger_launch(dvg_gp_s* h, int S, const float* x, int ldx, const int32_t
                       cudaStream_t stream);
 int gp_rsample_launch(dvg_gp_s* h, int S, int N, const float* x, int ldx, const float* eps, const uint8_t* mask,
                       float* out, int ldo, cudaStream_t stream);
+
+// gp_tc.cu: tcgen05 version of the large-M predictive partial sums
+bool gp_tc_enabled();
+int gp_tc_pack(dvg_gp_s* h, cudaStream_t stream);
+int gp_tc_partial_launch(dvg_gp_s* h, int n_rows, int n_pad, const float* x, int ldx, const int32_t* row_index,
+                         int want_mean, cudaStream_t stream);
 
 // gp_big.cu
 int gp_big_load_factors(dvg_gp_s* h, const float* inducing, const float* linv, const float* lq, const float* beta,
