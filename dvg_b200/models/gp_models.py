@@ -33,7 +33,10 @@ from .. import _capi
 
 JITTER = 1e-3
 NOISE_LOWER_BOUND = 1e-4
-MAX_INDUCING_ONDEVICE = 128      # include/dvg_b200.h: DVG_GP_MAX_INDUCING_ONDEVICE
+MAX_INDUCING_ONDEVICE = 128      # include/dvg_b200.h: DVG_GP_MAX_INDUCING_ONDEVICE (limit of the on-device fp64 factorisation)
+# Inducing sets above this size take the tiled path (pre-computed factors + tensor-core tiles, gp_tc.cu / gp_big.cu): the
+# shared-memory kernels, built for the reference's M = 40, reach 4 TFLOP/s at M = 128 where the tiled path reaches > 100.
+TILED_FROM = 64
 
 
 class _Holder(nn.Module):
@@ -91,7 +94,7 @@ class _GpRuntime:
             raw_noise = ts[6]
             lb = float(likelihood.noise_lower_bound)
         with torch.cuda.device(dev):
-            if M > MAX_INDUCING_ONDEVICE:
+            if M > TILED_FROM:
                 self._refresh_factors(ts, raw_noise, lb, D, M)
             else:
                 args = [_capi.ptr(t.detach().contiguous()) for t in ts[:6]] + [_capi.ptr(raw_noise.detach().contiguous())]

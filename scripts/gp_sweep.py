@@ -55,6 +55,6 @@ for M in [int(v) for v in a.M.split(",")]:
         ms = e0.elapsed_time(e1) / reps
         flops = 2.0 * (M * M + 2 * M) * S * D * 2 / 2           # lower + upper triangles, 2 flops per FMA
         print(json.dumps({"M": M, "samples": S, "D": D, "ms": round(ms, 4), "samples_per_s": round(S / ms * 1e3),
-                          "fp32_tflops": round(flops / ms / 1e9, 2), "path": "tiled" if M > 160 else "smem"}), flush=True)
+                          "fp32_tflops": round(flops / ms / 1e9, 2), "path": "tensor-core tiles" if M > 64 else "smem"}), flush=True)
     del gp, lik, rt
     torch.cuda.empty_cache()
