@@ -453,7 +453,7 @@ int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows, const floa
     if (rc || rs_in_kernel || rs_eps == nullptr || warmup) return rc;
     return dvg_gp_rsample(g, n_rollouts, n_points, x, ldx, rs_eps, mask, y, ldy, stream);
   }
-  // not fusable (fp32 variant, single row tile, large inducing set, scratch not reserved): separate calls, same semantics
+  // not fusable (fp32 variant, large inducing set, scratch not reserved): separate calls, same semantics
   int rc = dvg_gp_trigger(g, n_rollouts, x, ldx, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,
                           stream);
   if (rc) return rc;

@@ -1222,7 +1222,8 @@ bool lstm_step_usable(const dvg_lstm_s* h, int rows) {
   if (!h->tc_ok || !use_fused()) return false;
   const int RT = ceil_div(rows, TC_ROWS), groups = ceil_div(RT, 2), hk = h->dims.hidden_size / 64;
   const int pairs = h->sm_count / 2;
-  if (RT < 2 || pairs < 1 || hk > 16) return false;    // poll_deps samples at most 16 k-block flags per item
+  if (RT < 1 || pairs < 1 || hk > 16) return false;    // poll_deps samples at most 16 k-block flags per item
+  if (lstm_small_usable(h, rows)) return false;        // <= 64 rows at H = 256: the 16-CTA cluster kernel is faster
   return ceil_div(groups * hk, pairs) <= STEP_XMAX;
 }
 

@@ -186,7 +186,7 @@ def test_rsample_mask_leaves_rows_untouched():
             assert torch.all(blk == 7.0)
 
 
-# ---- large inducing sets (M > 128: pre-computed factors + tiled GEMM kernels, gp_big.cu; BASELINE configs[4]) ----------
+# ---- large inducing sets (M > 64: pre-computed factors + tcgen05 tiles, gp_tc.cu / gp_big.cu; BASELINE configs[4]) -------
 @pytest.mark.parametrize("params", ["init", "trained_smooth"])
 @pytest.mark.parametrize("D,M,N", [(6, 129, 70), (4, 200, 33), (3, 512, 130)])
 def test_predict_large_inducing_set(params, D, M, N):
@@ -209,7 +209,7 @@ def test_predict_large_inducing_set(params, D, M, N):
 
 @pytest.mark.parametrize("D,M,N", [(3, 256, 50), (2, 129, 7), (2, 512, 128), (2, 200, 65)])
 def test_rsample_large_inducing_set(D, M, N):
-    """.rsample() on a handle with pre-computed factors (M > 128, BASELINE configs[4]; gp_big_rsample_kernel):
+    """.rsample() on a handle with pre-computed factors (M > 64, BASELINE configs[4]; gp_big_rsample_kernel):
     the same bar as test_rsample, plus the mask semantics (unmasked rollouts untouched)."""
     from dvg_b200 import _capi
     gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=3 + M, trained_like=True, smooth_mean=True)
@@ -308,3 +308,16 @@ def test_trigger_large_inducing_set():
                     assert bool(m_gpu[s]) == bool(v > th)
                     n_checked += 1
     assert n_checked > 200
+
+
+def test_fp32_tiled_kernels_cross_check():
+    """The FP32 FFMA tiles of gp_big.cu (the path DVG_GP_TC=0 selects; the switch is read once per process) must hold
+    the same bar as the tensor-core tiles: re-run the large-M predictive and trigger tests in a child with it set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, DVG_GP_TC="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k",
+                        "predict_large_inducing_set or trigger_large_inducing_set or agree_at_the_boundary"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

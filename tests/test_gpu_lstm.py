@@ -111,7 +111,7 @@ def test_gaussian_lstm_5000_rows_vs_oracle(variant):
 
 
 @pytest.mark.parametrize("variant", ["fp32", "bf16x3", "bf16"])
-@pytest.mark.parametrize("rows", [16, 50, 300, 5000])
+@pytest.mark.parametrize("rows", [16, 50, 100, 300, 5000])
 def test_full_size_vs_oracle(variant, rows):
     """G90/H256/L2 (the reference's sizes): per-step with re-synchronised state, then free-running."""
     sd = lstm_ref.random_lstm_state_dict(90, 90, 256, 2, seed=7)
@@ -141,8 +141,8 @@ def test_full_size_vs_oracle(variant, rows):
 @pytest.mark.parametrize("variant", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("rows", [50, 300])
 def test_long_free_running(variant, rows):
-    """104 recurrent steps (generate_frames.py horizon) against the fp64 oracle: 50 rows (one row tile, per-GEMM
-    kernels) and 300 rows (three row tiles: the persistent step kernel with the embed Linear folded into layer 0)."""
+    """104 recurrent steps (generate_frames.py horizon) against the fp64 oracle: 50 rows (the 16-CTA cluster
+    kernel) and 300 rows (three row tiles: the persistent step kernel with the embed Linear folded into layer 0)."""
     sd = lstm_ref.random_lstm_state_dict(90, 90, 256, 2, seed=11)
     sd64 = lstm_ref.to_dtype(sd, torch.float64)
     m = make_lstm(sd, rows=rows, variant=variant)
@@ -245,7 +245,10 @@ def test_autograd_delegate_matches_fast_path():
                                       (1600, 256, 2),      # cfg 3: BAIR, 32 rollouts x 50 per GPU
                                       (6400, 256, 2),      # cfg 4: UCF, batch 64 x 100 samples
                                       (257, 512, 1),       # cfg 5 sweep: hidden 512 (odd row count: 3 row tiles)
-                                      (130, 1024, 2)])     # cfg 5 sweep: hidden 1024
+                                      (130, 1024, 2),      # cfg 5 sweep: hidden 1024
+                                      (100, 256, 2),       # one row tile, > 64 rows: persistent kernel, peer CTA all padding
+                                      (16, 512, 2),        # cfg 5 sweep: 16 samples at hidden 512 / 1024 (persistent kernel,
+                                      (64, 1024, 2)])      #   the cluster kernel is H = 256 only)
 def test_config_shapes(rows, H, L):
     sd = lstm_ref.random_lstm_state_dict(90, 90, H, L, seed=H + rows)
     gen = torch.Generator().manual_seed(1)
