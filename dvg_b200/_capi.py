@@ -19,6 +19,7 @@ VARIANTS = {"fp32": DVG_FP32, "bf16x3": DVG_BF16X3, "bf16": DVG_BF16}
 EXPORTS = [
     "dvg_last_error", "dvg_version", "dvg_device_info",
     "dvg_lstm_prepare", "dvg_lstm_refresh", "dvg_lstm_destroy", "dvg_lstm_reserve",
+    "dvg_lstm_chain_begin", "dvg_lstm_chain_end",
     "dvg_lstm_state_bytes", "dvg_lstm_state_packed_offset", "dvg_lstm_state_repack",
     "dvg_lstm_step", "dvg_lstm_profile", "dvg_gauss_lstm_step",
     "dvg_gp_prepare", "dvg_gp_refresh", "dvg_gp_prepare_factors", "dvg_gp_refresh_factors", "dvg_gp_destroy", "dvg_gp_predict", "dvg_gp_trigger",
@@ -52,7 +53,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not _build.is_current():
+    if not _build.is_current() and not os.environ.get("DVG_LIB_NOREBUILD"):     # (developer A/B of pre-built tagged libraries)
         try:
             _build.build(verbose=False)
         except Exception as e:  # stale-but-present library is still usable (e.g. no nvcc on the box)
@@ -72,6 +73,8 @@ def load():
     lib.dvg_lstm_refresh.argtypes = [P, P, P, PP, PP, PP, PP, P, P, P, P, P]
     lib.dvg_lstm_destroy.argtypes = [P]
     lib.dvg_lstm_reserve.argtypes = [P, c_int]
+    lib.dvg_lstm_chain_begin.argtypes = [P, P]
+    lib.dvg_lstm_chain_end.argtypes = [P, P]
     lib.dvg_lstm_state_bytes.restype = c_size_t
     lib.dvg_lstm_state_bytes.argtypes = [P, c_int]
     lib.dvg_lstm_state_packed_offset.restype = c_size_t

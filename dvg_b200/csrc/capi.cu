@@ -125,18 +125,31 @@ int dvg_lstm_reserve(dvg_lstm_t h, int rows) {
   if (h->tc_ok) {
     const size_t xpb = lstm_step_xp_bytes(h, rows) > lstm_tc_scratch_bytes_xp(h, rows) ? lstm_step_xp_bytes(h, rows)
                                                                                         : lstm_tc_scratch_bytes_xp(h, rows);
-    DVG_CUDA(cudaMalloc(&h->tc_xp, xpb));
-    DVG_CUDA(cudaMemset(h->tc_xp, 0, xpb));
+    h->xp_stride = align_up(xpb, 1024);            // two slabs: chained step launches alternate
+    DVG_CUDA(cudaMalloc(&h->tc_xp, 2 * h->xp_stride));
+    DVG_CUDA(cudaMemset(h->tc_xp, 0, 2 * h->xp_stride));
     DVG_CUDA(cudaMalloc(&h->rs_buf, sizeof(float) * (size_t)rows * h->dims.output_size));
     DVG_CUDA(cudaMalloc(&h->tc_ep, lstm_tc_scratch_bytes_ep(h, rows)));
     DVG_CUDA(cudaMemset(h->tc_ep, 0, lstm_tc_scratch_bytes_ep(h, rows)));
-    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * lstm_step_flag_words(h, rows)));
-    DVG_CUDA(cudaMemset(h->fused_flags, 0, sizeof(int) * lstm_step_flag_words(h, rows)));
+    h->flag_set_words = lstm_step_flag_words(h, rows);      // three sets: chained step launches rotate through them
+    DVG_CUDA(cudaMalloc(&h->fused_flags, sizeof(int) * (3 * h->flag_set_words + 8)));       // + the chain's retired counter
+    DVG_CUDA(cudaMemset(h->fused_flags, 0, sizeof(int) * (3 * h->flag_set_words + 8)));
+    h->chain_on = h->chain_ok = false;
+    h->chain_idx = 0;
     int rc = lstm_step_build_schedule(h, rows);
     if (rc) return rc;
   }
   h->reserved_rows = rows;
   return DVG_OK;
+}
+
+int dvg_lstm_chain_begin(dvg_lstm_t h, dvg_stream_t stream) {
+  DVG_REQUIRE(h, "null handle");
+  return lstm_step_chain(h, true, (cudaStream_t)stream);
+}
+int dvg_lstm_chain_end(dvg_lstm_t h, dvg_stream_t stream) {
+  DVG_REQUIRE(h, "null handle");
+  return lstm_step_chain(h, false, (cudaStream_t)stream);
 }
 
 static size_t state_f32_bytes(const dvg_lstm_s* h, int rows) {
@@ -266,12 +279,12 @@ int dvg_gp_prepare(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing
   if (e == cudaSuccess) e = cudaMalloc(&h->hyp, sizeof(float) * D * 4);
   if (e == cudaSuccess) e = cudaMalloc(&h->work, sizeof(double) * D * M * M);
   h->var_rows_cap = 4096;
-  if (e == cudaSuccess) e = cudaMalloc(&h->var_rows, sizeof(float) * D * h->var_rows_cap);
-  if (e == cudaSuccess) e = cudaMalloc(&h->trig_list, sizeof(int) * h->var_rows_cap);
-  if (e == cudaSuccess) e = cudaMalloc(&h->trig_count, sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, sizeof(unsigned int) * (1 + h->var_rows_cap / 8 + 1));
-  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int) * (1 + h->var_rows_cap / 8 + 1));
-  if (e == cudaSuccess) e = cudaMemset(h->trig_count, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->var_rows, sizeof(float) * 2 * D * h->var_rows_cap);   // two slots, like trig_list
+  if (e == cudaSuccess) e = cudaMalloc(&h->trig_list, sizeof(int) * 2 * h->var_rows_cap);   // two slots: chained step launches alternate
+  if (e == cudaSuccess) e = cudaMalloc(&h->trig_count, 2 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, sizeof(unsigned int) * (4 + h->var_rows_cap / 8));
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int) * (4 + h->var_rows_cap / 8));
+  if (e == cudaSuccess) e = cudaMemset(h->trig_count, 0, 2 * sizeof(int));
   if (e != cudaSuccess) {
     set_error("GP handle allocation failed: %s", cudaGetErrorString(e));
     gp_free_all(h);
@@ -312,12 +325,12 @@ int dvg_gp_prepare_factors(dvg_gp_t* out, const dvg_gp_dims* dims, const float* 
   if (e == cudaSuccess) e = cudaMalloc(&h->alpha, sizeof(float) * D * mp);
   if (e == cudaSuccess) e = cudaMalloc(&h->hyp, sizeof(float) * D * 4);
   h->var_rows_cap = 4096;
-  if (e == cudaSuccess) e = cudaMalloc(&h->var_rows, sizeof(float) * D * h->var_rows_cap);
-  if (e == cudaSuccess) e = cudaMalloc(&h->trig_list, sizeof(int) * h->var_rows_cap);
-  if (e == cudaSuccess) e = cudaMalloc(&h->trig_count, sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, sizeof(unsigned int) * (1 + h->var_rows_cap / 8 + 1));
-  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int) * (1 + h->var_rows_cap / 8 + 1));
-  if (e == cudaSuccess) e = cudaMemset(h->trig_count, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->var_rows, sizeof(float) * 2 * D * h->var_rows_cap);   // two slots, like trig_list
+  if (e == cudaSuccess) e = cudaMalloc(&h->trig_list, sizeof(int) * 2 * h->var_rows_cap);   // two slots: chained step launches alternate
+  if (e == cudaSuccess) e = cudaMalloc(&h->trig_count, 2 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->ticket, sizeof(unsigned int) * (4 + h->var_rows_cap / 8));
+  if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, sizeof(unsigned int) * (4 + h->var_rows_cap / 8));
+  if (e == cudaSuccess) e = cudaMemset(h->trig_count, 0, 2 * sizeof(int));
   if (e != cudaSuccess) {
     set_error("GP handle allocation failed: %s", cudaGetErrorString(e));
     gp_free_all(h);
@@ -368,14 +381,14 @@ int dvg_gp_trigger(dvg_gp_t h, int n_rollouts, const float* x, int ldx, const in
     if (h->var_rows) cudaFree(h->var_rows);
     h->var_rows = nullptr;
     h->var_rows_cap = 0;
-    DVG_CUDA(cudaMalloc(&h->var_rows, sizeof(float) * (size_t)h->dims.num_dims * n_rollouts));
+    DVG_CUDA(cudaMalloc(&h->var_rows, sizeof(float) * 2 * (size_t)h->dims.num_dims * n_rollouts));
     if (h->trig_list) cudaFree(h->trig_list);
     h->trig_list = nullptr;
-    DVG_CUDA(cudaMalloc(&h->trig_list, sizeof(int) * (size_t)n_rollouts));
+    DVG_CUDA(cudaMalloc(&h->trig_list, sizeof(int) * 2 * (size_t)n_rollouts));
     if (h->ticket) cudaFree(h->ticket);
     h->ticket = nullptr;
-    DVG_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int) * (size_t)(2 + n_rollouts / 8)));
-    DVG_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int) * (size_t)(2 + n_rollouts / 8)));
+    DVG_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int) * (size_t)(4 + n_rollouts / 8)));
+    DVG_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int) * (size_t)(4 + n_rollouts / 8)));
     h->var_rows_cap = n_rollouts;
   }
   if (h->big)
@@ -433,6 +446,7 @@ int dvg_rollout_step(dvg_lstm_t h, dvg_gp_t g, int variant, int rows, const floa
                                   n_rollouts, stat_rows, window, window_len, count, warmup, factor, value, thr, mask,
                                   rs_in_kernel ? rs_eps : nullptr, s);
     if (rc || rs_in_kernel || rs_eps == nullptr || warmup) return rc;
+    h->chain_ok = false;       // another kernel now sits between this step launch and the next
     return dvg_gp_rsample(g, n_rollouts, n_points, x, ldx, rs_eps, mask, y, ldy, stream);
   }
   if (tc && rows <= h->reserved_rows && window_len >= 1 && window_len <= 128 && ldx >= h->dims.input_size &&

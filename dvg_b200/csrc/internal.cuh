@@ -45,6 +45,14 @@ struct dvg_lstm_s {
   float* fold_wx = nullptr;      // [4H][G]  W_ih0 W_e
   float* fold_bx = nullptr;      // [4H]     W_ih0 b_e + b_ih0 + b_hh0
   int* fused_flags = nullptr;    // dependency counters of the persistent step kernel (lstm_step.cu), self-resetting
+  size_t flag_set_words = 0;     // three counter sets of this many words (chained launches rotate through them)
+  size_t xp_stride = 0;          // two packed-x slabs, this many bytes apart
+  // chained step launches (dvg_lstm_chain_begin / _end, lstm_step.cu): consecutive launches overlap
+  bool chain_on = false, chain_ok = false, chain_dirty = false;
+  int chain_idx = 0, chain_rows = 0, chain_nsplit = 0, chain_prev_trig = 0, chain_prev_restore = 0;
+  const void* chain_out = nullptr;         // h_out of the last chained launch (must be the next one's h_in)
+  const void* chain_gp = nullptr;
+  cudaStream_t chain_stream = nullptr;
   int* sched_dev = nullptr;      // optional item order of the step kernel for (sched_rows, sched_pairs)
   int sched_len = 0, sched_rows = 0, sched_pairs = 0;
 
@@ -143,6 +151,7 @@ int lstm_small_launch(dvg_lstm_s* h, int nsplit, int rows, const float* x, int l
 
 bool lstm_step_usable(const dvg_lstm_s* h, int rows);
 size_t lstm_step_flag_words(const dvg_lstm_s* h, int rows);
+int lstm_step_chain(dvg_lstm_s* h, bool begin, cudaStream_t stream);
 size_t lstm_step_xp_bytes(const dvg_lstm_s* h, int rows);
 int lstm_step_build_schedule(dvg_lstm_s* h, int rows);
 int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,

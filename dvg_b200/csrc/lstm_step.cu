@@ -89,6 +89,7 @@ struct StepPhase {
   const uint8_t* w; const float* bias;
   const int* wait_flags;  // [groups][kb_in] counters of the producing phase (nullptr: layer 0, local x-ready barrier)
   int* done_flags;        // [groups][n_tiles]
+  const int* prev_done;   // chained launches: done_flags of the same layer in the PREVIOUS launch (its packed h' is our h)
   const float* c_in; const float* h_in; float* h_out; float* c_out; uint8_t* hp_out;   // LSTM
   float* y; int ldy; int n_valid;                                                       // TANH
   const float* eps; float* z; float* mu; float* logvar; int Z;                          // GAUSS
@@ -110,6 +111,12 @@ struct StepArgs {
   const int* sched; int sched_len;   // optional host-built item order: pair p runs sched[p], sched[p + pairs], ...
   int* flag_words; int n_flag_words;     // dependency counters, then [mask_ready][done_ctr]; exit counter follows
   int* mask_ready; int* done_ctr; int* rs_next; int* rs_done;
+  int chained, in_chain, chain_idx, rot, self_reset, prev_trig, prev_restore;
+  int* retired;                   // number of launches of the chain that have completely exited
+  const int* prev_mask_ready; const int* prev_fin; const int* prev_trig_count;
+  int* fin_ctr;
+  int* dim_ctr; int* fin_claim;   // GP trigger work is claimed in start order (see trigger_partials)
+  int* reset_set;
   float* rs_buf;                  // [rows, G] side buffer of the in-kernel resample
   unsigned long long* trace;
   StepTrig trig;
@@ -220,7 +227,14 @@ __device__ __forceinline__ void poll_deps(const int* flags, int n, int j, int ta
 #endif
 }
 
+// CH: the launch belongs to a chain (dvg_lstm_chain_begin/_end).  Two instantiations, so that the stream-ordered kernel
+// is compiled without a trace of the chain code: the kernel sits at its register cap and the tile epilogue's code
+// generation reacts to every addition (a uniform `if (in_chain)` around the c' stores alone cost the stream-ordered
+// step 1 us).
+template <bool CH>
 __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid_constant__ StepArgs p) {
+  const bool in_chain = CH;
+  const bool chained = CH && p.chained != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = ptx::smem_u32(smem_raw);
   if ((base & 1023u) != 0) {
@@ -242,12 +256,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
   auto xready_bar = [&](int j) { return bar_base + 8u * (3 * STEP_MAX_STAGES + 4 + j); };
   const uint32_t tmem_slot = bar_base + 8u * (3 * STEP_MAX_STAGES + 4 + STEP_XMAX);
   uint8_t* tail = smem_raw + (size_t)p.stages * stage_bytes;
-  int* s_misc = reinterpret_cast<int*>(tail + 8 * (3 * STEP_MAX_STAGES + 4 + STEP_XMAX) + 16);
+  int* s_misc = reinterpret_cast<int*>(tail + 8 * (3 * STEP_MAX_STAGES + 4 + STEP_XMAX) + 16);     // 4 words
   float* s_bias = reinterpret_cast<float*>(tail + STEP_BAR_BYTES);                // [2][256] floats
   uint8_t* s_ebuf = tail + STEP_BAR_BYTES + 2 * 256 * sizeof(float);             // [STEP_EW][32 rows x STEP_RB] (32 KB)
 
-  const int cid = (int)ptx::cluster_id_x();
   const int ncl = (int)ptx::cluster_count_x();
+  const int cid = ((int)ptx::cluster_id_x() + p.rot) % ncl;
   // k-th item of this pair (-1: none)
   auto item_at = [&](int k) -> int {
     const int pos = cid + k * ncl;
@@ -356,7 +370,23 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
   // in the stream (normally the previous time step, whose last pairs finish ~10 us after the first); nothing below
   // may run before that grid has completed: it produced our state, and it resets the dependency counters on exit.
   ptx::griddep_launch_dependents();
-  ptx::griddep_wait();
+  if (!chained) {
+    ptx::griddep_wait();
+  } else {
+    if (threadIdx.x == 0) {
+      // At most TWO launches of a chain may be in flight: the counter sets rotate mod 3 and the x slabs / fired lists
+      // alternate.  "My SM is free" does not prove that the launch before the previous one is gone (its stragglers can
+      // outlive the first CTAs of the previous launch: measured, launches 3 / 5 of a chain), so it is checked.
+      // (Polling from an idle lane at kernel entry, to hide the round trip behind the set-up, measured 0.8 us slower.)
+      poll_ge(p.retired, p.chain_idx - 1, -7);
+      if (p.prev_trig) {
+        poll_ge(p.prev_mask_ready, 1, -4);
+        if (p.prev_restore && *reinterpret_cast<const volatile int*>(p.prev_trig_count) > 0)
+          poll_ge(p.prev_fin, (int)gridDim.x, -5);
+      }
+    }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
@@ -388,6 +418,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
         const int KB = kb_rec + kb_in;
         const int* wait_flags = f.wait_flags;
         const bool layer0 = wait_flags == nullptr;
+        const int* prev_done = chained ? f.prev_done : nullptr;
+        uint32_t ready_rec = 0;
         const uint8_t* a_rec = f.a_rec;
         const uint8_t* a_in = f.a_in;
         if (layer0) a_in += (size_t)nt * p.row_tiles * kb_in * (2u * TC_A_IMG);
@@ -426,6 +458,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
               ++xj;
             }
             if (pm < 3 && kb == 0) TRACE(2 + pm * 8 + 1);
+          } else if (prev_done != nullptr) {
+            poll_deps(prev_done + rg * kb_rec, kb_rec, kb, 2, ready_rec, item);
           }
           const uint8_t* asrc = rec ? a_rec + (size_t)(rt * kb_rec + kb) * (2u * TC_A_IMG)
                                     : a_in + (size_t)(rt * kb_in + kb) * (2u * TC_A_IMG);
@@ -538,7 +572,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       const StepTrig& g = p.trig;
       const int nblk = (g.S + 31) / 32;
       const int NF = nblk < (int)gridDim.x ? nblk : (int)gridDim.x;
-      const int fi = (int)gridDim.x - 1 - (int)blockIdx.x;
+      // (chained launches: the finaliser roles go to the first NF CTAs to get here -- the CTAs start as the previous
+      //  launch's CTAs exit, spread over ~20 us, and the mask should not wait for the stragglers)
+      int fi = (int)gridDim.x - 1 - (int)blockIdx.x;
+      if (chained) {
+        if (lane == 0) fi = atomicAdd(p.fin_claim, 1);
+        fi = __shfl_sync(0xffffffffu, fi, 0);
+      }
       if (fi < NF) {
         if (lane == 0) {
           const long long t0 = clock64();
@@ -604,6 +644,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       head_tanh_tile(tmem_base + tlane, p.ph[p.n_phases - 1].n_tile, ew >> 2, lane, s_bias, s_ebuf + ew * (32 * STEP_RB),
                      p.ph[p.n_phases - 1].y, p.ph[p.n_phases - 1].ldy, p.ph[p.n_phases - 1].n_valid, 0, 0);
 #endif
+    if (p.trig.enabled && chained && etid == 0) s_misc[3] = atomicAdd(p.dim_ctr, 1);   // see trigger_partials
     // x-pack of every layer-0 item of this pair, in item order
     {
       int xj = 0;
@@ -625,9 +666,15 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
     //      problems start as soon as the first pairs finish.
     //      (small grids -- fewer CTAs than latent dims -- take several dims per CTA)
     auto trigger_partials = [&]() {
-      const int trig_ctas = p.trig.D < (int)gridDim.x ? p.trig.D : (int)gridDim.x;
-      if (!p.trig.enabled || (int)gridDim.x - 1 - (int)blockIdx.x >= trig_ctas) return;
+      if (!p.trig.enabled) return;
       const StepTrig& g = p.trig;
+      // Stream-ordered launches: the last D CTAs take one dim each (with the default item order those pairs have the
+      // lightest tile load; measured 43.8 vs 49.3 us per step against first-come claiming).  Chained launches: dims are
+      // CLAIMED (atomic counter, up to `quota` per CTA) in the order the CTAs get here -- the CTAs start as the previous
+      // launch's CTAs exit, spread over ~20 us, and the next launch waits for this launch's mask: it must not wait for
+      // the dims of the last CTAs to start (measured 41.4 -> 38.1 us per step).
+      const int trig_ctas = g.D < (int)gridDim.x ? g.D : (int)gridDim.x;
+      const int quota = (g.D + (int)gridDim.x - 1) / (int)gridDim.x;
       const int MP = g.mp;
       constexpr int TPQ = STEP_EW * 8;              // threads per quarter
       float* s_linv = reinterpret_cast<float*>(s_ebuf);
@@ -635,8 +682,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       float* s_z = s_lqt + MP * MP;
       float* s_part = s_z + MP;                     // [3][TPQ]
       const int qt = etid / TPQ, li = etid % TPQ;
-      for (int d = (int)gridDim.x - 1 - (int)blockIdx.x; d < g.D; d += trig_ctas) {
+      for (int q = 0; q < quota; ++q) {
+        if (chained && q > 0 && etid == 0) s_misc[3] = atomicAdd(p.dim_ctr, 1);   // (first claim: before the x-pack)
         ptx::named_bar_sync(1, STEP_EW * 32);       // every warp is done with its transpose buffer / the last dim
+        const int d = chained ? s_misc[3] : (int)gridDim.x - 1 - (int)blockIdx.x + q * trig_ctas;
+        if (d >= g.D) break;
         {
           const float4* g1 = reinterpret_cast<const float4*>(g.linv + (size_t)d * MP * MP);
           const float4* g2 = reinterpret_cast<const float4*>(g.lqt + (size_t)d * MP * MP);
@@ -679,9 +729,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           ptx::named_bar_sync(1, STEP_EW * 32);
         }
         if (d == 0 && etid == 0) *g.trig_count = 0;   // ordered before the finalisers by the ticket below
-        __threadfence();
         ptx::named_bar_sync(1, STEP_EW * 32);      // also: the transpose buffers go back to the tile epilogues
         if (etid == 0) {
+          __threadfence();       // ONE thread fences at gpu scope: cumulative over the stores the barrier ordered before it
           atomicAdd(g.ticket, 1u);
           TRACE(26);
         }
@@ -721,6 +771,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
       const int row_w0 = rt * TC_ROWS + q * 32;            // first row of this warp
       const int ucol = nt * 64 + sub * STEP_UPW;           // first hidden unit of this warp within the layer
       if (f.type == PH_LSTM) {
+        if (chained) {
+          if (lane == 0) poll_ge(f.prev_done + rg * f.n_tiles + nt, 2, item);
+          __syncwarp();
+        }
         float4 cin[STEP_CPR];
 #pragma unroll
         for (int i = 0; i < STEP_CPR; ++i) {
@@ -820,6 +874,24 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
             }
           }
         }
+        // c' rows of this warp -> global (whole row segments).  Stream-ordered launches store them after the publish
+        // below (nobody in the launch reads them, and the publish is on the critical path of the launch's own
+        // consumers); inside a chain the NEXT launch's tile (rg, nt) reads them as soon as it has seen this tile's
+        // counter, so there they go first (+0.45 us per tile; a second "rows stored" counter bumped later -- behind
+        // the next CTA barrier, or on the next publish's fence -- measured slower: the next launch does wait for it).
+        auto store_c = [&]() {
+#pragma unroll
+          for (int i = 0; i < STEP_CPR; ++i) {
+            const int rr = i * RPI + er;
+            const float4 t = *reinterpret_cast<const float4*>(eb + rr * STEP_RB + ((ec ^ swz(rr)) << 4));
+            if (row_w0 + rr < p.rows)
+              reinterpret_cast<float4*>(f.c_out + (size_t)(row_w0 + rr) * p.H + ucol)[ec] = t;
+          }
+        };
+        if (in_chain) {
+          __syncwarp();
+          store_c();
+        }
         // publish the k-block: consumers (next layer / head) only read the packed image
         // (CTA barrier, then ONE thread fences at gpu scope and bumps the counter: the release is cumulative over
         // the stores the barrier ordered before it -- no per-thread membar)
@@ -842,13 +914,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
           else ptx::mbar_arrive_remote(tempty_bar(acc), 0);
         }
-#pragma unroll
-        for (int i = 0; i < STEP_CPR; ++i) {      // c' tile -> global, whole row segments
-          const int rr = i * RPI + er;
-          const float4 t = *reinterpret_cast<const float4*>(eb + rr * STEP_RB + ((ec ^ swz(rr)) << 4));
-          if (row_w0 + rr < p.rows)
-            reinterpret_cast<float4*>(f.c_out + (size_t)(row_w0 + rr) * p.H + ucol)[ec] = t;
-        }
+        if (!in_chain) store_c();
         __syncwarp();
 #pragma unroll
         for (int c8 = 0; c8 < STEP_CPR; ++c8)
@@ -925,10 +991,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
   // Decision step of the fused trigger: rollouts that fired keep their LSTM state (generate_frames.py:289-295).
   // Rare, so it is handled after the fact: once every CTA has finished its items, the state rows of the fired
   // rollouts are copied back from the input block (fp32 h, c and the packed h images), spread over all CTAs.
+  int n_fired = 0;
   if (p.restore) {
-    // (s_misc[0] = fired count, written by the auxiliary lane once the mask was published; the barrier of the
-    //  teardown above ordered it before us.  done_ctr is only waited for when something fired.)
-    const int n_fired = s_misc[0];
+    n_fired = s_misc[0];
     if (threadIdx.x == 0) TRACE(39);
     if (n_fired > 0) {
       if (threadIdx.x == 0) {
@@ -995,14 +1060,14 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
           const float4* src = reinterpret_cast<const float4*>((kind == 0 ? f.h_in : f.c_in) + (size_t)r0 * p.H);
           float4* dst = reinterpret_cast<float4*>((kind == 0 ? f.h_out : f.c_out) + (size_t)r0 * p.H);
           const int n4 = (r1 - r0) * p.H / 4;
-          for (int i = threadIdx.x; i < n4; i += STEP_THREADS) dst[i] = __ldg(src + i);
+          for (int i = threadIdx.x; i < n4; i += STEP_THREADS) dst[i] = __ldcg(src + i);
         } else {
           const int per_row = hk * 2 * 8;       // 16-byte units per row: k-blocks x (hi, lo) x 8 chunks
           for (int i = threadIdx.x; i < (r1 - r0) * per_row; i += STEP_THREADS) {
             const int r = r0 + i / per_row, e = i % per_row;
             const int kb = e >> 4, part = (e >> 3) & 1, qd = e & 7;
             const size_t off = ((size_t)((r / TC_ROWS) * hk + kb) * 2 + part) * TC_A_IMG + (size_t)(r % TC_ROWS) * 128 + qd * 16;
-            *reinterpret_cast<uint4*>(f.hp_out + off) = __ldg(reinterpret_cast<const uint4*>(f.a_rec + off));
+            *reinterpret_cast<uint4*>(f.hp_out + off) = __ldcg(reinterpret_cast<const uint4*>(f.a_rec + off));
           }
         }
       }
@@ -1015,10 +1080,19 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) lstm_step_kernel(const __grid
     TRACE(42);
     int* exit_ctr = p.flag_words + p.n_flag_words;
     __threadfence();
+    if (n_fired > 0) atomicAdd(p.fin_ctr, 1);       // a chained successor waits for the restored state rows
     if (atomicAdd(exit_ctr, 1) == (int)gridDim.x - 1) {
-      for (int i = 0; i < p.n_flag_words; ++i) p.flag_words[i] = 0;
+      if (p.self_reset)
+        for (int i = 0; i < p.n_flag_words; ++i) p.flag_words[i] = 0;
+      if (p.reset_set != nullptr)
+        for (int i = 0; i < p.n_flag_words; ++i) p.reset_set[i] = 0;
       __threadfence();
       *exit_ctr = 0;
+      if (in_chain) {
+        poll_ge(p.retired, p.chain_idx, -8);        // retire in order (the previous launch's last CTA may be behind us)
+        __threadfence();
+        atomicExch(p.retired, p.chain_idx + 1);     // launches up to chain_idx are gone, their counters are reset
+      }
     }
   }
 }
@@ -1033,6 +1107,64 @@ static bool use_fused() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
+}
+
+static bool use_chain() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVG_STEP_CHAIN");   // developer switch: 0 = every launch waits for the previous grid
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// dvg_lstm_chain_begin / _end: see include/dvg_b200.h
+#ifdef DVG_TRACE
+static unsigned long long* g_chain_tbuf = nullptr;     // [16 launches][256 CTAs][TRACE_SLOTS]
+static int g_chain_traced = 0;
+static void chain_trace_dump(cudaStream_t stream) {
+  if (!g_chain_tbuf || g_chain_traced < 2) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return;
+  cudaStreamSynchronize(stream);
+  const char* which = getenv("DVG_TC_TRACE_LAUNCH");
+  const int want = which ? atoi(which) : 6;
+  const size_t per = 256 * (size_t)TRACE_SLOTS;
+  std::vector<unsigned long long> hbuf(16 * per);
+  cudaMemcpy(hbuf.data(), g_chain_tbuf, 16 * per * 8, cudaMemcpyDeviceToHost);
+  unsigned long long t0 = ~0ull;
+  for (int b = 0; b < 256; ++b) { const unsigned long long v = hbuf[(size_t)(want % 16) * per + (size_t)b * TRACE_SLOTS]; if (v && v < t0) t0 = v; }
+  for (int li = want; li < want + 3 && li < g_chain_traced; ++li) {
+    fprintf(stderr, "STEP TRACE chain launch %d\n", li);
+    for (int b = 0; b < 256; ++b) {
+      const unsigned long long* r = &hbuf[(size_t)(li % 16) * per + (size_t)b * TRACE_SLOTS];
+      if (!r[0]) continue;
+      fprintf(stderr, "cta %3d:", b);
+      for (int i = 0; i < 128; ++i) {
+        const unsigned long long v = r[i];
+        if (v >= 1000000ull && v < 2000000ull) fprintf(stderr, " #%lld", (long long)(v - 1000000ull));
+        else fprintf(stderr, " %lld", v ? (long long)v - (long long)t0 : -1ll);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
+  g_chain_traced = 0;
+}
+#endif
+
+int lstm_step_chain(dvg_lstm_s* h, bool begin, cudaStream_t stream) {
+#ifdef DVG_TRACE
+  if (!begin) chain_trace_dump(stream);
+#endif
+  if (h->fused_flags != nullptr && h->chain_dirty) {
+    DVG_CUDA(cudaMemsetAsync(h->fused_flags, 0, sizeof(int) * (3 * h->flag_set_words + 8), stream));
+    h->chain_dirty = false;
+  }
+  h->chain_on = begin;
+  h->chain_ok = false;
+  h->chain_idx = 0;
+  return DVG_OK;
 }
 
 size_t lstm_step_flag_words(const dvg_lstm_s* h, int rows) {
@@ -1238,25 +1370,67 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   const size_t lpk = (size_t)RT * hk * 2 * TC_A_IMG;
   StepArgs a{};
   a.rows = rows; a.row_tiles = RT; a.groups = groups; a.nsplit = nsplit; a.H = H; a.L = L; a.G = G; a.ldx = ldx;
-  a.kbx = kbx; a.x = x; a.xp = h->tc_xp;
+  a.kbx = kbx; a.x = x;
   a.hold = hold; a.rows_per_flag = rows_per_flag > 0 ? rows_per_flag : 1;
   const int fstride = (int)align_up((size_t)groups * hk, 32);
-  int* flags = h->fused_flags;
+  int pairs = h->sm_count / 2;
+  {
+    const int total_items = L * groups * hk + groups;
+    if (pairs > total_items) pairs = total_items;
+  }
+  // Chain bookkeeping (see StepArgs::chained).  Inside dvg_lstm_chain_begin/_end the launches rotate through three
+  // counter sets and two x slabs / fired lists; a launch is CHAINED to its predecessor (skips the grid dependency
+  // wait) when that was a step launch of the same shape on the same stream whose output state is our input state.
+  // Needs the grid to cover the machine: only then is "my SM is free" proof that the launch before the previous one
+  // has drained completely.
+  const bool in_chain = h->chain_on && use_chain() && pairs * 2 == h->sm_count && hold == nullptr;
+  if (h->chain_on && !in_chain && h->chain_dirty) {       // not chainable: drop back to the self-resetting protocol
+    DVG_CUDA(cudaMemsetAsync(h->fused_flags, 0, sizeof(int) * (3 * h->flag_set_words + 8), stream));
+    h->chain_dirty = false; h->chain_ok = false; h->chain_idx = 0;
+  }
+  const int ci = in_chain ? h->chain_idx : 0;
+  const int set = ci % 3, pset = (ci + 2) % 3, par = ci & 1;
+  const bool chained = in_chain && h->chain_ok && h->chain_out == (const void*)h_in && h->chain_rows == rows &&
+                       h->chain_nsplit == nsplit && h->chain_stream == stream && h->chain_gp == (const void*)g;
+  if (getenv("DVG_STEP_CHAIN_VERBOSE"))
+    fprintf(stderr, "dvg_b200: step launch rows=%d in_chain=%d idx=%d chained=%d (ok=%d out==in %d rows %d nsplit %d stream %d gp %d) trig=%d\n",
+            rows, (int)in_chain, ci, (int)chained, (int)h->chain_ok, (int)(h->chain_out == (const void*)h_in),
+            (int)(h->chain_rows == rows), (int)(h->chain_nsplit == nsplit), (int)(h->chain_stream == stream),
+            (int)(h->chain_gp == (const void*)g), (int)(trig != nullptr));
+  int* flags = h->fused_flags + (size_t)set * h->flag_set_words;
+  int* pflags = h->fused_flags + (size_t)pset * h->flag_set_words;
+  a.xp = h->tc_xp + (size_t)par * h->xp_stride;
   a.flag_words = flags;
-  a.n_flag_words = L * fstride + 4;
+  a.n_flag_words = L * fstride + 7;
   a.mask_ready = flags + (size_t)L * fstride;
   a.done_ctr = a.mask_ready + 1;
   a.rs_next = a.mask_ready + 2;
   a.rs_done = a.mask_ready + 3;
+  a.fin_ctr = a.mask_ready + 4;
+  a.dim_ctr = a.mask_ready + 5;
+  a.fin_claim = a.mask_ready + 6;
   a.rs_buf = h->rs_buf;
+  a.chained = chained ? 1 : 0;
+  a.in_chain = in_chain ? 1 : 0;
+  a.chain_idx = ci;
+  a.retired = h->fused_flags + 3 * h->flag_set_words;
+  a.self_reset = in_chain ? 0 : 1;
+  a.reset_set = in_chain ? pflags : nullptr;
+  a.rot = in_chain ? (ci * 13) % pairs : 0;
+  a.prev_trig = chained ? h->chain_prev_trig : 0;
+  a.prev_restore = chained ? h->chain_prev_restore : 0;
+  a.prev_mask_ready = pflags + (size_t)L * fstride;
+  a.prev_fin = a.prev_mask_ready + 4;
+  a.prev_trig_count = g != nullptr ? g->trig_count + (par ^ 1) : nullptr;
   if (trig != nullptr) {
     StepTrig& t = a.trig;
     t.enabled = 1; t.S = trig->S; t.D = g->dims.num_dims; t.mp = g->mp; t.W = trig->W; t.warmup = trig->warmup;
     t.factor = trig->factor; t.stat_rows = trig->stat_rows;
     t.z = g->z; t.linv = g->linv; t.lqt = g->lqt; t.hyp = g->hyp;
     t.var_rows = g->var_rows; t.ticket = g->ticket; t.window = trig->window; t.count = trig->count;
-    t.value = trig->value; t.thr = trig->thr; t.mask = trig->mask; t.trig_list = g->trig_list;
-    t.trig_count = g->trig_count;
+    t.value = trig->value; t.thr = trig->thr; t.mask = trig->mask;
+    t.trig_list = g->trig_list + (size_t)par * g->var_rows_cap;
+    t.trig_count = g->trig_count + par;
     t.rs_eps = trig->warmup ? nullptr : trig->rs_eps; t.alpha = g->alpha; t.rs_out = y; t.rs_ldo = ldy;
     t.n_points = rows / trig->S;
     a.restore = trig->warmup ? 0 : 1;
@@ -1270,11 +1444,12 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
     f.type = PH_LSTM; f.n_tile = 256; f.n_tiles = hk; f.item_begin = item;
     f.kb_in = l == 0 ? kbx : hk; f.kb_rec = hk;
     f.in_ksteps = l == 0 ? ceil_div(G, 16) : hk * 4;
-    f.a_in = l == 0 ? h->tc_xp : hp_out + (l - 1) * lpk;
+    f.a_in = l == 0 ? a.xp : hp_out + (l - 1) * lpk;
     f.a_rec = hp_in + l * lpk;
     f.w = pl.w; f.bias = pl.bias;
     f.wait_flags = l == 0 ? nullptr : flags + (size_t)(l - 1) * fstride;
     f.done_flags = flags + (size_t)l * fstride;
+    f.prev_done = pflags + (size_t)l * fstride;
     f.c_in = c_in + l * lsz; f.h_in = h_in + l * lsz; f.h_out = h_out + l * lsz; f.c_out = c_out + l * lsz;
     f.hp_out = hp_out + l * lpk;
     item += groups * hk; ++np;
@@ -1302,11 +1477,10 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   const size_t smem = stages * stage_bytes + tail;
   static bool configured = false;
   if (!configured) {
-    DVG_CUDA(cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DVG_CUDA(cudaFuncSetAttribute(lstm_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DVG_CUDA(cudaFuncSetAttribute(lstm_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  int pairs = h->sm_count / 2;
-  if (pairs > a.total_items) pairs = a.total_items;
   if (h->sched_dev != nullptr && h->sched_rows == rows && h->sched_pairs == pairs) {
     a.sched = h->sched_dev; a.sched_len = h->sched_len;
   }
@@ -1328,7 +1502,14 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   cfg.attrs = attr; cfg.numAttrs = use_pdl ? 2 : 1;
 #ifdef DVG_TRACE
   static unsigned long long* tbuf = nullptr;
-  const bool tr = getenv("DVG_TC_TRACE") != nullptr;
+  bool tr = getenv("DVG_TC_TRACE") != nullptr;
+  if (tr && in_chain) {          // chained launches: one slab per launch, nothing between the launches, dumped at chain end
+    const size_t per = 256 * (size_t)TRACE_SLOTS;
+    if (!g_chain_tbuf) cudaMalloc(&g_chain_tbuf, 16 * per * 8);
+    if (ci == 0) cudaMemsetAsync(g_chain_tbuf, 0, 16 * per * 8, stream);
+    if (ci < 16) { a.trace = g_chain_tbuf + (size_t)ci * per; g_chain_traced = ci + 1; }
+    tr = false;
+  }
   if (tr) {
     if (!tbuf) cudaMalloc(&tbuf, 256 * TRACE_SLOTS * 8);
     cudaMemsetAsync(tbuf, 0, 256 * TRACE_SLOTS * 8, stream);
@@ -1336,8 +1517,15 @@ int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const flo
   }
 #endif
   h->prof_mark(stream);
-  DVG_CUDA(cudaLaunchKernelEx(&cfg, lstm_step_kernel, (const StepArgs)a));
+  if (in_chain) DVG_CUDA(cudaLaunchKernelEx(&cfg, lstm_step_kernel<true>, (const StepArgs)a));
+  else DVG_CUDA(cudaLaunchKernelEx(&cfg, lstm_step_kernel<false>, (const StepArgs)a));
   h->prof_mark(stream);
+  if (in_chain) {
+    h->chain_idx = ci + 1; h->chain_ok = true; h->chain_dirty = true;
+    h->chain_out = (const void*)h_out; h->chain_rows = rows; h->chain_nsplit = nsplit; h->chain_stream = stream;
+    h->chain_gp = (const void*)g;
+    h->chain_prev_trig = trig != nullptr ? 1 : 0; h->chain_prev_restore = a.restore;
+  }
 #ifdef DVG_TRACE
   if (tr) {
     static int n_dump = 0;

@@ -15,6 +15,7 @@ Instances restored by unpickling never ran ``__init__``; every runtime attribute
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -179,6 +180,19 @@ class _FastLstmBase(nn.Module):
         if v not in _capi.VARIANTS:
             raise ValueError(f"unknown variant {v!r}; choose from {sorted(_capi.VARIANTS)}")
         self.__dict__["_dvg_variant"] = v
+
+    @contextlib.contextmanager
+    def chained(self):
+        """Steps issued inside this block may overlap on the GPU (dvg_lstm_chain_begin / _end, include/dvg_b200.h).  Only for
+        loops whose inputs all exist before the block and that enqueue nothing else on the stream between the steps --
+        e.g. the teacher-forced context frames of a sequence; NOT the generation loop with the decoder / encoder between
+        the steps.  Results are identical."""
+        rt = self._runtime()
+        _capi.check(rt.lib.dvg_lstm_chain_begin(rt.handle, _capi.stream_ptr()), "dvg_lstm_chain_begin")
+        try:
+            yield self
+        finally:
+            _capi.check(rt.lib.dvg_lstm_chain_end(rt.handle, _capi.stream_ptr()), "dvg_lstm_chain_end")
 
     def init_hidden(self):
         """models/lstm.py:58-63 -- L tuples of zeros [batch_size, H] (views of one zeroed state block

@@ -24,6 +24,7 @@ correlates exactly those B points, generate_frames.py:171).
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -172,17 +173,31 @@ class RolloutEngine:
         if resample:
             self.resample(h, eps, out, masked=False)
 
+    @contextlib.contextmanager
+    def chained(self):
+        """Steps issued inside this block may overlap on the GPU (dvg_lstm_chain_begin / _end, include/dvg_b200.h: step
+        t+1 starts on the SMs step t no longer needs).  The caller's promise: all step inputs other than the recurrent
+        state exist before the block, nothing else is enqueued on the stream inside it, and each step writes its own
+        output rows.  Results are identical to the unchained sequence."""
+        _capi.check(self.lib.dvg_lstm_chain_begin(self.lrt.handle, _capi.stream_ptr()), "dvg_lstm_chain_begin")
+        try:
+            yield self
+        finally:
+            _capi.check(self.lib.dvg_lstm_chain_end(self.lrt.handle, _capi.stream_ptr()), "dvg_lstm_chain_end")
+
     # ---- latent-space rollout (hot path only; the bench / CUDA-graph unit) -------------------------
     def latent_rollout(self, lat, eps, out, warmup_steps: Optional[int] = None, masks=None, values=None):
         """Run T trigger-mode steps on pre-computed encoder latents ``lat`` [T, S*B, G] (stand-ins for
         encoder(x_in)), writing decoder inputs to ``out`` [T, S*B, G].  ``eps`` [T, S, D, B].
         Optional ``masks`` [T, S] u8 / ``values`` [T, S] record the trigger trace (device copies)."""
         W = self.cfg.window if warmup_steps is None else warmup_steps
-        for t in range(lat.shape[0]):
-            # the trigger writes its mask / value straight into row t of the trace buffers (no copy kernels)
-            self._mask_buf = masks[t] if masks is not None else self.mask
-            self._value_buf = values[t] if values is not None else self.value
-            self.step_trigger_mode(lat[t], eps[t], out[t], warmup=t < W)
+        # every input of every step exists up front and nothing else is enqueued between the steps: chain the launches
+        with self.chained():
+            for t in range(lat.shape[0]):
+                # the trigger writes its mask / value straight into row t of the trace buffers (no copy kernels)
+                self._mask_buf = masks[t] if masks is not None else self.mask
+                self._value_buf = values[t] if values is not None else self.value
+                self.step_trigger_mode(lat[t], eps[t], out[t], warmup=t < W)
         self._mask_buf, self._value_buf = self.mask, self.value
 
     def capture_latent_rollout(self, lat, eps, out, masks=None, values=None, post=None):

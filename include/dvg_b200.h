@@ -97,6 +97,20 @@ DVG_API int dvg_lstm_destroy(dvg_lstm_t h);
  * graph capture).  Synchronous (cudaMalloc). */
 DVG_API int dvg_lstm_reserve(dvg_lstm_t h, int rows);
 
+/* Chained steps.  Between dvg_lstm_chain_begin and dvg_lstm_chain_end, consecutive dvg_lstm_step / dvg_rollout_step
+ * calls on this handle whose state_in is the previous call's state_out (same rows, variant, stream) may OVERLAP on the
+ * GPU: the next time step's first tiles start on the SMs that ran out of work while the previous step's last tiles
+ * finish (the launches synchronise per tile through device counters instead of waiting for the whole previous grid).
+ * The caller promises that between the two calls it enqueues NOTHING on the stream: every input of every step of the
+ * chain other than the recurrent state (x, eps, rs_eps, stat_rows) is complete before dvg_lstm_chain_begin, and the
+ * outputs (y, value, thr, mask) are only read by work enqueued after dvg_lstm_chain_end.  This is the situation of
+ * a latent-space rollout whose inputs are known up front (teacher-forced context frames, the bench's hot-path loop);
+ * with the encoder / decoder between the steps (generate_frames.py:266-298) do not open a chain.  Results are
+ * identical with and without a chain.  Steps that cannot be chained (hold mask, small grids, the stand-alone resample
+ * fallback) silently take the ordinary stream-ordered path.  Both calls may be captured in a CUDA graph. */
+DVG_API int dvg_lstm_chain_begin(dvg_lstm_t h, dvg_stream_t stream);
+DVG_API int dvg_lstm_chain_end(dvg_lstm_t h, dvg_stream_t stream);
+
 /* Recurrent state block (replaces the list of (h,c) tuples of models/lstm.py:58-63).  One block holds
  *   h  fp32 [L][rows][H]   at byte offset 0
  *   c  fp32 [L][rows][H]   at byte offset L*rows*H*4

@@ -1,0 +1,7 @@
+timeout 600 python -m pytest tests/test_gpu_rollout.py -x -q -m gpu 2>&1 | tail -5
+export DVG_LIB_NOREBUILD=1
+fmt='import sys,json; d=json.loads(sys.stdin.read()); print(d["tag"], [round(s["us_per_step_best"],2) for s in d["steps"]])'
+for t in v5 v7 v5 v7; do
+DVG_LIB_TAG=$t timeout 200 python scripts/step_time.py --tag $t 2>&1 | tail -1 | python -c "$fmt"
+done
+DVG_LIB_TAG=v7 DVG_STEP_CHAIN=0 timeout 200 python scripts/step_time.py --tag v7nochain 2>&1 | tail -1 | python -c "$fmt"

@@ -61,19 +61,22 @@ def timed(fn, label):
 
 
 def plain():
-    for t in range(N):
-        eng.step_manual_mode(lat[t], None, out[t], resample=False)
+    with eng.chained():
+        for t in range(N):
+            eng.step_manual_mode(lat[t], None, out[t], resample=False)
 
 
 def warm():
     eng.reset()
-    for t in range(N):
-        eng.step_trigger_mode(lat[t], eps[t], out[t], warmup=True)
+    with eng.chained():
+        for t in range(N):
+            eng.step_trigger_mode(lat[t], eps[t], out[t], warmup=True)
 
 
 def decide():
-    for t in range(N):
-        eng.step_trigger_mode(lat[t], eps[t], out[t], warmup=False)
+    with eng.chained():
+        for t in range(N):
+            eng.step_trigger_mode(lat[t], eps[t], out[t], warmup=False)
 
 
 res = {"workload": a.workload, "variant": a.variant, "rows": R, "tag": a.tag, "steps": []}

@@ -285,3 +285,27 @@ def test_unfused_tensor_core_path_matches_fused(monkeypatch):
             outs.append(small(y))
         y_small = torch.cat(outs)
     assert relerr(y_big, y_small) < 2e-5
+
+
+def test_dropin_chained_steps_equal_stream_ordered_steps():
+    """``lstm.chained()`` (dvg_lstm_chain_begin/_end under the drop-in class): 5000 rows so that the grid covers the
+    machine and the launches really overlap; outputs and final state bit-identical to the plain loop."""
+    rows, T = 5000, 14
+    sd = lstm_ref.random_lstm_state_dict(90, 90, 256, 2, seed=21)
+    m = make_lstm(sd, rows=rows, variant="bf16x3")
+    xs = torch.tanh(torch.randn(T, rows, 90, generator=torch.Generator().manual_seed(2))).cuda()
+    res = []
+    with torch.no_grad():
+        for chained in (False, True, True):
+            m.hidden = m.init_hidden()
+            if chained:
+                with m.chained():
+                    ys = [m(xs[t]) for t in range(T)]
+            else:
+                ys = [m(xs[t]) for t in range(T)]
+            torch.cuda.synchronize()
+            res.append((torch.stack(ys), [(h.clone(), c.clone()) for h, c in m.hidden]))
+    for ys, hid in res[1:]:
+        assert torch.equal(ys, res[0][0])
+        for (h1, c1), (h0, c0) in zip(hid, res[0][1]):
+            assert torch.equal(h1, h0) and torch.equal(c1, c0)

@@ -2,6 +2,8 @@
 (oracle/rollout_ref.py restating generate_frames.py:138-178, :249-300, train.py:262-289), on the same inputs,
 weights and injected noise.  Encoder/decoder are small latent-space stand-ins so the test isolates the hot
 path (the conv nets stay on the stock PyTorch path and are not under test)."""
+import contextlib
+
 import numpy as np
 import pytest
 import torch
@@ -165,6 +167,83 @@ def test_small_batch_trigger_rollout_vs_oracle(B, S):
     checked, fired = check_latent_rollout(sd, gp_sd, lik_sd, lat, eps, out.cpu(), masks.cpu(), values.cpu(), B, W,
                                           stat_col=min(3, B - 1))
     assert checked >= 10 and fired >= 1, (checked, fired, sorted(jumps), masks.cpu().nonzero().tolist())
+
+
+def _sm_count():
+    return torch.cuda.get_device_properties(0).multi_processor_count
+
+
+@pytest.mark.parametrize("kind", ["trigger", "plain"])
+def test_chained_steps_equal_stream_ordered_steps(kind):
+    """dvg_lstm_chain_begin/_end (include/dvg_b200.h): consecutive step launches overlap on the GPU, synchronised per tile
+    through the previous launch's counters instead of the grid boundary.  Needs a grid that covers the machine, so the
+    bench's own shape: 5000 rows (B = 50 x S = 100), with crafted fires -- a fired step makes the next launch wait for the
+    restored state rows.  The chained sequence (eager and replayed from a CUDA graph) must equal the stream-ordered one
+    bit for bit: outputs of every step, masks, and the final state; two rollouts are also replayed on the CPU oracle."""
+    from dvg_b200.rollout import RolloutConfig, RolloutEngine
+    from util import check_latent_rollout, crafted_trigger_case
+    B, S, T, W = 50, 100, 24, 12
+    sd = lstm_ref.random_lstm_state_dict(G, G, H, L, seed=31)
+    gp_sd, lik_sd, lat, eps, jumps = crafted_trigger_case(G, M, B, S, T, W, seed=9, n_jumps=10)
+    fp = make_lstm(sd, rows=B, variant="bf16x3")
+    gp, lik = make_gp(gp_sd, lik_sd)
+    eng = RolloutEngine(fp, gp, lik, RolloutConfig(n_points=B, n_rollouts=S, window=W, variant="bf16x3"))
+    lat_d, eps_d = lat.cuda(), eps.cuda()
+
+    def run(chained, out, masks, vals=None):
+        eng.reset()
+        ctx = eng.chained() if chained else contextlib.nullcontext()
+        with ctx:
+            for t in range(T):
+                if kind == "plain":
+                    eng.step_manual_mode(lat_d[t], None, out[t], resample=False)
+                else:
+                    eng._mask_buf = masks[t]
+                    eng._value_buf = vals[t] if vals is not None else eng.value
+                    eng.step_trigger_mode(lat_d[t], eps_d[t], out[t], warmup=t < W)
+        eng._mask_buf, eng._value_buf = eng.mask, eng.value
+        return [(h.clone(), c.clone()) for h, c in eng.hidden()]
+
+    outs, masks, states = [], [], []
+    vals = torch.zeros(T, S, device="cuda")
+    with torch.no_grad():
+        for chained in (False, True, True):
+            o = torch.empty(T, S * B, G, device="cuda")
+            m = torch.zeros(T, S, dtype=torch.uint8, device="cuda")
+            states.append(run(chained, o, m, vals))
+            torch.cuda.synchronize()
+            outs.append(o)
+            masks.append(m)
+        # the same chain replayed from a CUDA graph (the launches then run back to back without host gaps)
+        og = torch.empty(T, S * B, G, device="cuda")
+        mg = torch.zeros(T, S, dtype=torch.uint8, device="cuda")
+        run(True, og, mg)                      # warm outside capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(g):
+                sg = run(True, og, mg)
+        for _ in range(3):
+            og.zero_()
+            g.replay()
+        torch.cuda.synchronize()
+    for o, m, stt in zip(outs[1:] + [og], masks[1:] + [mg], states[1:] + [sg]):
+        assert torch.equal(m, masks[0])
+        assert torch.equal(o, outs[0])
+        for (h1, c1), (h0, c0) in zip(stt, states[0]):
+            assert torch.equal(h1, h0) and torch.equal(c1, c0)
+    if kind == "trigger":
+        fired = int(masks[0].sum())
+        assert fired >= 5, (fired, sorted(jumps))
+        # oracle replay of two rollouts that fired and one that did not
+        rolls = sorted({s_ for _, s_ in jumps})[:2] + [next(s_ for s_ in range(S) if all(s_ != j for _, j in jumps))]
+        for s_ in rolls:
+            rows = slice(s_ * B, (s_ + 1) * B)
+            checked, f = check_latent_rollout(sd, gp_sd, lik_sd, lat[:, rows], eps[:, s_:s_ + 1], outs[1][:, rows].cpu(),
+                                              masks[1][:, s_:s_ + 1].cpu(), vals[:, s_:s_ + 1].cpu(), B, W)
+            assert checked >= 5
 
 
 def test_cuda_graph_latent_rollout_equals_eager():
