@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; echo "kth rc=$?"
+python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; echo "kth rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2>/dev/null; echo "ref rc=$?"
 python bench.py --variant bf16 --steps 20 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/r02_bench_bf16.json 2>/dev/null
 for wl in bair_s32 ucf_s100 smmnist_b16; do
