@@ -93,8 +93,11 @@ DVG_API int dvg_lstm_refresh(dvg_lstm_t h,
                      dvg_stream_t stream);
 DVG_API int dvg_lstm_destroy(dvg_lstm_t h);
 
-/* Grow the handle's scratch so that steps with up to `rows` rows never allocate (call before CUDA
- * graph capture).  Synchronous (cudaMalloc). */
+/* Grow the handle's scratch so that steps with up to `rows` rows never allocate.  Synchronous (cudaMalloc,
+ * cudaDeviceSynchronize).  Contract: reserve the largest row count BEFORE capturing step calls into a CUDA graph (a step
+ * that would have to grow the scratch during capture fails with DVG_ERR_STATE); scratch that an already captured graph
+ * may reference is retired, not freed, when the handle grows later, and released by dvg_lstm_destroy.  A handle is used
+ * from one stream at a time: the dependency counters and scratch of the step kernels are per handle. */
 DVG_API int dvg_lstm_reserve(dvg_lstm_t h, int rows);
 
 /* Chained steps.  Between dvg_lstm_chain_begin and dvg_lstm_chain_end, consecutive dvg_lstm_step / dvg_rollout_step
@@ -134,9 +137,11 @@ DVG_API int dvg_lstm_step(dvg_lstm_t h, int variant, int rows,
                   const uint8_t* hold, int rows_per_flag,
                   dvg_stream_t stream);
 
-/* Measurement aid (bench.py roofline): dvg_lstm_step with CUDA events recorded on `stream` between the
- * kernel launches; synchronises the stream and returns the device time of each launch in kernel_ms
- * (slots: 0 x-pack [tensor-core variants], 1 embed, 2..L+1 the LSTM layers, L+2 head). */
+/* Measurement aid: dvg_lstm_step with CUDA events recorded on `stream` around the kernel launches; synchronises the
+ * stream and returns the device time of each launch in kernel_ms.  The tensor-core variants issue ONE launch per step
+ * (slot 0 = the whole step: lstm_step_kernel, or lstm_small_kernel for <= 64 rows at hidden size 256); the DVG_FP32
+ * variant and the DVG_TC_FUSED=0 developer path issue one launch per GEMM (slots: 0 x-pack, 1 embed, 2..L+1 the LSTM
+ * layers, L+2 head). */
 DVG_API int dvg_lstm_profile(dvg_lstm_t h, int variant, int rows,
                      const float* x, int ldx,
                      const void* state_in, void* state_out,
@@ -178,14 +183,16 @@ DVG_API int dvg_gp_refresh(dvg_gp_t h,
                    const float* raw_noise, dvg_stream_t stream);
 DVG_API int dvg_gp_destroy(dvg_gp_t h);
 
-/* Inducing sets larger than DVG_GP_MAX_INDUCING_ONDEVICE (BASELINE configs[4] sweeps M = 128 .. 4096): the per-dimension
- * fp64 factorisation no longer fits shared memory, so the eval-mode constants are computed by the caller (the Python
- * host side does it with torch.linalg in fp64, the library the reference itself relies on through gpytorch) and
- * loaded here; dvg_gp_predict / dvg_gp_trigger then run tiled FP32 GEMM kernels over them (gp_big.cu).  Device
+/* Large inducing sets (BASELINE configs[4] sweeps M = 128 .. 4096).  dvg_gp_prepare factorises on the device in shared
+ * memory and accepts up to DVG_GP_MAX_INDUCING_ONDEVICE points; beyond that -- and, for speed, from 65 points on, which
+ * is what the Python host side does -- the eval-mode constants are computed by the caller (torch.linalg in fp64, the
+ * library the reference itself relies on through gpytorch) and loaded here; dvg_gp_predict / dvg_gp_trigger then run
+ * the tensor-core tiled kernels over them (gp_tc.cu: tcgen05, bf16x3 split operands, fp32 accumulation; DVG_GP_TC=0
+ * selects the FP32 FFMA tiles of gp_big.cu) and dvg_gp_rsample the large-M resample kernel (n_points <= 128).  Device
  * pointers, fp32, dense row-major:
  *   inducing [D,M], linv [D,M,M] = chol(K_ZZ + jitter I)^-1 (lower), lq [D,M,M] = tril(chol_variational_covar),
  *   beta [D,M] = linv (m_q - c), hyp [D,4] = (lengthscale, outputscale, mean constant, noise incl. lower bound).
- * dvg_gp_rsample is not available on such a handle yet. */
+ */
 #define DVG_GP_MAX_INDUCING_ONDEVICE 128
 DVG_API int dvg_gp_prepare_factors(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* linv,
                            const float* lq, const float* beta, const float* hyp, dvg_stream_t stream);
@@ -215,9 +222,8 @@ DVG_API int dvg_gp_trigger(dvg_gp_t h, int n_rollouts, const float* x, int ldx, 
  * Sigma_y the full [N,N] predictive covariance of rollout s in dimension d.
  *   x [S*N, D] (ldx), eps [S, D, N] standard normal, out [S*N, D] (ldo) -- rows of unmasked rollouts are
  *   left untouched, so `out` can be the LSTM output buffer (on-device select).  N <= 128 (the batch size of one
- *   rollout; the reference correlates exactly the N points of one call).
- *   When `mask` is the very buffer the last dvg_gp_trigger call on this handle wrote (same pointer, same
- *   n_rollouts), the compacted list of fired rollouts produced by that call is used instead of re-reading it. */
+ *   rollout; the reference correlates exactly the N points of one call).  The mask is read on the device at run time
+ *   (no host copy, no stale state between calls). */
 DVG_API int dvg_gp_rsample(dvg_gp_t h, int n_rollouts, int n_points, const float* x, int ldx,
                    const float* eps, const uint8_t* mask, float* out, int ldo, dvg_stream_t stream);
 
