@@ -15,7 +15,10 @@ synthetic tensors resident in HBM.  frames = S * B * n_future per rollout.
 JSON keys beyond the base contract:
 ``roofline``          dominant kernel = ``lstm_step_kernel`` (ONE persistent tcgen05 launch per time step: x-pack, all
                       LSTM layers, head, GP trigger, restore/resample of fired rollouts); launch duration = CUDA-graph
-                      replay of the T step launches of one rollout / T, CUDA events on the launching stream
+                      replay of the T step launches of one rollout / T, CUDA events on the launching stream.  The launches of
+                      a rollout are CHAINED (``config.step_launches``): all inputs of the latent-space rollout exist up front,
+                      so step t+1 starts on the SMs step t no longer needs; ``lstm_step_ms_stream_ordered`` is the same
+                      sequence without the chain (what a caller with the conv nets between the steps gets)
 ``cpu_baseline``      the reference's CPU path on the host cores, bounded sample (LSTM stage: the reference's own
                       ``models/lstm.py`` when present under baseline/_ref or /root/reference, GP stage: oracle port)
 ``e2e``               the same metric through the public Python API with pinned HOST buffers, H2D + D2H in the timed region
@@ -540,6 +543,10 @@ def run_ours(args):
                        "rows_per_gpu": R, "time_steps": T, "frames_per_step": frames_per_step,
                        "row_steps_per_s": world * R * T / (ms_per_step * 1e-3),
                        "variant": args.variant, "cuda_graph": True,
+                       "step_launches": "chained where the grid covers the GPU (include/dvg_b200.h dvg_lstm_chain_begin: every "
+                                        "input of the latent-space rollout exists up front, so consecutive step launches overlap; "
+                                        "results identical); stream-ordered figures: roofline.lstm_step_ms_stream_ordered, "
+                                        "stock_torch_b200.ours_us_per_step_stream_ordered; DVG_STEP_CHAIN=0 disables",
                        "l2": "inputs+outputs per rollout = %.0f MB > 126 MB L2" % ((lat.numel() + out.numel()) * 4 / 1e6),
                        "triggered_rollout_steps": n_trig, "scope": "hot path only; encoder/decoder convs excluded",
                        "multi_gpu": None if world == 1 else {
@@ -588,7 +595,7 @@ def measure_roofline(eng, w, R, lat, args):
     T = lat.shape[0]
     out = torch.empty(T, R, w["G"], device=lat.device)     # every step writes its own rows, as in the rollout
 
-    def step_time(engine, reps):
+    def step_time(engine, reps, chained=True):
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -601,7 +608,7 @@ def measure_roofline(eng, w, R, lat, args):
         torch.cuda.synchronize()
         with torch.cuda.graph(g):
             engine.reset()
-            with engine.chained():      # the rollout's launch sequence (RolloutEngine.latent_rollout)
+            with (engine.chained() if chained else contextlib.nullcontext()):   # chained: the rollout's launch sequence
                 for t in range(T):
                     engine.step_trigger_mode(lat[t], None, out[t], warmup=t < w["window"], resample=False)
         engine.cur = 0 if T % 2 == 0 else 1
@@ -618,6 +625,7 @@ def measure_roofline(eng, w, R, lat, args):
 
     reps = max(3, min(args.steps, 20))
     step_ms = step_time(eng, reps)
+    step_ms_so = step_time(eng, 3, chained=False)     # what a caller with other work between the steps gets
     other = {}
     for name in ("bf16x3", "bf16", "fp32"):
         if name == args.variant:
@@ -643,8 +651,10 @@ def measure_roofline(eng, w, R, lat, args):
             "hbm_frac_of_state_io": (b_row * R / (step_ms * 1e-3) / 1e9) / hbm,
             "note": "achieved counts ALGORITHMIC flops of the reference step, 2*(G*H + L*2H*4H + H*G) per row; the bf16x3 "
                     "variant issues 3 tcgen05.mma per algorithmic MMA (tensor_issue_frac = tensor-pipe work actually "
-                    "issued / peak); launch duration = CUDA-graph replay of the T step launches / T",
-            "kernel_ms": {"lstm_step_kernel": step_ms}, "lstm_step_ms": step_ms,
+                    "issued / peak); launch duration = CUDA-graph replay of the T step launches of one rollout / T "
+                    "(the launches are chained as in the timed rollout, i.e. they overlap: this is the step's cost in the "
+                    "sequence; lstm_step_ms_stream_ordered = the same without the chain)",
+            "kernel_ms": {"lstm_step_kernel": step_ms}, "lstm_step_ms": step_ms, "lstm_step_ms_stream_ordered": step_ms_so,
             "other_variants_lstm_step_ms": other}
 
 
