@@ -1,6 +1,7 @@
 """GPU parity of the LSTM hot path (through the C ABI) against the golden vectors of the real reference
 and against the CPU oracle.  Tolerances: fp32 / bf16x3 variants <= 1e-4 relative (north_star fp32 bar),
 bf16 variant <= 2e-2."""
+import contextlib
 import glob
 import os
 
@@ -287,22 +288,30 @@ def test_unfused_tensor_core_path_matches_fused(monkeypatch):
     assert relerr(y_big, y_small) < 2e-5
 
 
-def test_dropin_chained_steps_equal_stream_ordered_steps():
-    """``lstm.chained()`` (dvg_lstm_chain_begin/_end under the drop-in class): 5000 rows so that the grid covers the
-    machine and the launches really overlap; outputs and final state bit-identical to the plain loop."""
-    rows, T = 5000, 14
-    sd = lstm_ref.random_lstm_state_dict(90, 90, 256, 2, seed=21)
-    m = make_lstm(sd, rows=rows, variant="bf16x3")
-    xs = torch.tanh(torch.randn(T, rows, 90, generator=torch.Generator().manual_seed(2))).cuda()
+@pytest.mark.parametrize("kind,variant", [("lstm", "bf16x3"), ("lstm", "bf16"), ("gaussian", "bf16x3")])
+def test_dropin_chained_steps_equal_stream_ordered_steps(kind, variant):
+    """``module.chained()`` (dvg_lstm_chain_begin/_end under the drop-in classes): 5000 rows so that the grid covers the
+    machine and the launches really overlap; outputs and final state bit-identical to the plain loop, for both
+    tensor-core variants and for gaussian_lstm (the PH_GAUSS head with its injected eps)."""
+    rows, T, Z = 5000, 14, 10
+    gauss = kind == "gaussian"
+    sd = lstm_ref.random_lstm_state_dict(90, Z if gauss else 90, 256, 2, seed=21, gaussian=gauss)
+    m = make_lstm(sd, gaussian=gauss, rows=rows, variant=variant)
+    g = torch.Generator().manual_seed(2)
+    xs = torch.tanh(torch.randn(T, rows, 90, generator=g)).cuda()
+    eps = torch.randn(T, rows, Z, generator=g).cuda()
+
+    def step(t):
+        if gauss:
+            return torch.cat(m(xs[t], eps=eps[t]), 1)
+        return m(xs[t])
+
     res = []
     with torch.no_grad():
         for chained in (False, True, True):
             m.hidden = m.init_hidden()
-            if chained:
-                with m.chained():
-                    ys = [m(xs[t]) for t in range(T)]
-            else:
-                ys = [m(xs[t]) for t in range(T)]
+            with (m.chained() if chained else contextlib.nullcontext()):
+                ys = [step(t) for t in range(T)]
             torch.cuda.synchronize()
             res.append((torch.stack(ys), [(h.clone(), c.clone()) for h, c in m.hidden]))
     for ys, hid in res[1:]:
