@@ -22,7 +22,7 @@ EXPORTS = [
     "dvg_lstm_chain_begin", "dvg_lstm_chain_end",
     "dvg_lstm_state_bytes", "dvg_lstm_state_packed_offset", "dvg_lstm_state_repack",
     "dvg_lstm_step", "dvg_lstm_profile", "dvg_gauss_lstm_step",
-    "dvg_gp_prepare", "dvg_gp_refresh", "dvg_gp_prepare_factors", "dvg_gp_refresh_factors", "dvg_gp_destroy", "dvg_gp_predict", "dvg_gp_trigger",
+    "dvg_gp_prepare", "dvg_gp_refresh", "dvg_gp_prepare_factors", "dvg_gp_refresh_factors", "dvg_gp_factorize", "dvg_gp_factorize_workspace", "dvg_gp_destroy", "dvg_gp_predict", "dvg_gp_trigger",
     "dvg_gp_rsample", "dvg_gp_export", "dvg_rollout_step", "dvg_eval_seq_finn", "dvg_eval_seq", "dvg_rollout_score",
     "dvg_moving_mnist_draws", "dvg_moving_mnist",
 ]
@@ -88,6 +88,9 @@ def load():
     lib.dvg_gp_destroy.argtypes = [P]
     lib.dvg_gp_predict.argtypes = [P, c_int, P, c_int, P, P, c_int, P, c_int, P]
     lib.dvg_gp_prepare_factors.argtypes = [POINTER(c_void_p), POINTER(GpDims), P, P, P, P, P, P]
+    lib.dvg_gp_factorize.argtypes = [POINTER(GpDims), P, P, P, P, P, P, P, P, c_size_t, P]
+    lib.dvg_gp_factorize_workspace.restype = c_size_t
+    lib.dvg_gp_factorize_workspace.argtypes = [POINTER(GpDims), c_int]
     lib.dvg_gp_refresh_factors.argtypes = [P, P, P, P, P, P, P]
     lib.dvg_gp_trigger.argtypes = [P, c_int, P, c_int, P, P, c_int, P, c_int, c_float, P, P, P, P]
     lib.dvg_gp_rsample.argtypes = [P, c_int, c_int, P, c_int, P, P, P, c_int, P]
@@ -101,7 +104,7 @@ def load():
     lib.dvg_moving_mnist.argtypes = [c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
-        if name not in ("dvg_last_error", "dvg_lstm_state_bytes", "dvg_lstm_state_packed_offset"):
+        if name not in ("dvg_last_error", "dvg_lstm_state_bytes", "dvg_lstm_state_packed_offset", "dvg_gp_factorize_workspace"):
             fn.restype = c_int
     _lib = lib
     return lib

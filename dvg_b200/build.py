@@ -13,7 +13,7 @@ CSRC = os.path.join(PKG, "csrc")
 # trace build and the product build can travel to the GPU box side by side.
 LIB_DIR = os.path.join(PKG, "_lib" + ("_" + os.environ["DVG_LIB_TAG"] if os.environ.get("DVG_LIB_TAG") else ""))
 LIB = os.path.join(LIB_DIR, "libdvg_b200.so")
-SOURCES = ["capi.cu", "lstm_fp32.cu", "lstm_tc.cu", "lstm_step.cu", "lstm_small.cu", "gp.cu", "gp_big.cu", "gp_tc.cu", "rollout.cu", "moving_mnist.cu"]
+SOURCES = ["capi.cu", "lstm_fp32.cu", "lstm_tc.cu", "lstm_step.cu", "lstm_small.cu", "gp.cu", "gp_big.cu", "gp_tc.cu", "gp_factor.cu", "rollout.cu", "moving_mnist.cu"]
 HEADERS = ["common.cuh", "internal.cuh", "ptx.cuh", "gp_trigger.cuh", "gp_rsample.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "dvg_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

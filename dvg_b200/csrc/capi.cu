@@ -308,6 +308,21 @@ int dvg_gp_refresh(dvg_gp_t h, const float* inducing, const float* var_mean, con
                            (cudaStream_t)stream);
 }
 
+size_t dvg_gp_factorize_workspace(const dvg_gp_dims* dims, int batch_dims) {
+  if (!dims || dims->num_inducing <= 0) return 0;
+  return gp_factorize_workspace(dims->num_inducing, batch_dims);
+}
+
+int dvg_gp_factorize(const dvg_gp_dims* dims, const float* inducing, const float* var_mean, const float* mean_const,
+                     const float* raw_outputscale, const float* raw_lengthscale, float* linv, float* beta,
+                     void* workspace, size_t workspace_bytes, dvg_stream_t stream) {
+  DVG_REQUIRE(dims && inducing && var_mean && mean_const && raw_outputscale && raw_lengthscale && linv && beta,
+              "null argument");
+  DVG_REQUIRE(dims->num_dims > 0 && dims->num_inducing > 0 && dims->num_inducing <= 16384, "bad sizes");
+  return gp_factorize(dims->num_dims, dims->num_inducing, (double)dims->jitter, inducing, var_mean, mean_const,
+                      raw_outputscale, raw_lengthscale, linv, beta, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int dvg_gp_prepare_factors(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* linv,
                            const float* lq, const float* beta, const float* hyp, dvg_stream_t stream) {
   DVG_REQUIRE(out && dims && inducing && linv && lq && beta && hyp, "null argument");

@@ -152,6 +152,11 @@ int lstm_small_launch(dvg_lstm_s* h, int nsplit, int rows, const float* x, int l
 bool lstm_step_usable(const dvg_lstm_s* h, int rows);
 size_t lstm_step_flag_words(const dvg_lstm_s* h, int rows);
 int lstm_step_chain(dvg_lstm_s* h, bool begin, cudaStream_t stream);
+// gp_factor.cu: blocked fp64 Cholesky + triangular inverse of K_ZZ + jitter I (large inducing sets, once per weight load)
+size_t gp_factorize_workspace(int M, int batch);
+int gp_factorize(int D, int M, double jitter, const float* inducing, const float* var_mean, const float* mean_const,
+                 const float* raw_os, const float* raw_ls, float* linv, float* beta, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream);
 size_t lstm_step_xp_bytes(const dvg_lstm_s* h, int rows);
 int lstm_step_build_schedule(dvg_lstm_s* h, int rows);
 int lstm_step_launch(dvg_lstm_s* h, dvg_gp_s* g, int nsplit, int rows, const float* x, int ldx, const float* h_in,

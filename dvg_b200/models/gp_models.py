@@ -26,6 +26,8 @@ training steps (train.py:146-248) run against these classes (mi
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -111,10 +113,11 @@ class _GpRuntime:
         self.sig = self.signature(layer, likelihood)
 
     def _refresh_factors(self, ts, raw_noise, lb, D, M):
-        """Large inducing sets (M > 128, BASELINE configs[4]): the eval-mode constants are factorised here in fp64
-        with torch.linalg (cuSOLVER -- the library gpytorch itself calls for this step, once per weight load) and
-        handed to the C ABI, whose tiled kernels own the per-call work.  Same math as gp_prepare_kernel:
-        L = chol(K_ZZ + jitter I), Linv = L^-1, beta = Linv (m_q - c), L_q = tril(chol_variational_covar)."""
+        """Large inducing sets (M > 64, BASELINE configs[4]): the eval-mode constants -- L = chol(K_ZZ + jitter I),
+        Linv = L^-1, beta = Linv (m_q - c), L_q = tril(chol_variational_covar) -- are computed once per weight load and
+        handed to the C ABI, whose tiled kernels own the per-call work.  The factorisation itself is the library's
+        blocked fp64 kernels (``dvg_gp_factorize``, csrc/gp_factor.cu); ``DVG_GP_NATIVE_FACTOR=0`` takes torch.linalg
+        (cuSOLVER, what gpytorch itself calls for this step) instead -- tests/test_gpu_gp.py holds one against the other."""
         Z, m_q, chol_var, c_raw, raw_os, raw_ls = [t.detach() for t in ts[:6]]
         f64 = torch.float64
         sp = nn.functional.softplus
@@ -126,18 +129,30 @@ class _GpRuntime:
         z = Z.reshape(D, M)
         linv = torch.empty(D, M, M, dtype=torch.float32, device=z.device)
         beta = torch.empty(D, M, dtype=torch.float32, device=z.device)
-        eye = torch.eye(M, dtype=f64, device=z.device)
-        step = max(1, min(D, (1 << 28) // (M * M)))           # bound the fp64 temporaries (~2 GB per operand)
-        for d0 in range(0, D, step):
-            d1 = min(D, d0 + step)
-            zz = z[d0:d1].to(f64)
-            t = (zz[:, :, None] - zz[:, None, :]) / ell[d0:d1, None, None]
-            K = s[d0:d1, None, None] * torch.exp(-0.5 * t * t) + JITTER * eye
-            L = torch.linalg.cholesky(K)
-            Li = torch.linalg.solve_triangular(L, eye.expand(d1 - d0, M, M), upper=False)
-            linv[d0:d1] = Li.float()
-            beta[d0:d1] = torch.einsum("dij,dj->di", Li, m_q[d0:d1].to(f64) - c[d0:d1, None]).float()
-            del t, K, L, Li
+        if os.environ.get("DVG_GP_NATIVE_FACTOR", "1") != "0":
+            dims = _capi.GpDims(D, M, JITTER, lb)
+            keep = [z.float().contiguous(), m_q.float().contiguous(), c_raw.float().reshape(D).contiguous(),
+                    raw_os.float().reshape(D).contiguous(), raw_ls.float().reshape(D).contiguous()]
+            batch = max(1, min(D, (1 << 28) // (M * M)))           # ~2 GB per fp64 operand at most
+            ws = torch.empty(self.lib.dvg_gp_factorize_workspace(_capi.ctypes.byref(dims), batch), dtype=torch.uint8,
+                             device=z.device)
+            _capi.check(self.lib.dvg_gp_factorize(_capi.ctypes.byref(dims), *[_capi.ptr(t) for t in keep], _capi.ptr(linv),
+                                                  _capi.ptr(beta), _capi.ptr(ws), ws.numel(), _capi.stream_ptr()),
+                        "dvg_gp_factorize")
+            del ws
+        else:
+            eye = torch.eye(M, dtype=f64, device=z.device)
+            step = max(1, min(D, (1 << 28) // (M * M)))           # bound the fp64 temporaries (~2 GB per operand)
+            for d0 in range(0, D, step):
+                d1 = min(D, d0 + step)
+                zz = z[d0:d1].to(f64)
+                t = (zz[:, :, None] - zz[:, None, :]) / ell[d0:d1, None, None]
+                K = s[d0:d1, None, None] * torch.exp(-0.5 * t * t) + JITTER * eye
+                L = torch.linalg.cholesky(K)
+                Li = torch.linalg.solve_triangular(L, eye.expand(d1 - d0, M, M), upper=False)
+                linv[d0:d1] = Li.float()
+                beta[d0:d1] = torch.einsum("dij,dj->di", Li, m_q[d0:d1].to(f64) - c[d0:d1, None]).float()
+                del t, K, L, Li
         lq = torch.tril(chol_var).float().contiguous()
         zc = z.float().contiguous()
         args = [_capi.ptr(zc), _capi.ptr(linv), _capi.ptr(lq), _capi.ptr(beta), _capi.ptr(hyp)]

@@ -194,6 +194,18 @@ DVG_API int dvg_gp_destroy(dvg_gp_t h);
  *   beta [D,M] = linv (m_q - c), hyp [D,4] = (lengthscale, outputscale, mean constant, noise incl. lower bound).
  */
 #define DVG_GP_MAX_INDUCING_ONDEVICE 128
+/* The factorisation for such a handle, natively: blocked fp64 Cholesky of K_ZZ + jitter I (64 x 64 blocks: diagonal block
+ * factorised and inverted in shared memory, panel and trailing update by tiled FP64 GEMMs) and the triangular inverse by
+ * block rows, batched over the latent dims -- what the reference recomputes with cuSOLVER potrf on every call.
+ * Inputs as for dvg_gp_prepare (fp32 device pointers; dims->jitter is used); writes linv [D,M,M] and beta [D,M] (fp32)
+ * for dvg_gp_prepare_factors.  The caller owns the workspace (device memory, 256-byte aligned):
+ * dvg_gp_factorize_workspace(dims, b) bytes let b latent dims be processed per pass (b = 1 is the minimum; two
+ * Mp x Mp fp64 matrices per dim).  Synchronises the stream once at the end to read the "not positive definite" flag
+ * (DVG_ERR_ARG). */
+DVG_API size_t dvg_gp_factorize_workspace(const dvg_gp_dims* dims, int batch_dims);
+DVG_API int dvg_gp_factorize(const dvg_gp_dims* dims, const float* inducing, const float* var_mean, const float* mean_const,
+                     const float* raw_outputscale, const float* raw_lengthscale, float* linv, float* beta,
+                     void* workspace, size_t workspace_bytes, dvg_stream_t stream);
 DVG_API int dvg_gp_prepare_factors(dvg_gp_t* out, const dvg_gp_dims* dims, const float* inducing, const float* linv,
                            const float* lq, const float* beta, const float* hyp, dvg_stream_t stream);
 DVG_API int dvg_gp_refresh_factors(dvg_gp_t h, const float* inducing, const float* linv, const float* lq,

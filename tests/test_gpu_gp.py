@@ -310,6 +310,44 @@ def test_trigger_large_inducing_set():
     assert n_checked > 200
 
 
+@pytest.mark.parametrize("D,M", [(3, 65), (4, 200), (2, 512), (2, 1000)])
+def test_native_factorisation_matches_torch_linalg(D, M):
+    """dvg_gp_factorize (blocked fp64 Cholesky + triangular inverse, csrc/gp_factor.cu) against torch.linalg in fp64 on
+    the same parameters: Linv [D,M,M] and beta [D,M] as the C ABI receives them (fp32), plus L Linv = I in fp64."""
+    from dvg_b200 import _capi
+    gp_sd, lik_sd = gp_ref.random_gp_state_dicts(D, M, seed=5 + M, trained_like=True, smooth_mean=True)
+    dev = torch.device("cuda")
+    z = gp_sd[gp_ref.K_INDUCING].reshape(D, M).float().to(dev).contiguous()
+    m_q = gp_sd[gp_ref.K_VMEAN].float().to(dev).contiguous()
+    c = gp_sd["mean_module.constant"].reshape(D).float().to(dev).contiguous()
+    raw_os = gp_sd["covar_module.raw_outputscale"].reshape(D).float().to(dev).contiguous()
+    raw_ls = gp_sd["covar_module.base_kernel.raw_lengthscale"].reshape(D).float().to(dev).contiguous()
+    linv = torch.full((D, M, M), float("nan"), device=dev)
+    beta = torch.full((D, M), float("nan"), device=dev)
+    lib = _capi.load()
+    dims = _capi.GpDims(D, M, 1e-3, 1e-4)
+    ws = torch.empty(lib.dvg_gp_factorize_workspace(_capi.ctypes.byref(dims), 2), dtype=torch.uint8, device=dev)   # 2 dims per pass
+    _capi.check(lib.dvg_gp_factorize(_capi.ctypes.byref(dims), _capi.ptr(z), _capi.ptr(m_q), _capi.ptr(c), _capi.ptr(raw_os),
+                                     _capi.ptr(raw_ls), _capi.ptr(linv), _capi.ptr(beta), _capi.ptr(ws), ws.numel(),
+                                     _capi.stream_ptr()), "dvg_gp_factorize")
+    torch.cuda.synchronize()
+    f64 = torch.float64
+    sp = torch.nn.functional.softplus
+    ell, sc = sp(raw_ls.to(f64)), sp(raw_os.to(f64))
+    t = (z.to(f64)[:, :, None] - z.to(f64)[:, None, :]) / ell[:, None, None]
+    K = sc[:, None, None] * torch.exp(-0.5 * t * t) + 1e-3 * torch.eye(M, dtype=f64, device=dev)
+    L = torch.linalg.cholesky(K)
+    Li = torch.linalg.solve_triangular(L, torch.eye(M, dtype=f64, device=dev).expand(D, M, M), upper=False)
+    want_beta = torch.einsum("dij,dj->di", Li, m_q.to(f64) - c.to(f64)[:, None])
+    assert torch.isfinite(linv).all() and torch.isfinite(beta).all()
+    assert torch.all(torch.triu(linv, 1) == 0)
+    scale = Li.abs().amax(dim=(1, 2), keepdim=True)
+    assert ((linv.to(f64) - Li).abs() / scale).max().item() < 2e-7          # fp32 rounding of an fp64 result
+    assert relerr(beta, want_beta) < 2e-6
+    resid = (L @ linv.to(f64) - torch.eye(M, dtype=f64, device=dev)).abs().max().item()
+    assert resid < 1e-3, resid                                               # cond(L) x fp32 rounding
+
+
 def test_fp32_tiled_kernels_cross_check():
     """The FP32 FFMA tiles of gp_big.cu (the path DVG_GP_TC=0 selects; the switch is read once per process) must hold
     the same bar as the tensor-core tiles: re-run the large-M predictive and trigger tests in a child with it set."""
