@@ -86,11 +86,12 @@ __global__ void __launch_bounds__(256) fz_diag_kernel(int Mp, int kb, int nb, do
 // (BT) or B [k x n].  m, n multiples of 64, k a multiple of 16.  Grid (n / 64, m / 64, batch), 256 threads, each thread a
 // 4 x 4 block of C.  lower_only: tiles strictly above the diagonal are skipped (C square, trailing update of the
 // Cholesky).  A CTA reads everything it needs of A and B before it writes C, so C may alias A's own tile row (the
-// in-place panel solve).
+// in-place panel solve).  tri_b (B [k x n], lower triangular in 64 x 64 blocks): the k blocks above output column block
+// x are zero and skipped -- half the work of the block-row inverse.
 template <bool BT>
 __global__ void __launch_bounds__(256) fz_gemm_kernel(int k, double alpha, const double* A, int lda, long long sa,
                                                       const double* B, int ldb, long long sb, double beta, double* C,
-                                                      int ldc, long long sc, int lower_only) {
+                                                      int ldc, long long sc, int lower_only, int tri_b) {
   if (lower_only && blockIdx.x > blockIdx.y) return;
   __shared__ double s_A[FZ_KC][FZ_NB + 4];      // [kk][row]
   __shared__ double s_B[FZ_KC][FZ_NB + 4];      // [kk][col]
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) fz_gemm_kernel(int k, double alpha, const
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = 0; k0 < k; k0 += FZ_KC) {
+  for (int k0 = tri_b ? (int)blockIdx.x * FZ_NB : 0; k0 < k; k0 += FZ_KC) {
     // A tile: 64 rows x 16 k  (1024 doubles, 4 per thread)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -248,11 +249,11 @@ int gp_factorize(int D, int M, double jitter, const float* inducing, const float
       // panel <- panel * (L_kk^-1)^T
       fz_gemm_kernel<true><<<dim3(1, rem, nbat), 256, 0, stream>>>(FZ_NB, 1.0, panel, Mp, (long long)mat,
                                                                  dinv + (size_t)kb * FZ_NB * FZ_NB, FZ_NB,
-                                                                 (long long)nb * FZ_NB * FZ_NB, 0.0, panel, Mp, (long long)mat, 0);
+                                                                 (long long)nb * FZ_NB * FZ_NB, 0.0, panel, Mp, (long long)mat, 0, 0);
       // trailing <- trailing - panel * panel^T   (lower tiles only)
       double* trail = A + (size_t)(kb + 1) * FZ_NB * Mp + (size_t)(kb + 1) * FZ_NB;
       fz_gemm_kernel<true><<<dim3(rem, rem, nbat), 256, 0, stream>>>(FZ_NB, -1.0, panel, Mp, (long long)mat, panel, Mp,
-                                                                   (long long)mat, 1.0, trail, Mp, (long long)mat, 1);
+                                                                   (long long)mat, 1.0, trail, Mp, (long long)mat, 1, 0);
     }
     if (fail(cudaGetLastError())) break;
     // ---- Linv = L^-1 by block rows ----
@@ -262,11 +263,11 @@ int gp_factorize(int D, int M, double jitter, const float* inducing, const float
       if (i == 0) continue;
       // T[64 x i*64] = L[i, 0..i) * Linv[0..i, 0..i)
       fz_gemm_kernel<false><<<dim3(i, 1, nbat), 256, 0, stream>>>(i * FZ_NB, 1.0, A + (size_t)i * FZ_NB * Mp, Mp, (long long)mat,
-                                                                X, Mp, (long long)mat, 0.0, T, Mp, (long long)FZ_NB * Mp, 0);
+                                                                X, Mp, (long long)mat, 0.0, T, Mp, (long long)FZ_NB * Mp, 0, 1);
       // Linv[i, 0..i) = -L_ii^-1 * T
       fz_gemm_kernel<false><<<dim3(i, 1, nbat), 256, 0, stream>>>(FZ_NB, -1.0, dinv + (size_t)i * FZ_NB * FZ_NB, FZ_NB,
                                                                 (long long)nb * FZ_NB * FZ_NB, T, Mp, (long long)FZ_NB * Mp,
-                                                                0.0, X + (size_t)i * FZ_NB * Mp, Mp, (long long)mat, 0);
+                                                                0.0, X + (size_t)i * FZ_NB * Mp, Mp, (long long)mat, 0, 0);
     }
     if (fail(cudaGetLastError())) break;
     fz_finish_kernel<<<dim3(M, nbat), 128, 0, stream>>>(M, Mp, d0, X, var_mean, mean_const, linv, beta);
