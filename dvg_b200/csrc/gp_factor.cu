@@ -4,7 +4,7 @@
 // hoisted.)  For M <= 128 gp_prepare_kernel does this in shared memory; this file is the blocked fp64 version for any M:
 // right-looking Cholesky on 64 x 64 blocks -- the diagonal block is factorised AND inverted in shared memory, the
 // panel below it is multiplied by that inverse, the trailing matrix is updated by a tiled fp64 GEMM -- followed by the
-// block-row recursion  Linv[i, 0..i) = -L_ii^-1 (L[i, 0..i) Linv[0..i, 0..i)).  All of it is FP64 FMA work (B200 has the
+// block-column recursion  Linv[j+1.., j] = -Linv[j+1.., j+1..] L[j+1.., j] L_jj^-1  (last block column first).  All of it is FP64 FMA work (B200 has the
 // full-rate FP64 pipe; tensor cores do not apply), batched over the latent dims that fit the workspace.
 #include <vector>
 
@@ -83,48 +83,54 @@ __global__ void __launch_bounds__(256) fz_diag_kernel(int Mp, int kb, int nb, do
 }
 
 // C[m x n] = alpha * A[m x k] * op(B) + beta * C, fp64, row-major with leading dimensions; op(B) = B^T with B [n x k]
-// (BT) or B [k x n].  m, n multiples of 64, k a multiple of 16.  Grid (n / 64, m / 64, batch), 256 threads, each thread a
-// 4 x 4 block of C.  lower_only: tiles strictly above the diagonal are skipped (C square, trailing update of the
-// Cholesky).  A CTA reads everything it needs of A and B before it writes C, so C may alias A's own tile row (the
-// in-place panel solve).  tri_b (B [k x n], lower triangular in 64 x 64 blocks): the k blocks above output column block
-// x are zero and skipped -- half the work of the block-row inverse.
+// (BT) or B [k x n].  n a multiple of 64, k a multiple of 16, m any multiple of 64 (rows past m are masked).  Grid
+// (n / 64, ceil(m / 128), batch), 256 threads, each thread 8 rows x 4 (strided) columns of a 128 x 64 tile of C: 12 shared-memory
+// loads per 32 FMAs (the 64 x 64 / 4 x 4 version was shared-memory bound at a third of the FP64 pipe).
+//   lower_only  C square: tiles entirely above the diagonal are skipped (trailing update of the Cholesky)
+//   tri_b       B [k x n] lower triangular in 64-blocks: the k blocks above output column block x are zero, skipped
+//   tri_a       A [m x k] lower triangular in 64-blocks: k stops at the last block row of the tile
+// A CTA reads everything it needs of A and B before it writes C, so C may alias A's own tile rows (the in-place panel
+// solve).
+constexpr int FZ_BM = 128;
 template <bool BT>
-__global__ void __launch_bounds__(256) fz_gemm_kernel(int k, double alpha, const double* A, int lda, long long sa,
+__global__ void __launch_bounds__(256) fz_gemm_kernel(int m, int k, double alpha, const double* A, int lda, long long sa,
                                                       const double* B, int ldb, long long sb, double beta, double* C,
-                                                      int ldc, long long sc, int lower_only, int tri_b) {
-  if (lower_only && blockIdx.x > blockIdx.y) return;
-  __shared__ double s_A[FZ_KC][FZ_NB + 4];      // [kk][row]
-  __shared__ double s_B[FZ_KC][FZ_NB + 4];      // [kk][col]
+                                                      int ldc, long long sc, int lower_only, int tri_b, int tri_a) {
+  if (lower_only && (int)blockIdx.x * FZ_NB > (int)blockIdx.y * FZ_BM + FZ_BM - 1) return;
+  __shared__ double s_A[FZ_KC][FZ_BM + 2];      // [kk][row]
+  __shared__ double s_B[FZ_KC][FZ_NB + 2];      // [kk][col]
   const int tid = threadIdx.x;
-  const int tr = tid / 16, tc = tid % 16;       // 16 x 16 threads, 4 x 4 outputs each
-  const double* Ab = A + (size_t)blockIdx.z * sa + (size_t)blockIdx.y * FZ_NB * lda;
+  const int tr = tid / 16, tc = tid % 16;       // 16 x 16 threads, 8 x 4 outputs each
+  const int row0 = (int)blockIdx.y * FZ_BM;
+  const double* Ab = A + (size_t)blockIdx.z * sa + (size_t)row0 * lda;
   const double* Bb = B + (size_t)blockIdx.z * sb;
-  double* Cb = C + (size_t)blockIdx.z * sc + (size_t)blockIdx.y * FZ_NB * ldc + (size_t)blockIdx.x * FZ_NB;
-  double acc[4][4];
+  double* Cb = C + (size_t)blockIdx.z * sc + (size_t)row0 * ldc + (size_t)blockIdx.x * FZ_NB;
+  double acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = tri_b ? (int)blockIdx.x * FZ_NB : 0; k0 < k; k0 += FZ_KC) {
-    // A tile: 64 rows x 16 k  (1024 doubles, 4 per thread)
+  const int k_begin = tri_b ? (int)blockIdx.x * FZ_NB : 0;
+  int k_end = k;
+  if (tri_a && row0 + FZ_BM < k_end) k_end = row0 + FZ_BM;
+  for (int k0 = k_begin; k0 < k_end; k0 += FZ_KC) {
+    // A tile: 128 rows x 16 k (2048 doubles, 8 per thread)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const int e = tid + q * 256;
       const int r = e / FZ_KC, kk = e % FZ_KC;
-      s_A[kk][r] = Ab[(size_t)r * lda + k0 + kk];
+      s_A[kk][r] = row0 + r < m ? Ab[(size_t)r * lda + k0 + kk] : 0.0;
     }
     if (BT) {
-      // B^T: B is [n x k]: rows = output columns
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 4; ++q) {             // B is [n x k]: rows = output columns
         const int e = tid + q * 256;
         const int c = e / FZ_KC, kk = e % FZ_KC;
         s_B[kk][c] = Bb[(size_t)(blockIdx.x * FZ_NB + c) * ldb + k0 + kk];
       }
     } else {
-      // B is [k x n]
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 4; ++q) {             // B is [k x n]
         const int e = tid + q * 256;
         const int kk = e / FZ_NB, c = e % FZ_NB;
         s_B[kk][c] = Bb[(size_t)(k0 + kk) * ldb + blockIdx.x * FZ_NB + c];
@@ -133,25 +139,27 @@ __global__ void __launch_bounds__(256) fz_gemm_kernel(int k, double alpha, const
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < FZ_KC; ++kk) {
-      double a[4], b[4];
+      double a[8], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = s_A[kk][tr * 4 + i];
+      for (int i = 0; i < 8; ++i) a[i] = s_A[kk][tr * 8 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = s_B[kk][tc * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = s_B[kk][tc + 16 * j];      // columns tc, tc + 16, ...: conflict-free, coalesced stores
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i) {
+    if (row0 + tr * 8 + i >= m) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      double* cp = Cb + (size_t)(tr * 4 + i) * ldc + tc * 4 + j;
+      double* cp = Cb + (size_t)(tr * 8 + i) * ldc + tc + 16 * j;
       *cp = beta == 0.0 ? alpha * acc[i][j] : alpha * acc[i][j] + beta * *cp;
     }
+  }
 }
 
 // Linv64[d][i-block][i-block] = dinv[d][i]
@@ -247,27 +255,34 @@ int gp_factorize(int D, int M, double jitter, const float* inducing, const float
       if (rem == 0) break;
       double* panel = A + (size_t)(kb + 1) * FZ_NB * Mp + (size_t)kb * FZ_NB;       // rows below the diagonal block
       // panel <- panel * (L_kk^-1)^T
-      fz_gemm_kernel<true><<<dim3(1, rem, nbat), 256, 0, stream>>>(FZ_NB, 1.0, panel, Mp, (long long)mat,
-                                                                 dinv + (size_t)kb * FZ_NB * FZ_NB, FZ_NB,
-                                                                 (long long)nb * FZ_NB * FZ_NB, 0.0, panel, Mp, (long long)mat, 0, 0);
-      // trailing <- trailing - panel * panel^T   (lower tiles only)
+      const int mrows = rem * FZ_NB, mt = (mrows + FZ_BM - 1) / FZ_BM;
+      fz_gemm_kernel<true><<<dim3(1, mt, nbat), 256, 0, stream>>>(mrows, FZ_NB, 1.0, panel, Mp, (long long)mat,
+                                                                dinv + (size_t)kb * FZ_NB * FZ_NB, FZ_NB,
+                                                                (long long)nb * FZ_NB * FZ_NB, 0.0, panel, Mp, (long long)mat, 0, 0, 0);
+      // trailing <- trailing - panel * panel^T   (tiles entirely above the diagonal skipped)
       double* trail = A + (size_t)(kb + 1) * FZ_NB * Mp + (size_t)(kb + 1) * FZ_NB;
-      fz_gemm_kernel<true><<<dim3(rem, rem, nbat), 256, 0, stream>>>(FZ_NB, -1.0, panel, Mp, (long long)mat, panel, Mp,
-                                                                   (long long)mat, 1.0, trail, Mp, (long long)mat, 1, 0);
+      fz_gemm_kernel<true><<<dim3(rem, mt, nbat), 256, 0, stream>>>(mrows, FZ_NB, -1.0, panel, Mp, (long long)mat, panel, Mp,
+                                                                  (long long)mat, 1.0, trail, Mp, (long long)mat, 1, 0, 0);
     }
     if (fail(cudaGetLastError())) break;
-    // ---- Linv = L^-1 by block rows ----
+    // ---- Linv = L^-1 by block columns, last to first:  X[j+1.., j] = -X[j+1.., j+1..] L[j+1.., j] L_jj^-1 ----
     if (fail(cudaMemsetAsync(X, 0, sizeof(double) * nbat * mat, stream))) break;
-    for (int i = 0; i < nb; ++i) {
-      fz_place_diag_kernel<<<nbat, 256, 0, stream>>>(Mp, nb, i, dinv, X);
-      if (i == 0) continue;
-      // T[64 x i*64] = L[i, 0..i) * Linv[0..i, 0..i)
-      fz_gemm_kernel<false><<<dim3(i, 1, nbat), 256, 0, stream>>>(i * FZ_NB, 1.0, A + (size_t)i * FZ_NB * Mp, Mp, (long long)mat,
-                                                                X, Mp, (long long)mat, 0.0, T, Mp, (long long)FZ_NB * Mp, 0, 1);
-      // Linv[i, 0..i) = -L_ii^-1 * T
-      fz_gemm_kernel<false><<<dim3(i, 1, nbat), 256, 0, stream>>>(FZ_NB, -1.0, dinv + (size_t)i * FZ_NB * FZ_NB, FZ_NB,
-                                                                (long long)nb * FZ_NB * FZ_NB, T, Mp, (long long)FZ_NB * Mp,
-                                                                0.0, X + (size_t)i * FZ_NB * Mp, Mp, (long long)mat, 0, 0);
+    for (int j = nb - 1; j >= 0; --j) {
+      fz_place_diag_kernel<<<nbat, 256, 0, stream>>>(Mp, nb, j, dinv, X);
+      const int rem = nb - 1 - j;
+      if (rem == 0) continue;
+      const int mrows = rem * FZ_NB, mt = (mrows + FZ_BM - 1) / FZ_BM;
+      const double* xt = X + (size_t)(j + 1) * FZ_NB * Mp + (size_t)(j + 1) * FZ_NB;     // trailing inverse (lower triangular)
+      const double* lp = A + (size_t)(j + 1) * FZ_NB * Mp + (size_t)j * FZ_NB;           // panel of L below block j
+      // T[m x 64] = X_trail * L_panel          (A operand triangular: k stops at the tile's last block row)
+      fz_gemm_kernel<false><<<dim3(1, mt, nbat), 256, 0, stream>>>(mrows, mrows, 1.0, xt, Mp, (long long)mat, lp, Mp,
+                                                                 (long long)mat, 0.0, T, FZ_NB, (long long)FZ_NB * Mp, 0, 0, 1);
+      // X[j+1.., j] = -T * L_jj^-1
+      fz_gemm_kernel<false><<<dim3(1, mt, nbat), 256, 0, stream>>>(mrows, FZ_NB, -1.0, T, FZ_NB, (long long)FZ_NB * Mp,
+                                                                 dinv + (size_t)j * FZ_NB * FZ_NB, FZ_NB,
+                                                                 (long long)nb * FZ_NB * FZ_NB, 0.0,
+                                                                 X + (size_t)(j + 1) * FZ_NB * Mp + (size_t)j * FZ_NB, Mp,
+                                                                 (long long)mat, 0, 0, 0);
     }
     if (fail(cudaGetLastError())) break;
     fz_finish_kernel<<<dim3(M, nbat), 128, 0, stream>>>(M, Mp, d0, X, var_mean, mean_const, linv, beta);
